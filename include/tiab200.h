@@ -1,0 +1,118 @@
+/* tiab200.h — C ABI of libtiab200.so: the B200-native per-patch hot path behind tiatoolbox's
+ * Python seams.
+ *
+ * The reference (tiatoolbox 2.0.1, pure Python) has no FFI of its own; the seams this ABI sits
+ * behind are duck-typed Python methods.  Each entry point names the reference
+ * interface it replaces (paths relative to /root/reference/tiatoolbox).  INTEGRATION.md shows the
+ * ctypes stub a tiatoolbox maintainer would add.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative TIAB_E_*;
+ * tiab_last_error() gives the message; pointers named *_dev are device pointers, *_host host
+ * pointers; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls taking
+ * only device pointers are asynchronous on `stream`; calls with host outputs synchronise it.
+ * A handle owns one device's workspaces and is not thread-safe: use one handle per thread.
+ */
+#ifndef TIAB200_H
+#define TIAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tiab_ctx* tiab_handle_t;
+
+enum {
+  TIAB_OK = 0,
+  TIAB_E_INVALID = -1,   /* bad argument */
+  TIAB_E_CUDA = -2,      /* CUDA runtime error (see tiab_last_error) */
+  TIAB_E_NOMEM = -3,
+  TIAB_E_UNSUPPORTED = -4
+};
+
+/* per-image status written by the stain calls */
+enum {
+  TIAB_STAIN_OK = 0,
+  TIAB_STAIN_EMPTY_TISSUE_MASK = 1, /* reference raises ValueError("Empty tissue mask computed.") utils/misc.py:286-288 */
+  TIAB_STAIN_DEGENERATE = 2,        /* <2 tissue pixels / singular stain matrix: reference yields NaN */
+  TIAB_STAIN_UNUSED_ATOM = 3        /* Vahadane: sklearn would re-sample a random atom (unspecified) */
+};
+
+enum { TIAB_STAIN_MACENKO = 0, TIAB_STAIN_VAHADANE = 1, TIAB_STAIN_RUIFROK = 2, TIAB_STAIN_CUSTOM = 3 };
+
+int tiab_create(int device, tiab_handle_t* out);
+void tiab_destroy(tiab_handle_t h);
+const char* tiab_last_error(tiab_handle_t h);
+/* "major.minor" of the ABI */
+const char* tiab_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stain normalisation  (tools/stainnorm.py:19-219, tools/stainextract.py:71-322,
+ * utils/misc.py:261-290,405-444, utils/transforms.py:209-256)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int method;                  /* TIAB_STAIN_* — which extractor (stainextract.py:71,104,141,230) */
+  int y_threshold;             /* tissue <=> cv2-Lab fixed-point Y <= y_threshold (1146 for luminosity 0.8; misc.py:281-283) */
+  double angular_percentile;   /* MacenkoExtractor(angular_percentile=99)  stainextract.py:168-175 */
+  double regularizer;          /* VahadaneExtractor(regularizer=0.1)       stainextract.py:259-279 */
+  double fixed_matrix[6];      /* RUIFROK / CUSTOM: the constant 2x3 source stain matrix (row-major) */
+} tiab_stain_params_t;
+
+/* StainNormalizer.fit  (stainnorm.py:68-87): stain matrix + 99th-percentile concentrations of the
+ * target.  target_dev: H*W*3 uint8 (HWC) on the device.  Outputs on the host; synchronises. */
+int tiab_stain_fit(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t* target_dev, int H, int W,
+                   double M_target_host[6], double maxC_target_host[2], int* status_host, void* stream);
+
+/* StainNormalizer.transform over a batch (stainnorm.py:89-113 applied per image).
+ * in_dev/out_dev: N*H*W*3 uint8 (NHWC), may alias.  Optional device outputs (NULL to skip):
+ *   M_src_dev   N*6 doubles  — extractor.get_stain_matrix per image (stainextract.py:177/281)
+ *   maxC_src_dev N*2 doubles — np.percentile(C, 99, axis=0) per image (stainnorm.py:103)
+ *   status_dev  N ints       — TIAB_STAIN_*; on a non-OK status the image is copied through unchanged
+ *   out_f32_dev N*H*W*3 float — the pre-quantisation value 255*exp(-C.M) clipped to [0,255]
+ * Asynchronous on `stream`. */
+int tiab_stain_transform_batch(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t* in_dev,
+                               uint8_t* out_dev, int N, int H, int W, const double M_target[6],
+                               const double maxC_target[2], double* M_src_dev, double* maxC_src_dev,
+                               int* status_dev, float* out_f32_dev, void* stream);
+
+/* Same with HOST buffers — the call the Python StainNormalizer.transform makes for numpy input:
+ * pinned staging, H2D, kernels, D2H, synchronise.  M_src_host (N*6), maxC_src_host (N*2) and
+ * status_host (N) are optional. */
+int tiab_stain_transform_host(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t* in_host,
+                              uint8_t* out_host, int N, int H, int W, const double M_target[6],
+                              const double maxC_target[2], double* M_src_host, double* maxC_src_host,
+                              int* status_host);
+
+/* fit with a HOST target buffer (the call StainNormalizer.fit makes for a numpy target). */
+int tiab_stain_fit_host(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t* target_host, int H, int W,
+                        double M_target_host[6], double maxC_target_host[2], int* status_host);
+
+/* get_luminosity_tissue_mask (utils/misc.py:261-290) for a batch: mask_dev N*H*W bytes (0/1). */
+int tiab_stain_tissue_mask(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t* in_dev, uint8_t* mask_dev,
+                           int N, int H, int W, int* status_dev, void* stream);
+
+/* StainNormalizer.get_concentrations (stainnorm.py:49-66) for N images with one stain matrix:
+ * conc_dev N*H*W*2 float32 = OD @ pinv(M). */
+int tiab_stain_concentrations(tiab_handle_t h, const uint8_t* in_dev, int N, int H, int W, const double M[6],
+                              float* conc_dev, void* stream);
+
+/* Force one of the two device paths (testing / benchmarking): 0 = auto, 1 = fused one-CTA-per-patch
+ * kernel (requires H*W*3 <= 196608 and H*W % 16 == 0), 2 = multi-pass general path. */
+int tiab_stain_set_path(tiab_handle_t h, int path);
+/* number of kernel launches issued by the last stain call on this handle */
+int tiab_last_launch_count(tiab_handle_t h);
+
+/* Host-side scalar pieces exported for the CPU unit tests (no GPU needed): the same
+ * __host__ __device__ code the kernels' finalise steps run. */
+int tiab_dbg_percentile_u8(const unsigned* hist256, double q, double* out);
+int tiab_dbg_contrast_lut(const unsigned* hist256, unsigned n, uint8_t lut_out[256]);
+int tiab_dbg_eigh3(const double cov[9], double evals[3], double evecs[9]);
+int tiab_dbg_lasso2(const double gram[4], const double c[2], double reg, double n, double out[2]);
+int tiab_dbg_macenko_from_angles(const double evec[6], double phi_min, double phi_max, double M_out[6]);
+int tiab_dbg_tables(unsigned tabg[256], float od[256]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIAB200_H */

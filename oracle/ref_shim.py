@@ -1,0 +1,139 @@
+"""Load the UNMODIFIED reference sources from /root/reference through stub modules.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Works only in the build
+container (``/root/reference`` does not exist on the GPU box).  Used by
+``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/`` and by the
+``-m "not gpu"`` tests that pin the numpy/C restatements against the real reference.
+
+Recipe: ``tiatoolbox.tools.stainnorm`` cannot be imported normally here
+because ``tiatoolbox/tools/__init__.py`` pulls in umap/skimage/... which are absent.  We
+register bare namespace packages for ``tiatoolbox.utils`` / ``tiatoolbox.tools`` /
+``tiatoolbox.models[.architecture]`` (only ``__path__``), synthesise
+``tiatoolbox.utils.misc`` from the *verbatim text* of the handful of functions the hot
+path uses (AST-extracted from ``utils/misc.py``), and then let importlib load
+``stainnorm.py``, ``stainextract.py``, ``utils/transforms.py``, ``hovernet.py``,
+``unet.py``, ``vanilla.py`` unmodified.
+
+The only restated third-party function is ``skimage.exposure.rescale_intensity``
+(scikit-image is not installed); the restatement is pinned by the reference's own
+golden vector ``tests/test_utils.py:882-911``.
+"""
+from __future__ import annotations
+
+import ast
+import importlib
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+
+REF_ROOT = Path("/root/reference")
+REF_PKG = REF_ROOT / "tiatoolbox"
+
+
+def available() -> bool:
+    return (REF_PKG / "tools" / "stainnorm.py").exists()
+
+
+class _Exposure:
+    """Restatement of skimage.exposure.rescale_intensity for (uint8 image, float in_range,
+    float out_range) — the only way the reference calls it (utils/misc.py:439-443)."""
+
+    @staticmethod
+    def rescale_intensity(image, in_range, out_range):
+        imin, imax = float(in_range[0]), float(in_range[1])
+        omin, omax = float(out_range[0]), float(out_range[1])
+        image = np.clip(image.astype(np.float64), imin, imax)
+        if imin != imax:
+            image = (image - imin) / (imax - imin)
+            return image * (omax - omin) + omin
+        return np.clip(image, omin, omax)
+
+
+def _stub(name: str, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_MISC_WANTED = [
+    "contrast_enhancer",
+    "get_luminosity_tissue_mask",
+    "load_stain_matrix",
+    "split_path_name_ext",
+    "get_bounding_box",
+    "parse_cv2_interpolaton",
+    "select_cv2_interpolation",
+]
+
+_loaded = {}
+
+
+def _base_packages():
+    """Register tiatoolbox + bare namespace sub-packages (skipping their __init__)."""
+    if "base" in _loaded:
+        return
+    if str(REF_ROOT) not in sys.path:
+        sys.path.insert(0, str(REF_ROOT))
+    import tiatoolbox  # noqa: F401  (top-level import is light: yaml + logging)
+
+    for sub in ("utils", "tools", "models"):
+        m = _stub(f"tiatoolbox.{sub}")
+        m.__path__ = [str(REF_PKG / sub)]
+    m = _stub("tiatoolbox.models.architecture")
+    m.__path__ = [str(REF_PKG / "models" / "architecture")]
+    importlib.import_module("tiatoolbox.utils.exceptions")  # dependency-free
+    _loaded["base"] = True
+
+
+def _extract_misc():
+    import cv2
+    import pandas as pd
+
+    _base_packages()
+    from tiatoolbox.utils.exceptions import FileNotSupportedError
+
+    src = (REF_PKG / "utils" / "misc.py").read_text()
+    fns = [
+        ast.get_source_segment(src, n)
+        for n in ast.parse(src).body
+        if isinstance(n, ast.FunctionDef) and n.name in _MISC_WANTED
+    ]
+    ns = {
+        "np": np,
+        "cv2": cv2,
+        "pd": pd,
+        "Path": Path,
+        "exposure": _Exposure,
+        "FileNotSupportedError": FileNotSupportedError,
+    }
+    exec("from __future__ import annotations\n" + "\n\n".join(fns), ns)  # noqa: S102
+    return {k: ns[k] for k in _MISC_WANTED}
+
+
+def load_stain():
+    """Return the reference's ``tiatoolbox.tools.stainnorm`` module (unmodified source)."""
+    if "stain" in _loaded:
+        return _loaded["stain"]
+    if not available():
+        raise RuntimeError("reference not present at /root/reference")
+    misc = _extract_misc()
+    _stub("tiatoolbox.utils.misc", **misc)
+    sn = importlib.import_module("tiatoolbox.tools.stainnorm")
+    _loaded["stain"] = sn
+    return sn
+
+
+def load_misc():
+    load_stain()
+    return sys.modules["tiatoolbox.utils.misc"]
+
+
+def target_image() -> np.ndarray:
+    """The in-tree 1000x1000x3 stain target (tiatoolbox/data/target_image.png)."""
+    import cv2
+
+    bgr = cv2.imread(str(REF_PKG / "data" / "target_image.png"), cv2.IMREAD_COLOR)
+    return np.ascontiguousarray(bgr[..., ::-1])

@@ -1,0 +1,40 @@
+// ctx.h — per-device handle shared by the subsystems of libtiab200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+struct tiab_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  int stain_path = 0;       // 0 auto, 1 fused, 2 general
+  int last_launches = 0;
+  // stain workspaces (grown on demand)
+  void* stain_work = nullptr;   // StainWork[n]
+  size_t stain_work_bytes = 0;
+  void* stain_state = nullptr;  // StainState[n]
+  size_t stain_state_bytes = 0;
+  void* stain_lut = nullptr;    // global constant tables
+  // host staging (pinned) + device staging for the *_host entry points
+  void* pin_in = nullptr;
+  void* pin_out = nullptr;
+  size_t pin_bytes = 0;
+  void* dev_in = nullptr;
+  void* dev_out = nullptr;
+  size_t dev_bytes = 0;
+  void* dev_small = nullptr;    // N*(6+2) doubles + N ints
+  void* pin_small = nullptr;
+  size_t small_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+};
+
+#define TIAB_CUDA_OK(h, expr)                                                                  \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                           \
+      return TIAB_E_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
