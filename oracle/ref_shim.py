@@ -137,3 +137,41 @@ def target_image() -> np.ndarray:
 
     bgr = cv2.imread(str(REF_PKG / "data" / "target_image.png"), cv2.IMREAD_COLOR)
     return np.ascontiguousarray(bgr[..., ::-1])
+
+
+def load_models():
+    """Return the reference's architecture modules (hovernet, unet, vanilla, utils) loaded
+    unmodified, with the absent third-party packages (dask, skimage, timm) stubbed out."""
+    if "models" in _loaded:
+        return _loaded["models"]
+    load_stain()  # base packages + tiatoolbox.utils.misc stub (get_bounding_box included)
+
+    class _Array:  # dask.array.Array placeholder for type annotations
+        pass
+
+    if "dask" not in sys.modules:
+        da = _stub("dask.array", Array=_Array)
+        d = _stub("dask", array=da, delayed=lambda f: f, compute=lambda *a, **k: a)
+        d.__path__ = []
+    for name in ("skimage", "skimage.morphology", "skimage.segmentation", "skimage.feature", "skimage.measure", "skimage.exposure"):
+        if name not in sys.modules:
+            m = _stub(name)
+            m.__path__ = []
+    sys.modules["skimage.morphology"].remove_small_objects = None
+    sys.modules["skimage.segmentation"].watershed = None
+    sys.modules["skimage.feature"].peak_local_max = None
+    sys.modules["skimage.measure"].label = None
+    sys.modules["skimage.measure"].regionprops = None
+    if "timm" not in sys.modules:
+        t = _stub("timm", list_models=lambda *a, **k: [], create_model=None)
+        t.__path__ = []
+        t.layers = _stub("timm.layers", SwiGLUPacked=None)
+        t.models = _stub("timm.models", VisionTransformer=None)
+    mods = types.SimpleNamespace()
+    mods.models_abc = importlib.import_module("tiatoolbox.models.models_abc")
+    mods.utils = importlib.import_module("tiatoolbox.models.architecture.utils")
+    mods.hovernet = importlib.import_module("tiatoolbox.models.architecture.hovernet")
+    mods.unet = importlib.import_module("tiatoolbox.models.architecture.unet")
+    mods.vanilla = importlib.import_module("tiatoolbox.models.architecture.vanilla")
+    _loaded["models"] = mods
+    return mods
