@@ -97,6 +97,68 @@ int tiab_stain_tissue_mask(tiab_handle_t h, const tiab_stain_params_t* p, const 
 int tiab_stain_concentrations(tiab_handle_t h, const uint8_t* in_dev, int N, int H, int W, const double M[6],
                               float* conc_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Convolution engine (patch CNNs).  Replaces the torch.nn.Conv2d / BatchNorm2d / ReLU library calls
+ * inside tiatoolbox/models/architecture/hovernet.py:61-262,330-454, unet.py:24-418,
+ * vanilla.py:256-333 (the per-batch `model(x)` of infer_batch: vanilla.py:251, unet.py:457,
+ * hovernet.py:896).  All tensors are NHWC; activations fp16, accumulation fp32.
+ * ------------------------------------------------------------------------------------------- */
+#define TIAB_MAX_TAPS 49
+
+/* One shifted-GEMM convolution:  D[p, co] = sum_t sum_ci X[p + tap_off[t], ci] * W[co, t, ci]
+ * over the virtual output rows p in [0, M) of the input grid (Hin x Win per image); rows whose
+ * (y, x) fall outside [y0,y1) x [x0,x1) are discarded.  Epilogue per surviving element:
+ *   v = D + bias[co] (+ residual) ; relu? ; out32 / out16 <- v ; out16b <- relu(v*scale2 + shift2)
+ * written at destination row (img*Hd + y + dy)*Wd + x + dx with channel offset coff*. */
+typedef struct {
+  const void* x;        /* fp16 [x_rows, cin], row pitch x_ld elements */
+  long long x_rows;
+  long long x_ld;
+  int cin;
+  const void* w;        /* fp16 [N, taps*ceil64(cin)] K-major (BN folded), row pitch w_ld elements */
+  long long w_ld;
+  int M, N, taps;
+  int tap_off[TIAB_MAX_TAPS];
+  int Hin, Win, y0, y1, x0, x1;
+  int Hd, Wd, dy, dx;
+  int Hr, Wr, ry, rx;
+  void* out16;
+  int ld16, coff16;
+  void* out32;
+  int ld32, coff32;
+  void* out16b;
+  int ld16b, coff16b;
+  const void* scale2;   /* fp32 [N] */
+  const void* shift2;   /* fp32 [N] */
+  const void* bias;     /* fp32 [N] or NULL */
+  const void* res32;    /* fp32 residual or NULL */
+  const void* res16;    /* fp16 residual or NULL */
+  int ldres, coffres;
+  int relu;
+} tiab_conv_desc_t;
+
+int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);
+/* explicit im2col (strided convs, 3-channel stems): out [N*Ho*Wo, Kpad] fp16, k = (kh*KW + kw)*C + c */
+int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int N, int H, int W, int C, int ldsrc,
+                int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int Kpad, void* stream);
+/* dst = relu?(src*scale + shift) -> fp16 (per-unit pre-activation of dense blocks, hovernet.py:84-86) */
+int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, const float* scale,
+                 const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, void* stream);
+/* dst = relu?(bn?(up2x(a) + b[window])) (hovernet.py:440-451, unet.py:405-411) */
+int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, const void* b_f16, int Hb, int Wb, int by, int bx,
+                      int N, int C, const float* scale, const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy,
+                      int dx, void* dst_f32, void* stream);
+int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, void* dst_f16, void* stream);
+/* out[p, j] = sum_c relu?(x[p,c]*scale[c]+shift[c]) * Wt[j,c] + bias[j], nout <= 16 (hovernet.py:487-497, unet.py:353) */
+int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int C, int ldx, const float* scale,
+                        const float* shift, int relu, const float* Wt, const float* bias, int nout, float* out, int ldout,
+                        int coffout, void* stream);
+/* global average pool + Linear + softmax (vanilla.py:312-316) */
+int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, const float* Wt, const float* bias, int ncls,
+                        float* feat_out, float* probs, void* stream);
+int tiab_u8_to_f16(tiab_handle_t h, const uint8_t* src, int N, int H, int W, int C, float scale, void* dst_f16, int Hd, int Wd,
+                   int dy, int dx, int Cd, void* stream);
+
 /* Force one of the two device paths (testing / benchmarking): 0 = auto, 1 = fused one-CTA-per-patch
  * kernel (requires H*W*3 <= 196608 and H*W % 16 == 0), 2 = multi-pass general path. */
 int tiab_stain_set_path(tiab_handle_t h, int path);

@@ -1,0 +1,131 @@
+"""GPU tests of the tcgen05 shifted-GEMM convolution kernel against plain PyTorch fp32 references
+computed from the same fp16-rounded operands (so the only difference is fp32 summation order)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from tiatoolbox_b200.models import ops as _ops
+
+    return _ops
+
+
+def _pack_w(w_oihw, cin_pad):
+    """[Cout, Cin, KH, KW] fp32 -> [Cout, taps*cin_pad] fp16 (tap-major, channels zero padded)."""
+    import torch
+
+    co, ci, kh, kw = w_oihw.shape
+    w = torch.zeros(co, kh * kw, cin_pad, dtype=torch.float16, device=w_oihw.device)
+    w[:, :, :ci] = w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).half()
+    return w.reshape(co, kh * kw * cin_pad).contiguous()
+
+
+@pytest.mark.parametrize("m,k,n", [(1000, 192, 64), (128, 64, 32), (4096 + 77, 288, 128), (777, 1024, 256), (300, 64, 512)])
+def test_gemm_1x1(ops, m, k, n):
+    import torch
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    x = torch.randn(m, k, device=dev).half()
+    w = (torch.randn(n, k, device=dev) / k**0.5)
+    bias = torch.randn(n, device=dev)
+    kp = (k + 63) // 64 * 64
+    wp = _pack_w(w.reshape(n, k, 1, 1), kp)
+    out32 = torch.full((m, n), float("nan"), device=dev)
+    out16 = torch.zeros((m, n), dtype=torch.float16, device=dev)
+    op = ops.ConvOp(x=x, x_rows=m, x_ld=k, cin=k, w=wp, taps=[0], M=m, N=n, grid=(1, m), window=(0, 1, 0, m),
+                    dst_geom=(1, m, 0, 0), out32=out32, ld32=n, out16=out16, ld16=n, bias=bias)
+    op()
+    torch.cuda.synchronize()
+    ref = x.float() @ w.half().float().t() + bias
+    assert torch.isfinite(out32).all()
+    err = (out32 - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+    assert (out16.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, 20), (128, 32, 17), (96, 128, 33)])
+def test_conv3x3_valid_with_epilogues(ops, cin, cout, hw):
+    import torch
+    import torch.nn.functional as F
+
+    torch.manual_seed(1)
+    dev = torch.device("cuda")
+    nimg, h, w_ = 3, hw, hw + 3
+    x = torch.randn(nimg, h, w_, cin, device=dev).half()          # NHWC
+    wt = torch.randn(cout, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
+    bias = torch.randn(cout, device=dev) * 0.1
+    res = torch.randn(nimg, h - 2, w_ - 2, cout, device=dev)      # fp32 residual on the output grid
+    scale2 = torch.rand(cout, device=dev) + 0.5
+    shift2 = torch.randn(cout, device=dev) * 0.1
+    cin_pad = (cin + 63) // 64 * 64
+    wp = _pack_w(wt, cin_pad)
+    ho, wo = h - 2, w_ - 2
+    # destination: interior of a zero padded buffer (pad 1) with extra channels (channel offset 32)
+    cd = cout + 64
+    dst16 = torch.zeros(nimg, ho + 2, wo + 2, cd, dtype=torch.float16, device=dev)
+    dst32 = torch.zeros(nimg, ho, wo, cout, device=dev)
+    dst16b = torch.zeros(nimg, ho, wo, cout, dtype=torch.float16, device=dev)
+    taps = [kh * w_ + kw for kh in range(3) for kw in range(3)]
+    op = ops.ConvOp(x=x, x_rows=nimg * h * w_, x_ld=cin, cin=cin, w=wp, taps=taps, M=nimg * h * w_, N=cout,
+                    grid=(h, w_), window=(0, ho, 0, wo), dst_geom=(ho + 2, wo + 2, 1, 1), out16=dst16, ld16=cd, coff16=32,
+                    out32=dst32, ld32=cout, out16b=dst16b, ld16b=cout, scale2=scale2, shift2=shift2, bias=bias,
+                    res32=res, ldres=cout, res_geom=(ho, wo, 0, 0), relu=False)
+    # out32 uses a different destination geometry than out16 -> launch twice with two descriptors instead
+    op.desc.out32 = None
+    op.desc.out16b = None
+    op()
+    op2 = ops.ConvOp(x=x, x_rows=nimg * h * w_, x_ld=cin, cin=cin, w=wp, taps=taps, M=nimg * h * w_, N=cout,
+                     grid=(h, w_), window=(0, ho, 0, wo), dst_geom=(ho, wo, 0, 0), out32=dst32, ld32=cout,
+                     out16b=dst16b, ld16b=cout, scale2=scale2, shift2=shift2, bias=bias, res32=res, ldres=cout,
+                     res_geom=(ho, wo, 0, 0), relu=False)
+    op2()
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.half().float(), bias).permute(0, 2, 3, 1) + res
+    tol = 3e-3 * max(1.0, ref.abs().max().item())
+    assert (dst32 - ref).abs().max().item() < tol
+    assert (dst16[:, 1:-1, 1:-1, 32:32 + cout].float() - ref).abs().max().item() < 3e-2
+    # untouched: the zero border and the other channels
+    assert dst16[:, 0].abs().max().item() == 0 and dst16[:, :, 0].abs().max().item() == 0
+    assert dst16[..., :32].abs().max().item() == 0 and dst16[..., 32 + cout:].abs().max().item() == 0
+    ref_b = torch.relu(ref * scale2 + shift2)
+    assert (dst16b.float() - ref_b).abs().max().item() < 3e-2
+
+
+def test_conv_relu_fp16_residual_and_many_tiles(ops):
+    import torch
+    import torch.nn.functional as F
+
+    torch.manual_seed(2)
+    dev = torch.device("cuda")
+    nimg, h, w_, cin, cout = 4, 66, 66, 256, 256      # > 148 tiles: persistent loop + TMEM double buffering
+    x = torch.randn(nimg, h, w_, cin, device=dev).half()
+    wt = torch.randn(cout, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
+    res16 = torch.randn(nimg, h - 2, w_ - 2, cout, device=dev).half()
+    wp = _pack_w(wt, cin)
+    ho, wo = h - 2, w_ - 2
+    dst16 = torch.zeros(nimg, ho, wo, cout, dtype=torch.float16, device=dev)
+    taps = [kh * w_ + kw for kh in range(3) for kw in range(3)]
+    op = ops.ConvOp(x=x, x_rows=nimg * h * w_, x_ld=cin, cin=cin, w=wp, taps=taps, M=nimg * h * w_, N=cout, grid=(h, w_),
+                    window=(0, ho, 0, wo), dst_geom=(ho, wo, 0, 0), out16=dst16, ld16=cout, res16=res16, ldres=cout,
+                    res_geom=(ho, wo, 0, 0), relu=True)
+    op()
+    torch.cuda.synchronize()
+    ref = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.half().float()).permute(0, 2, 3, 1) + res16.float())
+    assert (dst16.float() - ref).abs().max().item() < 3e-2
+    # timing sanity (not a benchmark): 2*M*N*K flops
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        op()
+    start.record()
+    for _ in range(10):
+        op()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / 10
+    print(f"conv3x3 256->256 @66x66x4: {ms*1e3:.1f} us, {op.flops/ms/1e9:.1f} TFLOP/s")

@@ -1,0 +1,838 @@
+// conv.cu — B200 (sm_100a) convolution engine for the patch CNNs (resnet18-kather100k,
+// fcn-tissue_mask, hovernet_fast-pannuke).
+//
+// One tcgen05 kernel does every dense contraction of the three networks as a *shifted GEMM*:
+//
+//     D[p, co] = sum_t  sum_ci  X[p + off_t, ci] * W[co, t, ci]            (fp16 x fp16 -> fp32)
+//
+// where X is an NHWC activation tensor viewed as a [rows, C] matrix, p runs over the *input* grid
+// ("virtual" output pixels: positions whose receptive field leaves the valid window are computed
+// and discarded by the epilogue), and off_t = kh*W_in + kw is a plain row offset per filter tap.
+// A stride-1 KxK convolution on a (pre-padded) NHWC buffer therefore needs no im2col and no 4-D
+// boxes: every A tile is one 2-D TMA load of 128 consecutive rows x 64 channels at row p0 + off_t
+// (out-of-range rows are zero-filled by TMA).  1x1 convs are the T = 1 case; strided convs and the
+// 3-channel stems go through an explicit im2col (few layers) and then the same kernel.
+//
+// Pipeline (CUTLASS-free, inline PTX): warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma
+// issuer (UMMA 128 x BLOCK_N x 16, kind::f16, accumulators in TMEM, double buffered), warp 2 =
+// TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias / residual / ReLU / second
+// BN+ReLU output -> NHWC stores with window + destination remapping).  Persistent CTAs, static
+// tile scheduler, S-stage smem ring with full/empty mbarriers.
+//
+// Reference layers this replaces: torch.nn.Conv2d/BatchNorm2d/ReLU inside
+// tiatoolbox/models/architecture/hovernet.py:61-262,330-454, unet.py:24-418, vanilla.py:256-333
+// (CPU: oneDNN, CUDA: cuDNN library calls).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/tiab200.h"
+#include "ctx.h"
+
+namespace tiab {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // fp16: 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int CONV_THREADS = 256;
+constexpr int MAX_STAGES = 8;
+
+struct ConvParams {
+  int M, N;
+  int taps, kchunks;
+  int tap_off[TIAB_MAX_TAPS];
+  int Hin, Win;           // virtual grid (rows per image = Hin*Win)
+  int y0, y1, x0, x1;     // valid output window on the grid
+  int Hd, Wd, dy, dx;     // destination row = (img*Hd + y + dy)*Wd + x + dx
+  int Hr, Wr, ry, rx;     // residual row    = (img*Hr + y + ry)*Wr + x + rx
+  __half* out16;
+  int ld16, coff16;
+  float* out32;
+  int ld32, coff32;
+  __half* out16b;
+  int ld16b, coff16b;
+  const float* scale2;
+  const float* shift2;
+  const float* bias;
+  const float* res32;
+  const __half* res16;
+  int ldres, coffres;
+  int relu;
+  int num_m_tiles, num_n_tiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cvta_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cvta_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cvta_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(cvta_smem(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          cvta_smem(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(cvta_smem(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cvta_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major) ;
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) ; [46,48) version = 1 ;
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+struct ConvSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (200 * 1024 / STAGE_BYTES);
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr, + slack for 1024 B alignment
+  static constexpr int TMEM_COLS = (2 * BLOCK_N) <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using S = ConvSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kiters = p.taps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbarrier_init(&full_bar[s], 1);
+      mbarrier_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbarrier_init(&tfull_bar[b], 1);
+      mbarrier_init(&tempty_bar[b], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cvta_smem(tmem_ptr_smem)),
+                 "n"(S::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (int t = 0; t < p.taps; ++t) {
+          const int row = m0 + p.tap_off[t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbarrier_wait(&empty_bar[s], ph ^ 1u);
+            mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
+            uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+            tma_load_2d(a_dst, &tmA, kc * BLOCK_K, row, &full_bar[s]);
+            tma_load_2d(a_dst + S::A_BYTES, &tmB, (t * p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
+            if (++s == S::STAGES) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int ab = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbarrier_wait(&tempty_bar[ab], aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BLOCK_N);
+        for (int k = 0; k < kiters; ++k) {
+          mbarrier_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = cvta_smem(smem + s * S::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + S::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
+            tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                            (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[s]);  // frees the smem stage when these MMAs have consumed it
+          if (++s == S::STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        tcgen05_commit(&tfull_bar[ab]);  // accumulator ready for the epilogue
+        if (++ab == 2) {
+          ab = 0;
+          aph ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int ab = 0;
+    uint32_t aph = 0;
+    const int grid_px = p.Hin * p.Win;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
+      const int n0 = n_blk * BLOCK_N;
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      bool valid = row < p.M;
+      long long drow = 0, rrow = 0;
+      {
+        const int img = row / grid_px;
+        const int rem = row - img * grid_px;
+        const int y = rem / p.Win;
+        const int x = rem - y * p.Win;
+        valid = valid && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
+        drow = ((long long)img * p.Hd + (y + p.dy)) * p.Wd + (x + p.dx);
+        rrow = ((long long)img * p.Hr + (y + p.ry)) * p.Wr + (x + p.rx);
+      }
+      mbarrier_wait(&tfull_bar[ab], aph);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+          const int n = n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          }
+          if (p.res32) {
+            const float* rp = p.res32 + rrow * p.ldres + p.coffres + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+            }
+          } else if (p.res16) {
+            const __half* rp = p.res16 + rrow * p.ldres + p.coffres + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h2[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.out32) {
+            float* op = p.out32 + drow * p.ld32 + p.coff32 + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.out16) {
+            __half* op = p.out16 + drow * p.ld16 + p.coff16 + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              __half2* h2 = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(op + j) = q;
+            }
+          }
+          if (p.out16b) {
+            __half* op = p.out16b + drow * p.ld16b + p.coff16b + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              __half2* h2 = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = n + j + 2 * e;
+                float a0 = fmaxf(fmaf(v[j + 2 * e], __ldg(p.scale2 + c), __ldg(p.shift2 + c)), 0.f);
+                float a1 = fmaxf(fmaf(v[j + 2 * e + 1], __ldg(p.scale2 + c + 1), __ldg(p.shift2 + c + 1)), 0.f);
+                h2[e] = __floats2half2_rn(a0, a1);
+              }
+              *reinterpret_cast<uint4*>(op + j) = q;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&tempty_bar[ab]);
+      if (++ab == 2) {
+        ab = 0;
+        aph ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// auxiliary kernels (memory-bound glue between the GEMMs)
+// ---------------------------------------------------------------------------------------------
+// Explicit im2col for strided convs / 3-channel stems: out[m, t*Cin + c] (fp16, row pitch Kpad, zero padded)
+// from an NHWC source that is fp16 or uint8 (uint8 is scaled by `u8_scale`, e.g. 1/255).
+__global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ src, int src_is_u8, float u8_scale, int Nimg,
+                                                     int H, int W, int C, int ldsrc, int KH, int KW, int stride,
+                                                     int pad_t, int pad_l, int Ho, int Wo, __half* __restrict__ out,
+                                                     int Kpad) {
+  const long long total = (long long)Nimg * Ho * Wo * Kpad;
+  const int K = KH * KW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const long long m = i / Kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, t = k / C, kw = t % KW, kh = t / KW;
+      const int xo = (int)(m % Wo);
+      const int yo = (int)((m / Wo) % Ho);
+      const int img = (int)(m / ((long long)Wo * Ho));
+      const int y = yo * stride - pad_t + kh, x = xo * stride - pad_l + kw;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const long long off = ((long long)(img * H + y) * W + x) * ldsrc + c;
+        v = src_is_u8 ? (float)reinterpret_cast<const uint8_t*>(src)[off] * u8_scale
+                      : __half2float(reinterpret_cast<const __half*>(src)[off]);
+      }
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// y = relu(x * scale[c] + shift[c]) over a window of an NHWC tensor (fp32 or fp16 source) -> fp16.
+// Used for the per-unit pre-activation of HoVer-Net's dense blocks (hovernet.py:84-86).
+__global__ void __launch_bounds__(256) bn_relu_kernel(const void* __restrict__ src, int src_is_f32, int ldsrc, int coffsrc,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      int relu, long long rows, int C, __half* __restrict__ dst, int lddst,
+                                                      int coffdst) {
+  const int c8 = C >> 3;
+  const long long total = rows * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8) * 8;
+    const long long r = i / c8;
+    float v[8];
+    if (src_is_f32) {
+      const float* s = reinterpret_cast<const float*>(src) + r * ldsrc + coffsrc + cg;
+      float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+      uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + r * ldsrc + coffsrc + cg);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        v[2 * e] = f.x, v[2 * e + 1] = f.y;
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+    for (int e = 0; e < 4; ++e) {
+      float a0 = v[2 * e], a1 = v[2 * e + 1];
+      if (scale) {
+        a0 = fmaf(a0, scale[cg + 2 * e], shift[cg + 2 * e]);
+        a1 = fmaf(a1, scale[cg + 2 * e + 1], shift[cg + 2 * e + 1]);
+      }
+      if (relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
+      oh[e] = __floats2half2_rn(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(dst + r * lddst + coffdst + cg) = o;
+  }
+}
+
+// dst[n, y, x, :] = up2x(a)[n, y, x, :] + b[n, y + by, x + bx, :]   (nearest-neighbour 2x, NHWC fp16)
+// hovernet.py:440-451 `upsample2x(d[-1]) + d[-2]`, unet.py:405-411.  Optional per-channel BN+ReLU on the sum
+// (UNet decoder pre-activation, unet.py:211-224).  dst may be a window of a larger (pre-padded) buffer.
+__global__ void __launch_bounds__(256)
+upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, const __half* __restrict__ b, int Hb, int Wb, int by,
+                    int bx, int Nimg, int C, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                    __half* __restrict__ dst, int Hd, int Wd, int dy, int dx, float* __restrict__ dst32) {
+  const int Ho = 2 * Ha, Wo = 2 * Wa, c8 = C >> 3;
+  const long long total = (long long)Nimg * Ho * Wo * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const int x = (int)(r % Wo);
+    r /= Wo;
+    const int y = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    uint4 qa = *reinterpret_cast<const uint4*>(a + ((long long)(img * Ha + (y >> 1)) * Wa + (x >> 1)) * C + cg);
+    float v[8];
+    const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+    for (int e = 0; e < 4; ++e) {
+      float2 fa = __half22float2(ha[e]);
+      v[2 * e] = fa.x, v[2 * e + 1] = fa.y;
+    }
+    if (b) {
+      uint4 qb = *reinterpret_cast<const uint4*>(b + ((long long)(img * Hb + y + by) * Wb + (x + bx)) * C + cg);
+      const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+      for (int e = 0; e < 4; ++e) {
+        float2 fb = __half22float2(hb[e]);
+        v[2 * e] += fb.x, v[2 * e + 1] += fb.y;
+      }
+    }
+    const long long drow = (long long)(img * Hd + y + dy) * Wd + (x + dx);
+    if (dst32) {
+      float* d32 = dst32 + drow * C + cg;
+      *reinterpret_cast<float4*>(d32) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(d32 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+    for (int e = 0; e < 4; ++e) {
+      float a0 = v[2 * e], a1 = v[2 * e + 1];
+      if (scale) {
+        a0 = fmaf(a0, scale[cg + 2 * e], shift[cg + 2 * e]);
+        a1 = fmaf(a1, scale[cg + 2 * e + 1], shift[cg + 2 * e + 1]);
+      }
+      if (relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
+      oh[e] = __floats2half2_rn(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(dst + drow * C + cg) = o;
+  }
+}
+
+// 3x3 stride-2 pad-1 max pool, NHWC fp16 (torchvision ResNet stem).
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ src, int Nimg, int H, int W, int C,
+                                                           __half* __restrict__ dst, int Ho, int Wo) {
+  const int c8 = C >> 3;
+  const long long total = (long long)Nimg * Ho * Wo * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const int xo = (int)(r % Wo);
+    r /= Wo;
+    const int yo = (int)(r % Ho);
+    const int img = (int)(r / Ho);
+    float m[8];
+    for (int e = 0; e < 8; ++e) m[e] = -65504.f;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int y = 2 * yo - 1 + ky, x = 2 * xo - 1 + kx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        uint4 q = *reinterpret_cast<const uint4*>(src + ((long long)(img * H + y) * W + x) * C + cg);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(h2[e]);
+          m[2 * e] = fmaxf(m[2 * e], f.x), m[2 * e + 1] = fmaxf(m[2 * e + 1], f.y);
+        }
+      }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(m[2 * e], m[2 * e + 1]);
+    *reinterpret_cast<uint4*>(dst + ((long long)(img * Ho + yo) * Wo + xo) * C + cg) = o;
+  }
+}
+
+// Small-N pointwise head: out[p, j] = sum_c relu(x[p,c]*scale[c]+shift[c]) * Wt[j, c] + b[j], j < NOUT <= 16, fp32 out.
+// HoVer-Net u0 (hovernet.py:487-497: BN, ReLU, 1x1 conv with bias) and the UNet clf (unet.py:353).
+__global__ void __launch_bounds__(128) pointwise_head_kernel(const __half* __restrict__ x, long long rows, int C, int ldx,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             int relu, const float* __restrict__ Wt, const float* __restrict__ b,
+                                                             int nout, float* __restrict__ out, int ldout, int coffout) {
+  extern __shared__ float sh[];  // Wt[nout*C] | scale[C] | shift[C]
+  float* sw = sh;
+  float* ss = sh + nout * C;
+  float* st = ss + C;
+  for (int i = threadIdx.x; i < nout * C; i += blockDim.x) sw[i] = Wt[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    ss[i] = scale ? scale[i] : 1.f;
+    st[i] = shift ? shift[i] : 0.f;
+  }
+  __syncthreads();
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    float acc[16];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    const __half* xp = x + r * ldx;
+    for (int c = 0; c < C; c += 8) {
+      uint4 q = *reinterpret_cast<const uint4*>(xp + c);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+      float v[8];
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        v[2 * e] = f.x, v[2 * e + 1] = f.y;
+      }
+      for (int e = 0; e < 8; ++e) {
+        float a = fmaf(v[e], ss[c + e], st[c + e]);
+        if (relu) a = fmaxf(a, 0.f);
+        for (int j = 0; j < nout; ++j) acc[j] = fmaf(a, sw[j * C + c + e], acc[j]);
+      }
+    }
+    for (int j = 0; j < nout; ++j) out[r * ldout + coffout + j] = acc[j] + (b ? b[j] : 0.f);
+  }
+}
+
+// Global-average-pool + Linear + softmax (vanilla.py:312-316): x NHWC fp16 [N, HW, C] -> probs [N, ncls] fp32.
+__global__ void __launch_bounds__(256) gap_fc_softmax_kernel(const __half* __restrict__ x, int HW, int C,
+                                                             const float* __restrict__ Wt, const float* __restrict__ b,
+                                                             int ncls, float* __restrict__ feat_out, float* __restrict__ probs) {
+  extern __shared__ float sh[];  // feat[C] | logits[ncls]
+  float* feat = sh;
+  float* logits = sh + C;
+  const int img = blockIdx.x;
+  const __half* xp = x + (long long)img * HW * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < HW; ++i) s += __half2float(xp[(long long)i * C + c]);
+    feat[c] = s / (float)HW;
+    if (feat_out) feat_out[(long long)img * C + c] = feat[c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < ncls; j += blockDim.x >> 5) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(feat[c], Wt[j * C + c], s);
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) logits[j] = s + b[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = -1e30f;
+    for (int j = 0; j < ncls; ++j) m = fmaxf(m, logits[j]);
+    float z = 0.f;
+    for (int j = 0; j < ncls; ++j) z += expf(logits[j] - m);
+    for (int j = 0; j < ncls; ++j) probs[(long long)img * ncls + j] = expf(logits[j] - m) / z;
+  }
+}
+
+// uint8 NHWC -> fp16 NHWC with scale, optionally into a window of a zero-padded buffer and with channel padding.
+__global__ void __launch_bounds__(256) u8_to_f16_kernel(const uint8_t* __restrict__ src, int Nimg, int H, int W, int C, float scale,
+                                                        __half* __restrict__ dst, int Hd, int Wd, int dy, int dx, int Cd) {
+  const long long total = (long long)Nimg * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int img = (int)(i / ((long long)W * H));
+    __half* d = dst + ((long long)(img * Hd + y + dy) * Wd + x + dx) * Cd;
+    for (int c = 0; c < C; ++c) d[c] = __float2half_rn((float)src[i * C + c] * scale);
+  }
+}
+
+}  // namespace tiab
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace tiab;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn(tiab_ctx* h) {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    h->err = "cuTensorMapEncodeTiled driver entry point not available";
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 2-D fp16 matrix [rows, cols] with row pitch ld (elements); box = {64 cols, box_rows}; 128-byte swizzle.
+static int make_map_2d(tiab_ctx* h, CUtensorMap* map, const void* base, long long rows, int cols, long long ld,
+                       int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn(h);
+  if (!enc) return TIAB_E_CUDA;
+  if (((uintptr_t)base & 15) || ((ld * 2) & 15)) {
+    h->err = "conv: operand base/pitch must be 16-byte aligned";
+    return TIAB_E_INVALID;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+    return TIAB_E_CUDA;
+  }
+  return TIAB_OK;
+}
+
+template <int BN>
+static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& tb, ConvParams& p, cudaStream_t s) {
+  using S = ConvSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = p.N / BN;
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = std::min(tiles, h->sm_count);
+  conv_gemm_kernel<BN><<<grid, CONV_THREADS, S::TOTAL, s>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    h->err = std::string("conv_gemm launch: ") + cudaGetErrorString(e);
+    return TIAB_E_CUDA;
+  }
+  h->last_launches++;
+  return TIAB_OK;
+}
+
+#define AUX_LAUNCH_CHECK(h, what)                                                \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) {                                                     \
+      (h)->err = std::string(what " launch: ") + cudaGetErrorString(_e);         \
+      return TIAB_E_CUDA;                                                        \
+    }                                                                            \
+    (h)->last_launches++;                                                        \
+  } while (0)
+
+static int aux_grid(tiab_ctx* h, long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  long long cap = (long long)h->sm_count * 16;
+  return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+extern "C" {
+
+int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
+  if (!h) return TIAB_E_INVALID;
+  if (!d || !d->x || !d->w || d->M <= 0 || d->N <= 0 || d->taps <= 0 || d->taps > TIAB_MAX_TAPS || d->cin <= 0) {
+    h->err = "tiab_conv_gemm: invalid descriptor";
+    return TIAB_E_INVALID;
+  }
+  if (d->N % 32) {
+    h->err = "tiab_conv_gemm: N (output channels) must be a multiple of 32";
+    return TIAB_E_INVALID;
+  }
+  if (d->x_rows + 0 < 1 || d->Hin <= 0 || d->Win <= 0) {
+    h->err = "tiab_conv_gemm: invalid grid";
+    return TIAB_E_INVALID;
+  }
+  const int kchunks = (d->cin + BLOCK_K - 1) / BLOCK_K;
+  if (d->w_ld < (long long)d->taps * kchunks * BLOCK_K) {
+    h->err = "tiab_conv_gemm: weight pitch smaller than taps*ceil64(cin)";
+    return TIAB_E_INVALID;
+  }
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  const int BN = (d->N % 256 == 0) ? 256 : (d->N % 128 == 0) ? 128 : (d->N % 64 == 0) ? 64 : 32;
+  CUtensorMap ta, tb;
+  int rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map_2d(h, &tb, d->w, d->N, (int)std::min<long long>(d->w_ld, (long long)d->taps * kchunks * BLOCK_K), d->w_ld, BN);
+  if (rc) return rc;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M;
+  p.N = d->N;
+  p.taps = d->taps;
+  p.kchunks = kchunks;
+  for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t];
+  p.Hin = d->Hin, p.Win = d->Win;
+  p.y0 = d->y0, p.y1 = d->y1, p.x0 = d->x0, p.x1 = d->x1;
+  p.Hd = d->Hd, p.Wd = d->Wd, p.dy = d->dy, p.dx = d->dx;
+  p.Hr = d->Hr, p.Wr = d->Wr, p.ry = d->ry, p.rx = d->rx;
+  p.out16 = (__half*)d->out16, p.ld16 = d->ld16, p.coff16 = d->coff16;
+  p.out32 = (float*)d->out32, p.ld32 = d->ld32, p.coff32 = d->coff32;
+  p.out16b = (__half*)d->out16b, p.ld16b = d->ld16b, p.coff16b = d->coff16b;
+  p.scale2 = (const float*)d->scale2, p.shift2 = (const float*)d->shift2;
+  p.bias = (const float*)d->bias;
+  p.res32 = (const float*)d->res32, p.res16 = (const __half*)d->res16, p.ldres = d->ldres, p.coffres = d->coffres;
+  p.relu = d->relu;
+  if (p.out16b && (!p.scale2 || !p.shift2)) {
+    h->err = "tiab_conv_gemm: out16b needs scale2/shift2";
+    return TIAB_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (BN) {
+    case 256: return launch_conv<256>(h, ta, tb, p, s);
+    case 128: return launch_conv<128>(h, ta, tb, p, s);
+    case 64: return launch_conv<64>(h, ta, tb, p, s);
+    default: return launch_conv<32>(h, ta, tb, p, s);
+  }
+}
+
+int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int N, int H, int W, int C, int ldsrc,
+                int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int Kpad, void* stream) {
+  if (!h || !src || !out_f16 || Kpad < KH * KW * C) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  long long total = (long long)N * Ho * Wo * Kpad;
+  im2col_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_u8, u8_scale, N, H, W, C, ldsrc, KH, KW,
+                                                                           stride, pad_t, pad_l, Ho, Wo, (__half*)out_f16, Kpad);
+  AUX_LAUNCH_CHECK(h, "im2col");
+  return TIAB_OK;
+}
+
+int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, const float* scale,
+                 const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, void* stream) {
+  if (!h || !src || !dst_f16 || (C & 7) || (ldsrc & 7) || (lddst & 7) || (coffsrc & 7) || (coffdst & 7)) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  bn_relu_kernel<<<aux_grid(h, rows * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_f32, ldsrc, coffsrc, scale, shift,
+                                                                                       relu, rows, C, (__half*)dst_f16, lddst, coffdst);
+  AUX_LAUNCH_CHECK(h, "bn_relu");
+  return TIAB_OK;
+}
+
+int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, const void* b_f16, int Hb, int Wb, int by, int bx,
+                      int N, int C, const float* scale, const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy,
+                      int dx, void* dst_f32, void* stream) {
+  if (!h || !a_f16 || !dst_f16 || (C & 7)) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  long long total = (long long)N * 4 * Ha * Wa * (C >> 3);
+  upsample_add_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a_f16, Ha, Wa, (const __half*)b_f16, Hb, Wb, by, bx, N, C, scale, shift, relu, (__half*)dst_f16, Hd, Wd, dy, dx,
+      (float*)dst_f32);
+  AUX_LAUNCH_CHECK(h, "upsample_add");
+  return TIAB_OK;
+}
+
+int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, void* dst_f16, void* stream) {
+  if (!h || !src_f16 || !dst_f16 || (C & 7)) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C >> 3);
+  maxpool3x3s2_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, N, H, W, C, (__half*)dst_f16, Ho, Wo);
+  AUX_LAUNCH_CHECK(h, "maxpool");
+  return TIAB_OK;
+}
+
+int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int C, int ldx, const float* scale,
+                        const float* shift, int relu, const float* Wt, const float* bias, int nout, float* out, int ldout,
+                        int coffout, void* stream) {
+  if (!h || !x_f16 || !Wt || !out || nout < 1 || nout > 16 || (C & 7) || (ldx & 7)) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  size_t sm = (size_t)(nout * C + 2 * C) * sizeof(float);
+  pointwise_head_kernel<<<aux_grid(h, rows, 128), 128, sm, (cudaStream_t)stream>>>((const __half*)x_f16, rows, C, ldx, scale, shift, relu,
+                                                                                    Wt, bias, nout, out, ldout, coffout);
+  AUX_LAUNCH_CHECK(h, "pointwise_head");
+  return TIAB_OK;
+}
+
+int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, const float* Wt, const float* bias, int ncls,
+                        float* feat_out, float* probs, void* stream) {
+  if (!h || !x_f16 || !Wt || !bias || !probs || ncls < 1 || ncls > 1024) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  size_t sm = (size_t)(C + ncls) * sizeof(float);
+  gap_fc_softmax_kernel<<<N, 256, sm, (cudaStream_t)stream>>>((const __half*)x_f16, HW, C, Wt, bias, ncls, feat_out, probs);
+  AUX_LAUNCH_CHECK(h, "gap_fc_softmax");
+  return TIAB_OK;
+}
+
+int tiab_u8_to_f16(tiab_handle_t h, const uint8_t* src, int N, int H, int W, int C, float scale, void* dst_f16, int Hd, int Wd,
+                   int dy, int dx, int Cd, void* stream) {
+  if (!h || !src || !dst_f16 || Cd < C) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  u8_to_f16_kernel<<<aux_grid(h, (long long)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(src, N, H, W, C, scale, (__half*)dst_f16, Hd,
+                                                                                             Wd, dy, dx, Cd);
+  AUX_LAUNCH_CHECK(h, "u8_to_f16");
+  return TIAB_OK;
+}
+
+}  // extern "C"
