@@ -1,0 +1,168 @@
+"""HoVer-Net (Graham et al. 2019) for the B200 — architecture definition + fp32 reference forward.
+
+Mirrors tiatoolbox/models/architecture/hovernet.py: same constructor arguments, same state_dict
+keys (so `hovernet_fast-pannuke` / `hovernet_original-*` checkpoints load unchanged), same
+`infer_batch` / `postproc` contract.  Layer structure restated from hovernet.py:30-262 (blocks) and
+:330-500 (network + decoder branches):
+
+  conv0: [TF-same pad (fast)] 7x7 s1 -> BN -> ReLU
+  d0..d3: pre-activation bottleneck residual blocks (3,4,6,3 units; 1x1 -> 3x3 (TF-same pad, stride on
+          unit 0) -> 1x1; 1x1 shortcut conv on unit 0), closing BN+ReLU
+  conv_bot 1x1 2048->1024
+  per branch (tp?, np, hv): u3 = up2x(d3)+crop(d2) -> conv k valid -> Dense(8 units, g=4) -> 1x1
+                            u2 = up2x(u3)+crop(d1) -> conv k valid -> Dense(4 units)      -> 1x1
+                            u1 = up2x(u2)+crop(d0) -> TF-same pad -> conv k ; u0 = BN-ReLU-1x1(+bias)
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from tiatoolbox_b200.models.architecture._params import ParamSpec, seeded_state_dict
+
+RES_CFG = (("d0", 64, (64, 64, 256), 3, 1), ("d1", 256, (128, 128, 512), 4, 2),
+           ("d2", 512, (256, 256, 1024), 6, 2), ("d3", 1024, (512, 512, 2048), 3, 2))
+
+
+def hovernet_spec(num_input_channels: int = 3, num_types: int | None = None, mode: str = "original") -> ParamSpec:
+    sp = ParamSpec()
+    sp.conv("conv0./", 64, num_input_channels, 7)
+    sp.bn("conv0.bn", 64)
+    for name, cin, (c1, c2, c3), units, stride in RES_CFG:
+        ch = cin
+        for i in range(units):
+            u = f"{name}.units.{i}"
+            if i > 0:
+                sp.bn(f"{u}.preact/bn", ch)
+            sp.conv(f"{u}.conv1", c1, ch, 1)
+            sp.bn(f"{u}.conv1/bn", c1)
+            sp.conv(f"{u}.conv2", c2, c1, 3)
+            sp.bn(f"{u}.conv2/bn", c2)
+            sp.conv(f"{u}.conv3", c3, c2, 1)
+            ch = c3
+        if cin != c3 or stride != 1:
+            sp.conv(f"{name}.shortcut", c3, cin, 1)
+        sp.bn(f"{name}.blk_bna.bn", c3)
+    sp.conv("conv_bot", 1024, 2048, 1)
+    k = 5 if mode == "original" else 3
+    branches = (["tp"] if num_types is not None else []) + ["np", "hv"]
+    for b in branches:
+        out_ch = num_types if b == "tp" else 2
+        for lvl, cin, cmid, units in (("u3", 1024, 256, 8), ("u2", 512, 128, 4)):
+            p = f"decoder.{b}.{lvl}"
+            sp.conv(f"{p}.conva", cmid, cin, k)
+            ch = cmid
+            for i in range(units):
+                u = f"{p}.dense.units.{i}"
+                sp.bn(f"{u}.preact_bna/bn", ch)
+                sp.conv(f"{u}.conv1", 128, ch, 1)
+                sp.bn(f"{u}.conv1/bn", 128)
+                sp[f"{u}.conv2.weight"] = ((32, 128 // 4, k, k), "conv")  # groups = 4
+                ch += 32
+            sp.bn(f"{p}.dense.blk_bna.bn", ch)
+            sp.conv(f"{p}.convf", ch, ch, 1)
+        sp.conv(f"decoder.{b}.u1.conva", 64, 256, k)
+        sp.bn(f"decoder.{b}.u0.bn", 64)
+        sp.conv(f"decoder.{b}.u0.conv", out_ch, 64, 1, bias=True)
+    sp["upsample2x.unpool_mat"] = ((2, 2), "ones")  # buffer of the reference's UpSample2x (utils.py:202-243)
+    return sp
+
+
+def tf_same_pad(size: int, ksize: int, stride: int) -> tuple[int, int]:
+    """(before, after) zero padding of TFSamepaddingLayer (hovernet.py:44-58)."""
+    pad = max(ksize - stride, 0) if size % stride == 0 else max(ksize - (size % stride), 0)
+    return pad // 2, pad - pad // 2
+
+
+def _bn(x, sd, name):
+    if sd.get("__calibrate__", False):  # test-weight calibration: adopt the batch statistics (see _params.calibrate)
+        sd[name + ".running_mean"] = x.mean(dim=(0, 2, 3)).detach()
+        sd[name + ".running_var"] = x.var(dim=(0, 2, 3), unbiased=False).detach() + 1e-3
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
+                        sd[name + ".bias"], False, 0.0, 1e-5)
+
+
+def _crop_to(x, ref):
+    dh, dw = x.shape[2] - ref.shape[2], x.shape[3] - ref.shape[3]
+    return x[:, :, dh // 2: x.shape[2] - (dh - dh // 2), dw // 2: x.shape[3] - (dw - dw // 2)]
+
+
+def _up2(x):
+    return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+
+
+def _residual_block(x, sd, name, units, stride):
+    shortcut = F.conv2d(x, sd[f"{name}.shortcut.weight"], stride=stride) if f"{name}.shortcut.weight" in sd else x
+    prev = x
+    for i in range(units):
+        u = f"{name}.units.{i}"
+        y = prev
+        if i > 0:
+            y = F.relu(_bn(y, sd, f"{u}.preact/bn"))
+        y = F.relu(_bn(F.conv2d(y, sd[f"{u}.conv1.weight"]), sd, f"{u}.conv1/bn"))
+        s = stride if i == 0 else 1
+        pb, pa = tf_same_pad(y.shape[2], 3, s)
+        y = F.pad(y, (pb, pa, pb, pa))
+        y = F.relu(_bn(F.conv2d(y, sd[f"{u}.conv2.weight"], stride=s), sd, f"{u}.conv2/bn"))
+        y = F.conv2d(y, sd[f"{u}.conv3.weight"])
+        prev = y + shortcut
+        shortcut = prev
+    return F.relu(_bn(prev, sd, f"{name}.blk_bna.bn"))
+
+
+def _dense_block(x, sd, name, units):
+    prev = x
+    for i in range(units):
+        u = f"{name}.units.{i}"
+        y = F.relu(_bn(prev, sd, f"{u}.preact_bna/bn"))
+        y = F.relu(_bn(F.conv2d(y, sd[f"{u}.conv1.weight"]), sd, f"{u}.conv1/bn"))
+        y = F.conv2d(y, sd[f"{u}.conv2.weight"], groups=4)
+        prev = torch.cat([_crop_to(prev, y), y], dim=1)
+    return F.relu(_bn(prev, sd, f"{name}.blk_bna.bn"))
+
+
+def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: int | None) -> OrderedDict:
+    """fp32 PyTorch restatement of HoVerNet.forward (hovernet.py:405-454).  x in [0, 255]."""
+    x = x_nchw / 255.0
+    if mode == "fast":
+        pb, pa = tf_same_pad(x.shape[2], 7, 1)
+        x = F.pad(x, (pb, pa, pb, pa))
+    d = F.relu(_bn(F.conv2d(x, sd["conv0./.weight"]), sd, "conv0.bn"))
+    feats = []
+    for name, _, _, units, stride in RES_CFG:
+        d = _residual_block(d, sd, name, units, stride)
+        feats.append(d)
+    feats[3] = F.conv2d(feats[3], sd["conv_bot.weight"])
+    c0, c1 = (184, 72) if mode == "original" else (92, 36)
+    d0 = feats[0][:, :, c0 // 2: feats[0].shape[2] - c0 // 2, c0 // 2: feats[0].shape[3] - c0 // 2]
+    d1 = feats[1][:, :, c1 // 2: feats[1].shape[2] - c1 // 2, c1 // 2: feats[1].shape[3] - c1 // 2]
+    k = 5 if mode == "original" else 3
+    out = OrderedDict()
+    for b in (["tp"] if num_types is not None else []) + ["np", "hv"]:
+        p = f"decoder.{b}"
+        u3 = _up2(feats[3]) + feats[2]
+        u3 = F.conv2d(u3, sd[f"{p}.u3.conva.weight"])
+        u3 = F.conv2d(_dense_block(u3, sd, f"{p}.u3.dense", 8), sd[f"{p}.u3.convf.weight"])
+        u2 = _up2(u3) + d1
+        u2 = F.conv2d(u2, sd[f"{p}.u2.conva.weight"])
+        u2 = F.conv2d(_dense_block(u2, sd, f"{p}.u2.dense", 4), sd[f"{p}.u2.convf.weight"])
+        u1 = _up2(u2) + d0
+        pb, pa = tf_same_pad(u1.shape[2], k, 1)
+        u1 = F.conv2d(F.pad(u1, (pb, pa, pb, pa)), sd[f"{p}.u1.conva.weight"])
+        u0 = F.relu(_bn(u1, sd, f"{p}.u0.bn"))
+        out[b] = F.conv2d(u0, sd[f"{p}.u0.conv.weight"], sd[f"{p}.u0.conv.bias"])
+    return out
+
+
+def hovernet_heads_reference(out: OrderedDict) -> tuple[torch.Tensor, ...]:
+    """Head activations of HoVerNet.infer_batch (hovernet.py:897-909): NHWC, np = softmax[..., 1:],
+    tp = argmax as float32, hv raw.  Returns (np, hv[, tp])."""
+    o = {k: v.permute(0, 2, 3, 1).contiguous() for k, v in out.items()}
+    o["np"] = F.softmax(o["np"], dim=-1)[..., 1:]
+    if "tp" in o:
+        tp = torch.argmax(F.softmax(o["tp"], dim=-1), dim=-1, keepdim=True).type(torch.float32)
+        return o["np"], o["hv"], tp
+    return o["np"], o["hv"]
