@@ -144,8 +144,10 @@ int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale,
 /* dst = relu?(src*scale + shift) -> fp16 (per-unit pre-activation of dense blocks, hovernet.py:84-86) */
 int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, const float* scale,
                  const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, void* stream);
-/* dst = relu?(bn?(up2x(a) + b[window])) (hovernet.py:440-451, unet.py:405-411) */
-int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, const void* b_f16, int Hb, int Wb, int by, int bx,
+/* dst = relu?(bn?(up2x(a[window]) + b[window])) (hovernet.py:440-451, unet.py:405-411); a is a Ha x Wa window at
+ * (ay, ax) of an Hag x Wag grid */
+int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Hag, int Wag, int ay, int ax, const void* b_f16,
+                      int Hb, int Wb, int by, int bx,
                       int N, int C, const float* scale, const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy,
                       int dx, void* dst_f32, void* stream);
 int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, void* dst_f16, void* stream);
@@ -156,6 +158,9 @@ int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int 
 /* global average pool + Linear + softmax (vanilla.py:312-316) */
 int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, const float* Wt, const float* bias, int ncls,
                         float* feat_out, float* probs, void* stream);
+/* HoVerNet.infer_batch head activations (hovernet.py:897-909) */
+int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv_logits, const float* tp_logits, int nt,
+                        long long rows, float* np_out, float* hv_out, float* tp_out, void* stream);
 int tiab_u8_to_f16(tiab_handle_t h, const uint8_t* src, int N, int H, int W, int C, float scale, void* dst_f16, int Hd, int Wd,
                    int dy, int dx, int Cd, void* stream);
 

@@ -1,0 +1,93 @@
+"""GPU parity of the HoVer-Net device plan (fp16 operands, fp32 accumulate) against
+ (a) the plain-PyTorch fp32 restatement of the forward (architecture/hovernet.py), run on the same GPU
+     with TF32 disabled, and
+ (b) the UNMODIFIED reference module's CPU outputs for the same seeded weights (tests/golden).
+Tolerance (north_star: 1e-3 relative): relative L2 error <= 1e-3 per output map and
+max|delta| <= 4e-3 * max|ref|; the argmax type map must agree on >= 99.5 % of pixels (ties between
+near-equal logits are the only admissible differences)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests.cnn_common import GOLDEN, hovernet_test_weights, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hv(built_lib):
+    import torch
+
+    from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = hovernet_test_weights("fast", 6)
+    plan = HoVerNetPlan(sd, batch=2, device="cuda:0", mode="fast", num_types=6)
+    tiles = he_tiles(2, 256, 256, seed=0)
+    return sd, plan, tiles
+
+
+def test_logits_match_fp32_reference_and_golden(hv):
+    import torch
+
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference
+
+    sd, plan, tiles = hv
+    x = torch.from_numpy(tiles).cuda()
+    plan.forward(x)
+    torch.cuda.synchronize()
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        ref = hovernet_forward_reference(sd_gpu, x.permute(0, 3, 1, 2).float(), "fast", 6)
+    gold = np.load(GOLDEN / "hovernet_golden.npz")
+    for b in ("tp", "np", "hv"):
+        got = plan.logits[b].cpu().numpy()
+        r = ref[b].permute(0, 2, 3, 1).cpu().numpy()
+        assert np.isfinite(got).all()
+        e = rel_l2(got, r)
+        m = np.abs(got - r).max() / np.abs(r).max()
+        print(f"{b}: rel_l2 {e:.2e}  max/max {m:.2e}")
+        assert e <= 1e-3 and m <= 4e-3, (b, e, m)
+        # the unmodified reference (CPU fp32) on the same weights, every 2nd pixel
+        g = gold[f"fast_logits_{b}"]
+        assert rel_l2(got[:, ::2, ::2], g) <= 1e-3
+
+
+def test_heads_match_reference_infer_batch(hv):
+    import torch
+
+    sd, plan, tiles = hv
+    np_o, hv_o, tp_o = plan.forward(torch.from_numpy(tiles).cuda())
+    torch.cuda.synchronize()
+    gold = np.load(GOLDEN / "hovernet_golden.npz")
+    assert np_o.shape == (2, 164, 164, 1) and hv_o.shape == (2, 164, 164, 2) and tp_o.shape == (2, 164, 164, 1)
+    assert np.abs(np_o[:1].cpu().numpy() - gold["fast_head_np"]).max() <= 1e-3
+    assert rel_l2(hv_o[:1].cpu().numpy(), gold["fast_head_hv"]) <= 1e-3
+    agree = (tp_o[:1].cpu().numpy() == gold["fast_head_tp"]).mean()
+    assert agree >= 0.995, agree
+
+
+def test_cuda_graph_replay_is_bit_identical_and_fast(hv):
+    import torch
+
+    sd, plan, tiles = hv
+    x = torch.from_numpy(tiles).cuda()
+    a = [t.clone() for t in plan.forward(x)]
+    plan.capture()
+    b = [t.clone() for t in plan.forward(x)]
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        plan.forward(x)
+    s.record()
+    for _ in range(10):
+        plan.forward(x)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f"hovernet_fast B=2: {ms:.3f} ms/step, {2 / ms * 1e3:.1f} patches/s, {plan.flops / ms / 1e9:.1f} TFLOP/s useful, "
+          f"{plan.num_launches} launches, {plan.bytes_allocated() / 1e6:.0f} MB buffers")

@@ -86,11 +86,12 @@ SIGNATURES = {
     "tiab_conv_gemm": (C.c_int, [_vp, C.POINTER(ConvDesc), _vp]),
     "tiab_im2col": (C.c_int, [_vp, _vp, C.c_int, C.c_float] + [C.c_int] * 12 + [_vp, C.c_int, _vp]),
     "tiab_bn_relu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_longlong, C.c_int, _vp, C.c_int, C.c_int, _vp]),
-    "tiab_upsample_add": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,
+    "tiab_upsample_add": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,
                                     C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_maxpool3x3s2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_pointwise_head": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "tiab_gap_fc_softmax": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "tiab_hovernet_heads": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_longlong, _vp, _vp, _vp, _vp]),
     "tiab_u8_to_f16": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "tiab_stain_set_path": (C.c_int, [_vp, C.c_int]),
     "tiab_last_launch_count": (C.c_int, [_vp]),

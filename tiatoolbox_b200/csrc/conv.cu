@@ -450,8 +450,8 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const void* __restrict__ s
 // hovernet.py:440-451 `upsample2x(d[-1]) + d[-2]`, unet.py:405-411.  Optional per-channel BN+ReLU on the sum
 // (UNet decoder pre-activation, unet.py:211-224).  dst may be a window of a larger (pre-padded) buffer.
 __global__ void __launch_bounds__(256)
-upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, const __half* __restrict__ b, int Hb, int Wb, int by,
-                    int bx, int Nimg, int C, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, int Hag, int Wag, int ay, int ax,
+                    const __half* __restrict__ b, int Hb, int Wb, int by, int bx, int Nimg, int C, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                     __half* __restrict__ dst, int Hd, int Wd, int dy, int dx, float* __restrict__ dst32) {
   const int Ho = 2 * Ha, Wo = 2 * Wa, c8 = C >> 3;
   const long long total = (long long)Nimg * Ho * Wo * c8;
@@ -462,7 +462,7 @@ upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, const __half* 
     r /= Wo;
     const int y = (int)(r % Ho);
     const int img = (int)(r / Ho);
-    uint4 qa = *reinterpret_cast<const uint4*>(a + ((long long)(img * Ha + (y >> 1)) * Wa + (x >> 1)) * C + cg);
+    uint4 qa = *reinterpret_cast<const uint4*>(a + ((long long)(img * Hag + (y >> 1) + ay) * Wag + (x >> 1) + ax) * C + cg);
     float v[8];
     const __half2* ha = reinterpret_cast<const __half2*>(&qa);
     for (int e = 0; e < 4; ++e) {
@@ -611,6 +611,30 @@ __global__ void __launch_bounds__(256) u8_to_f16_kernel(const uint8_t* __restric
     const int img = (int)(i / ((long long)W * H));
     __half* d = dst + ((long long)(img * Hd + y + dy) * Wd + x + dx) * Cd;
     for (int c = 0; c < C; ++c) d[c] = __float2half_rn((float)src[i * C + c] * scale);
+  }
+}
+
+// HoVer-Net head activations (hovernet.py:897-909): np = softmax(np_logits)[..., 1], hv raw, tp = argmax as float.
+__global__ void __launch_bounds__(256) hovernet_heads_kernel(const float* __restrict__ npl, const float* __restrict__ hvl,
+                                                             const float* __restrict__ tpl, int nt, long long rows,
+                                                             float* __restrict__ np_out, float* __restrict__ hv_out,
+                                                             float* __restrict__ tp_out) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const float l0 = npl[2 * r], l1 = npl[2 * r + 1];
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    np_out[r] = e1 / (e0 + e1);
+    hv_out[2 * r] = hvl[2 * r];
+    hv_out[2 * r + 1] = hvl[2 * r + 1];
+    if (tpl) {
+      int best = 0;
+      float bv = tpl[r * nt];
+      for (int j = 1; j < nt; ++j) {
+        float v = tpl[r * nt + j];
+        if (v > bv) bv = v, best = j;
+      }
+      tp_out[r] = (float)best;
+    }
   }
 }
 
@@ -780,14 +804,15 @@ int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, in
   return TIAB_OK;
 }
 
-int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, const void* b_f16, int Hb, int Wb, int by, int bx,
+int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Hag, int Wag, int ay, int ax, const void* b_f16,
+                      int Hb, int Wb, int by, int bx,
                       int N, int C, const float* scale, const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy,
                       int dx, void* dst_f32, void* stream) {
   if (!h || !a_f16 || !dst_f16 || (C & 7)) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   long long total = (long long)N * 4 * Ha * Wa * (C >> 3);
   upsample_add_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)a_f16, Ha, Wa, (const __half*)b_f16, Hb, Wb, by, bx, N, C, scale, shift, relu, (__half*)dst_f16, Hd, Wd, dy, dx,
+      (const __half*)a_f16, Ha, Wa, Hag, Wag, ay, ax, (const __half*)b_f16, Hb, Wb, by, bx, N, C, scale, shift, relu, (__half*)dst_f16, Hd, Wd, dy, dx,
       (float*)dst_f32);
   AUX_LAUNCH_CHECK(h, "upsample_add");
   return TIAB_OK;
@@ -822,6 +847,16 @@ int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C
   size_t sm = (size_t)(C + ncls) * sizeof(float);
   gap_fc_softmax_kernel<<<N, 256, sm, (cudaStream_t)stream>>>((const __half*)x_f16, HW, C, Wt, bias, ncls, feat_out, probs);
   AUX_LAUNCH_CHECK(h, "gap_fc_softmax");
+  return TIAB_OK;
+}
+
+int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv_logits, const float* tp_logits, int nt,
+                        long long rows, float* np_out, float* hv_out, float* tp_out, void* stream) {
+  if (!h || !np_logits || !hv_logits || !np_out || !hv_out || (tp_logits && (!tp_out || nt < 1))) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  hovernet_heads_kernel<<<aux_grid(h, rows, 256), 256, 0, (cudaStream_t)stream>>>(np_logits, hv_logits, tp_logits, nt, rows, np_out,
+                                                                                  hv_out, tp_out);
+  AUX_LAUNCH_CHECK(h, "hovernet_heads");
   return TIAB_OK;
 }
 

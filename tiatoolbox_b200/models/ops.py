@@ -69,9 +69,9 @@ def bn_relu(src, src_is_f32, ldsrc, coffsrc, scale, shift, relu, rows, c, dst, l
                                           int(relu), rows, c, dst.data_ptr(), lddst, coffdst, _stream(src.device)))
 
 
-def upsample_add(a, ha, wa, b, hb, wb, by, bx, n, c, scale, shift, relu, dst, hd, wd, dy, dx, dst32=None):
+def upsample_add(a, ha, wa, hag, wag, ay, ax, b, hb, wb, by, bx, n, c, scale, shift, relu, dst, hd, wd, dy, dx, dst32=None):
     h = _lib.handle(a.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_upsample_add(h, a.data_ptr(), ha, wa, _ptr(b), hb, wb, by, bx, n, c, _ptr(scale),
+    _lib.check(h, _lib.lib().tiab_upsample_add(h, a.data_ptr(), ha, wa, hag, wag, ay, ax, _ptr(b), hb, wb, by, bx, n, c, _ptr(scale),
                                                _ptr(shift), int(relu), dst.data_ptr(), hd, wd, dy, dx, _ptr(dst32),
                                                _stream(a.device)))
 
@@ -98,3 +98,9 @@ def u8_to_f16(src, n, h_, w_, c, scale, dst, hd, wd, dy, dx, cd):
     h = _lib.handle(src.device.index or 0)
     _lib.check(h, _lib.lib().tiab_u8_to_f16(h, src.data_ptr(), n, h_, w_, c, float(scale), dst.data_ptr(), hd, wd, dy, dx, cd,
                                             _stream(src.device)))
+
+
+def hovernet_heads(npl, hvl, tpl, nt, rows, np_out, hv_out, tp_out):
+    h = _lib.handle(npl.device.index or 0)
+    _lib.check(h, _lib.lib().tiab_hovernet_heads(h, npl.data_ptr(), hvl.data_ptr(), _ptr(tpl), nt, rows, np_out.data_ptr(),
+                                                 hv_out.data_ptr(), _ptr(tp_out), _stream(npl.device)))
