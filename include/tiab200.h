@@ -115,7 +115,9 @@ typedef struct {
   long long x_rows;
   long long x_ld;
   int cin;
-  const void* w;        /* fp16 [N, taps*ceil64(cin)] K-major (BN folded), row pitch w_ld elements */
+  int x_lo_off;         /* 0: fp16 operands.  >0: element offset of the residual plane x_lo = x - fp16(x); the GEMM
+                           then runs the 3-term split A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (w holds [W_hi|W_hi|W_lo] per tap) */
+  const void* w;        /* fp16 [N, taps*segments*ceil64(cin)] K-major (BN folded), row pitch w_ld elements */
   long long w_ld;
   int M, N, taps;
   int tap_off[TIAB_MAX_TAPS];
@@ -123,46 +125,49 @@ typedef struct {
   int Hd, Wd, dy, dx;
   int Hr, Wr, ry, rx;
   void* out16;
-  int ld16, coff16;
+  int ld16, coff16, lo16;     /* lo16: channel offset of the residual plane of out16 (0 = none) */
   void* out32;
   int ld32, coff32;
   void* out16b;
-  int ld16b, coff16b;
+  int ld16b, coff16b, lo16b;
   const void* scale2;   /* fp32 [N] */
   const void* shift2;   /* fp32 [N] */
   const void* bias;     /* fp32 [N] or NULL */
   const void* res32;    /* fp32 residual or NULL */
   const void* res16;    /* fp16 residual or NULL */
-  int ldres, coffres;
+  int ldres, coffres, reslo;
   int relu;
 } tiab_conv_desc_t;
 
 int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);
-/* explicit im2col (strided convs, 3-channel stems): out [N*Ho*Wo, Kpad] fp16, k = (kh*KW + kw)*C + c */
-int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int N, int H, int W, int C, int ldsrc,
-                int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int Kpad, void* stream);
-/* dst = relu?(src*scale + shift) -> fp16 (per-unit pre-activation of dense blocks, hovernet.py:84-86) */
-int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, const float* scale,
-                 const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, void* stream);
+/* explicit im2col (strided convs, 3-channel stems): out [N*Ho*Wo, ldout] fp16, k = (kh*KW + kw)*C + c, lo plane at +out_lo */
+int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int src_lo, int N, int H, int W, int C,
+                int ldsrc, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int ldout,
+                int Kpad, int out_lo, void* stream);
+/* dst = relu?(src*scale + shift) -> fp16(+lo) (per-unit pre-activation of dense blocks, hovernet.py:84-86) */
+int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, int src_lo, const float* scale,
+                 const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, int dst_lo,
+                 void* stream);
 /* dst = relu?(bn?(up2x(a[window]) + b[window])) (hovernet.py:440-451, unet.py:405-411); a is a Ha x Wa window at
  * (ay, ax) of an Hag x Wag grid */
-int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Hag, int Wag, int ay, int ax, const void* b_f16,
-                      int Hb, int Wb, int by, int bx,
-                      int N, int C, const float* scale, const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy,
-                      int dx, void* dst_f32, void* stream);
-int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, void* dst_f16, void* stream);
+int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Hag, int Wag, int ay, int ax, int lda, int a_lo,
+                      const void* b_f16, int Hb, int Wb, int by, int bx, int ldb, int b_lo, int N, int C, const float* scale,
+                      const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy, int dx, int ldd, int dst_lo,
+                      void* stream);
+int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, int lds, int src_lo, void* dst_f16,
+                      int Hd, int Wd, int dy, int dx, int ldd, int dst_lo, void* stream);
 /* out[p, j] = sum_c relu?(x[p,c]*scale[c]+shift[c]) * Wt[j,c] + bias[j], nout <= 16 (hovernet.py:487-497, unet.py:353) */
-int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int C, int ldx, const float* scale,
+int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int C, int ldx, int x_lo, const float* scale,
                         const float* shift, int relu, const float* Wt, const float* bias, int nout, float* out, int ldout,
                         int coffout, void* stream);
 /* global average pool + Linear + softmax (vanilla.py:312-316) */
-int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, const float* Wt, const float* bias, int ncls,
-                        float* feat_out, float* probs, void* stream);
+int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, int ldx, int x_lo, const float* Wt,
+                        const float* bias, int ncls, float* feat_out, float* probs, void* stream);
 /* HoVerNet.infer_batch head activations (hovernet.py:897-909) */
 int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv_logits, const float* tp_logits, int nt,
                         long long rows, float* np_out, float* hv_out, float* tp_out, void* stream);
-int tiab_u8_to_f16(tiab_handle_t h, const uint8_t* src, int N, int H, int W, int C, float scale, void* dst_f16, int Hd, int Wd,
-                   int dy, int dx, int Cd, void* stream);
+/* UNetModel.infer_batch tail (unet.py:458-465): softmax -> bilinear x2 -> centre crop */
+int tiab_softmax_up2_crop(tiab_handle_t h, const float* logits, int N, int H, int W, int C, float* out, void* stream);
 
 /* Force one of the two device paths (testing / benchmarking): 0 = auto, 1 = fused one-CTA-per-patch
  * kernel (requires H*W*3 <= 196608 and H*W % 16 == 0), 2 = multi-pass general path. */

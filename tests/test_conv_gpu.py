@@ -129,3 +129,32 @@ def test_conv_relu_fp16_residual_and_many_tiles(ops):
     torch.cuda.synchronize()
     ms = start.elapsed_time(end) / 10
     print(f"conv3x3 256->256 @66x66x4: {ms*1e3:.1f} us, {op.flops/ms/1e9:.1f} TFLOP/s")
+
+
+@pytest.mark.parametrize("m,k,n", [(1000, 192, 64), (515, 288, 128)])
+def test_split_precision_gemm(ops, m, k, n):
+    """3-term split (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo): matches the full fp32 product to ~1e-6 relative,
+    and writes hi/lo output planes whose sum carries the fp32 result."""
+    import torch
+
+    from tiatoolbox_b200.models.plan import pack_weight
+
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    xf = torch.randn(m, k, device=dev)
+    w = torch.randn(n, k, device=dev) / k**0.5
+    x = torch.zeros(m, 2 * k, dtype=torch.float16, device=dev)
+    x[:, :k] = xf.half()
+    x[:, k:] = (xf - xf.half().float()).half()
+    wp = pack_weight(w.reshape(n, k, 1, 1), split=True, device=dev)
+    out32 = torch.zeros(m, n, device=dev)
+    out16 = torch.zeros(m, 2 * n, dtype=torch.float16, device=dev)
+    op = ops.ConvOp(x=x, x_rows=m, x_ld=2 * k, x_lo_off=k, cin=k, w=wp, taps=[0], M=m, N=n, grid=(1, m), window=(0, 1, 0, m),
+                    dst_geom=(1, m, 0, 0), out32=out32, ld32=n, out16=out16, ld16=2 * n, lo16=n)
+    op()
+    torch.cuda.synchronize()
+    ref = (xf.double() @ w.double().t()).float()
+    scale = ref.abs().max().item()
+    assert (out32 - ref).abs().max().item() < 2e-5 * scale
+    recon = out16[:, :n].float() + out16[:, n:].float()
+    assert (recon - ref).abs().max().item() < 2e-5 * scale

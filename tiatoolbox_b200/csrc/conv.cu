@@ -63,6 +63,8 @@ struct ConvParams {
   const __half* res16;
   int ldres, coffres;
   int relu;
+  int nseg;               // 1: fp16 operands ; 3: split-fp16 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo ~ fp32 operands)
+  int lo16, lo16b, reslo; // channel offsets of the residual ("lo") planes of out16 / out16b / res16 (0 = none)
   int num_m_tiles, num_n_tiles;
 };
 
@@ -154,7 +156,8 @@ struct ConvSmem {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using S = ConvSmem<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -168,10 +171,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int kiters = p.taps * p.kchunks;
+  const int kiters = p.taps * p.nseg * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
@@ -206,15 +210,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         for (int t = 0; t < p.taps; ++t) {
           const int row = m0 + p.tap_off[t];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbarrier_wait(&empty_bar[s], ph ^ 1u);
-            mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
-            uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-            tma_load_2d(a_dst, &tmA, kc * BLOCK_K, row, &full_bar[s]);
-            tma_load_2d(a_dst + S::A_BYTES, &tmB, (t * p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
-            if (++s == S::STAGES) {
-              s = 0;
-              ph ^= 1u;
+          for (int seg = 0; seg < p.nseg; ++seg) {
+            const CUtensorMap* am = (seg == 1) ? &tmA2 : &tmA;  // segment 1 multiplies the residual plane A_lo
+            const int kbase = (t * p.nseg + seg) * p.kchunks;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              mbarrier_wait(&empty_bar[s], ph ^ 1u);
+              mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
+              uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+              tma_load_2d(a_dst, am, kc * BLOCK_K, row, &full_bar[s]);
+              tma_load_2d(a_dst + S::A_BYTES, &tmB, (kbase + kc) * BLOCK_K, n0, &full_bar[s]);
+              if (++s == S::STAGES) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
           }
         }
@@ -318,6 +326,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[j + 2 * e] += f.x;
                 v[j + 2 * e + 1] += f.y;
               }
+              if (p.reslo) {
+                uint4 ql = *reinterpret_cast<const uint4*>(rp + p.reslo + j);
+                const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __half22float2(l2[e]);
+                  v[j + 2 * e] += f.x;
+                  v[j + 2 * e + 1] += f.y;
+                }
+              }
             }
           }
           if (p.relu) {
@@ -338,22 +356,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
               *reinterpret_cast<uint4*>(op + j) = q;
+              if (p.lo16) {
+                uint4 ql;
+                __half2* l2 = reinterpret_cast<__half2*>(&ql);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 hf = __half22float2(h2[e]);
+                  l2[e] = __floats2half2_rn(v[j + 2 * e] - hf.x, v[j + 2 * e + 1] - hf.y);
+                }
+                *reinterpret_cast<uint4*>(op + p.lo16 + j) = ql;
+              }
             }
           }
           if (p.out16b) {
             __half* op = p.out16b + drow * p.ld16b + p.coff16b + n;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              uint4 q;
+              uint4 q, ql;
               __half2* h2 = reinterpret_cast<__half2*>(&q);
+              __half2* l2 = reinterpret_cast<__half2*>(&ql);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int c = n + j + 2 * e;
                 float a0 = fmaxf(fmaf(v[j + 2 * e], __ldg(p.scale2 + c), __ldg(p.shift2 + c)), 0.f);
                 float a1 = fmaxf(fmaf(v[j + 2 * e + 1], __ldg(p.scale2 + c + 1), __ldg(p.shift2 + c + 1)), 0.f);
                 h2[e] = __floats2half2_rn(a0, a1);
+                float2 hf = __half22float2(h2[e]);
+                l2[e] = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
               }
               *reinterpret_cast<uint4*>(op + j) = q;
+              if (p.lo16b) *reinterpret_cast<uint4*>(op + p.lo16b + j) = ql;
             }
           }
         }
@@ -377,14 +409,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// auxiliary kernels (memory-bound glue between the GEMMs)
+// auxiliary kernels (memory-bound glue between the GEMMs).
+// Activations may carry a second fp16 plane ("lo" = x - fp16(x)) at a fixed channel offset so that
+// hi + lo represents the value to ~22 bits (split-precision mode); an offset of 0 means "no lo plane".
 // ---------------------------------------------------------------------------------------------
-// Explicit im2col for strided convs / 3-channel stems: out[m, t*Cin + c] (fp16, row pitch Kpad, zero padded)
-// from an NHWC source that is fp16 or uint8 (uint8 is scaled by `u8_scale`, e.g. 1/255).
-__global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ src, int src_is_u8, float u8_scale, int Nimg,
-                                                     int H, int W, int C, int ldsrc, int KH, int KW, int stride,
+__device__ __forceinline__ void load8(const __half* p, int lo, float (&v)[8]) {
+  uint4 q = *reinterpret_cast<const uint4*>(p);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __half22float2(h2[e]);
+    v[2 * e] = f.x, v[2 * e + 1] = f.y;
+  }
+  if (lo) {
+    uint4 ql = *reinterpret_cast<const uint4*>(p + lo);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(l2[e]);
+      v[2 * e] += f.x, v[2 * e + 1] += f.y;
+    }
+  }
+}
+__device__ __forceinline__ void store8(__half* p, int lo, const float (&v)[8]) {
+  uint4 q, ql;
+  __half2* h2 = reinterpret_cast<__half2*>(&q);
+  __half2* l2 = reinterpret_cast<__half2*>(&ql);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    float2 hf = __half22float2(h2[e]);
+    l2[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+  }
+  *reinterpret_cast<uint4*>(p) = q;
+  if (lo) *reinterpret_cast<uint4*>(p + lo) = ql;
+}
+
+// Explicit im2col for strided convs / 3-channel stems: out[m, (kh*KW + kw)*C + c] (row pitch ldout, K zero padded to
+// Kpad, lo plane at +out_lo) from an NHWC source that is fp16 (+lo plane) or uint8 (scaled by u8_scale).
+__global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ src, int src_is_u8, float u8_scale, int src_lo,
+                                                     int Nimg, int H, int W, int C, int ldsrc, int KH, int KW, int stride,
                                                      int pad_t, int pad_l, int Ho, int Wo, __half* __restrict__ out,
-                                                     int Kpad) {
+                                                     int ldout, int Kpad, int out_lo) {
   const long long total = (long long)Nimg * Ho * Wo * Kpad;
   const int K = KH * KW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -399,20 +465,27 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ sr
       const int y = yo * stride - pad_t + kh, x = xo * stride - pad_l + kw;
       if (y >= 0 && y < H && x >= 0 && x < W) {
         const long long off = ((long long)(img * H + y) * W + x) * ldsrc + c;
-        v = src_is_u8 ? (float)reinterpret_cast<const uint8_t*>(src)[off] * u8_scale
-                      : __half2float(reinterpret_cast<const __half*>(src)[off]);
+        if (src_is_u8) {
+          v = (float)reinterpret_cast<const uint8_t*>(src)[off] * u8_scale;
+        } else {
+          const __half* sp = reinterpret_cast<const __half*>(src);
+          v = __half2float(sp[off]);
+          if (src_lo) v += __half2float(sp[off + src_lo]);
+        }
       }
     }
-    out[i] = __float2half_rn(v);
+    const __half hi = __float2half_rn(v);
+    out[m * ldout + k] = hi;
+    if (out_lo) out[m * ldout + out_lo + k] = __float2half_rn(v - __half2float(hi));
   }
 }
 
-// y = relu(x * scale[c] + shift[c]) over a window of an NHWC tensor (fp32 or fp16 source) -> fp16.
-// Used for the per-unit pre-activation of HoVer-Net's dense blocks (hovernet.py:84-86).
+// y = relu?(x * scale[c] + shift[c]) over C channels of `rows` rows (fp32 or fp16(+lo) source) -> fp16(+lo).
+// Per-unit pre-activation of HoVer-Net's dense blocks (hovernet.py:84-86).
 __global__ void __launch_bounds__(256) bn_relu_kernel(const void* __restrict__ src, int src_is_f32, int ldsrc, int coffsrc,
-                                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      int relu, long long rows, int C, __half* __restrict__ dst, int lddst,
-                                                      int coffdst) {
+                                                      int src_lo, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, int relu, long long rows, int C,
+                                                      __half* __restrict__ dst, int lddst, int coffdst, int dst_lo) {
   const int c8 = C >> 3;
   const long long total = rows * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -424,35 +497,24 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const void* __restrict__ s
       float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
       v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
     } else {
-      uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + r * ldsrc + coffsrc + cg);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(h2[e]);
-        v[2 * e] = f.x, v[2 * e + 1] = f.y;
-      }
+      load8(reinterpret_cast<const __half*>(src) + r * ldsrc + coffsrc + cg, src_lo, v);
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-    for (int e = 0; e < 4; ++e) {
-      float a0 = v[2 * e], a1 = v[2 * e + 1];
-      if (scale) {
-        a0 = fmaf(a0, scale[cg + 2 * e], shift[cg + 2 * e]);
-        a1 = fmaf(a1, scale[cg + 2 * e + 1], shift[cg + 2 * e + 1]);
-      }
-      if (relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
-      oh[e] = __floats2half2_rn(a0, a1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (scale) v[e] = fmaf(v[e], scale[cg + e], shift[cg + e]);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
     }
-    *reinterpret_cast<uint4*>(dst + r * lddst + coffdst + cg) = o;
+    store8(dst + r * lddst + coffdst + cg, dst_lo, v);
   }
 }
 
-// dst[n, y, x, :] = up2x(a)[n, y, x, :] + b[n, y + by, x + bx, :]   (nearest-neighbour 2x, NHWC fp16)
-// hovernet.py:440-451 `upsample2x(d[-1]) + d[-2]`, unet.py:405-411.  Optional per-channel BN+ReLU on the sum
-// (UNet decoder pre-activation, unet.py:211-224).  dst may be a window of a larger (pre-padded) buffer.
+// dst[n, y+dy, x+dx, :] = relu?(bn?(up2x(a window)[n, y, x, :] + b[n, y+by, x+bx, :]))  (nearest 2x, NHWC fp16(+lo))
+// hovernet.py:440-451 `upsample2x(d[-1]) + d[-2]`, unet.py:405-411 (+ the decoder's BN-ReLU pre-activation, :211-224).
 __global__ void __launch_bounds__(256)
-upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, int Hag, int Wag, int ay, int ax,
-                    const __half* __restrict__ b, int Hb, int Wb, int by, int bx, int Nimg, int C, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                    __half* __restrict__ dst, int Hd, int Wd, int dy, int dx, float* __restrict__ dst32) {
+upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, int Hag, int Wag, int ay, int ax, int lda, int a_lo,
+                    const __half* __restrict__ b, int Hb, int Wb, int by, int bx, int ldb, int b_lo, int Nimg, int C,
+                    const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ dst,
+                    int Hd, int Wd, int dy, int dx, int ldd, int dst_lo) {
   const int Ho = 2 * Ha, Wo = 2 * Wa, c8 = C >> 3;
   const long long total = (long long)Nimg * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -462,45 +524,27 @@ upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, int Hag, int W
     r /= Wo;
     const int y = (int)(r % Ho);
     const int img = (int)(r / Ho);
-    uint4 qa = *reinterpret_cast<const uint4*>(a + ((long long)(img * Hag + (y >> 1) + ay) * Wag + (x >> 1) + ax) * C + cg);
     float v[8];
-    const __half2* ha = reinterpret_cast<const __half2*>(&qa);
-    for (int e = 0; e < 4; ++e) {
-      float2 fa = __half22float2(ha[e]);
-      v[2 * e] = fa.x, v[2 * e + 1] = fa.y;
-    }
+    load8(a + ((long long)(img * Hag + (y >> 1) + ay) * Wag + (x >> 1) + ax) * lda + cg, a_lo, v);
     if (b) {
-      uint4 qb = *reinterpret_cast<const uint4*>(b + ((long long)(img * Hb + y + by) * Wb + (x + bx)) * C + cg);
-      const __half2* hb = reinterpret_cast<const __half2*>(&qb);
-      for (int e = 0; e < 4; ++e) {
-        float2 fb = __half22float2(hb[e]);
-        v[2 * e] += fb.x, v[2 * e + 1] += fb.y;
-      }
+      float w[8];
+      load8(b + ((long long)(img * Hb + y + by) * Wb + (x + bx)) * ldb + cg, b_lo, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += w[e];
     }
-    const long long drow = (long long)(img * Hd + y + dy) * Wd + (x + dx);
-    if (dst32) {
-      float* d32 = dst32 + drow * C + cg;
-      *reinterpret_cast<float4*>(d32) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(d32 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (scale) v[e] = fmaf(v[e], scale[cg + e], shift[cg + e]);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-    for (int e = 0; e < 4; ++e) {
-      float a0 = v[2 * e], a1 = v[2 * e + 1];
-      if (scale) {
-        a0 = fmaf(a0, scale[cg + 2 * e], shift[cg + 2 * e]);
-        a1 = fmaf(a1, scale[cg + 2 * e + 1], shift[cg + 2 * e + 1]);
-      }
-      if (relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f);
-      oh[e] = __floats2half2_rn(a0, a1);
-    }
-    *reinterpret_cast<uint4*>(dst + drow * C + cg) = o;
+    store8(dst + ((long long)(img * Hd + y + dy) * Wd + (x + dx)) * ldd + cg, dst_lo, v);
   }
 }
 
-// 3x3 stride-2 pad-1 max pool, NHWC fp16 (torchvision ResNet stem).
-__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ src, int Nimg, int H, int W, int C,
-                                                           __half* __restrict__ dst, int Ho, int Wo) {
+// 3x3 stride-2 pad-1 max pool, NHWC fp16(+lo) (torchvision ResNet stem), destination may be a padded window.
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ src, int Nimg, int H, int W, int C, int lds,
+                                                           int src_lo, __half* __restrict__ dst, int Ho, int Wo, int Hd, int Wd,
+                                                           int dy, int dx, int ldd, int dst_lo) {
   const int c8 = C >> 3;
   const long long total = (long long)Nimg * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -511,28 +555,24 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restr
     const int yo = (int)(r % Ho);
     const int img = (int)(r / Ho);
     float m[8];
-    for (int e = 0; e < 8; ++e) m[e] = -65504.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -3.0e38f;
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
         const int y = 2 * yo - 1 + ky, x = 2 * xo - 1 + kx;
         if (y < 0 || y >= H || x < 0 || x >= W) continue;
-        uint4 q = *reinterpret_cast<const uint4*>(src + ((long long)(img * H + y) * W + x) * C + cg);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-        for (int e = 0; e < 4; ++e) {
-          float2 f = __half22float2(h2[e]);
-          m[2 * e] = fmaxf(m[2 * e], f.x), m[2 * e + 1] = fmaxf(m[2 * e + 1], f.y);
-        }
+        float v[8];
+        load8(src + ((long long)(img * H + y) * W + x) * lds + cg, src_lo, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
       }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(m[2 * e], m[2 * e + 1]);
-    *reinterpret_cast<uint4*>(dst + ((long long)(img * Ho + yo) * Wo + xo) * C + cg) = o;
+    store8(dst + ((long long)(img * Hd + yo + dy) * Wd + xo + dx) * ldd + cg, dst_lo, m);
   }
 }
 
-// Small-N pointwise head: out[p, j] = sum_c relu(x[p,c]*scale[c]+shift[c]) * Wt[j, c] + b[j], j < NOUT <= 16, fp32 out.
+// Small-N pointwise head: out[p, j] = sum_c relu?(x[p,c]*scale[c]+shift[c]) * Wt[j, c] + b[j], j < nout <= 16, fp32 out.
 // HoVer-Net u0 (hovernet.py:487-497: BN, ReLU, 1x1 conv with bias) and the UNet clf (unet.py:353).
-__global__ void __launch_bounds__(128) pointwise_head_kernel(const __half* __restrict__ x, long long rows, int C, int ldx,
+__global__ void __launch_bounds__(128) pointwise_head_kernel(const __half* __restrict__ x, long long rows, int C, int ldx, int x_lo,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              int relu, const float* __restrict__ Wt, const float* __restrict__ b,
                                                              int nout, float* __restrict__ out, int ldout, int coffout) {
@@ -548,38 +588,40 @@ __global__ void __launch_bounds__(128) pointwise_head_kernel(const __half* __res
   __syncthreads();
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
     float acc[16];
+#pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
     const __half* xp = x + r * ldx;
     for (int c = 0; c < C; c += 8) {
-      uint4 q = *reinterpret_cast<const uint4*>(xp + c);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
       float v[8];
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(h2[e]);
-        v[2 * e] = f.x, v[2 * e + 1] = f.y;
-      }
+      load8(xp + c, x_lo, v);
+#pragma unroll
       for (int e = 0; e < 8; ++e) {
         float a = fmaf(v[e], ss[c + e], st[c + e]);
         if (relu) a = fmaxf(a, 0.f);
-        for (int j = 0; j < nout; ++j) acc[j] = fmaf(a, sw[j * C + c + e], acc[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nout) acc[j] = fmaf(a, sw[j * C + c + e], acc[j]);
       }
     }
     for (int j = 0; j < nout; ++j) out[r * ldout + coffout + j] = acc[j] + (b ? b[j] : 0.f);
   }
 }
 
-// Global-average-pool + Linear + softmax (vanilla.py:312-316): x NHWC fp16 [N, HW, C] -> probs [N, ncls] fp32.
-__global__ void __launch_bounds__(256) gap_fc_softmax_kernel(const __half* __restrict__ x, int HW, int C,
+// Global-average-pool + Linear + softmax (vanilla.py:312-316): x NHWC fp16(+lo) [N, HW, ldx] -> probs [N, ncls] fp32.
+__global__ void __launch_bounds__(256) gap_fc_softmax_kernel(const __half* __restrict__ x, int HW, int C, int ldx, int x_lo,
                                                              const float* __restrict__ Wt, const float* __restrict__ b,
                                                              int ncls, float* __restrict__ feat_out, float* __restrict__ probs) {
   extern __shared__ float sh[];  // feat[C] | logits[ncls]
   float* feat = sh;
   float* logits = sh + C;
   const int img = blockIdx.x;
-  const __half* xp = x + (long long)img * HW * C;
+  const __half* xp = x + (long long)img * HW * ldx;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int i = 0; i < HW; ++i) s += __half2float(xp[(long long)i * C + c]);
+    for (int i = 0; i < HW; ++i) {
+      s += __half2float(xp[(long long)i * ldx + c]);
+      if (x_lo) s += __half2float(xp[(long long)i * ldx + x_lo + c]);
+    }
     feat[c] = s / (float)HW;
     if (feat_out) feat_out[(long long)img * C + c] = feat[c];
   }
@@ -598,19 +640,6 @@ __global__ void __launch_bounds__(256) gap_fc_softmax_kernel(const __half* __res
     float z = 0.f;
     for (int j = 0; j < ncls; ++j) z += expf(logits[j] - m);
     for (int j = 0; j < ncls; ++j) probs[(long long)img * ncls + j] = expf(logits[j] - m) / z;
-  }
-}
-
-// uint8 NHWC -> fp16 NHWC with scale, optionally into a window of a zero-padded buffer and with channel padding.
-__global__ void __launch_bounds__(256) u8_to_f16_kernel(const uint8_t* __restrict__ src, int Nimg, int H, int W, int C, float scale,
-                                                        __half* __restrict__ dst, int Hd, int Wd, int dy, int dx, int Cd) {
-  const long long total = (long long)Nimg * H * W;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int img = (int)(i / ((long long)W * H));
-    __half* d = dst + ((long long)(img * Hd + y + dy) * Wd + x + dx) * Cd;
-    for (int c = 0; c < C; ++c) d[c] = __float2half_rn((float)src[i * C + c] * scale);
   }
 }
 
@@ -635,6 +664,43 @@ __global__ void __launch_bounds__(256) hovernet_heads_kernel(const float* __rest
       }
       tp_out[r] = (float)best;
     }
+  }
+}
+
+// UNetModel.infer_batch tail (unet.py:458-465): softmax over C logits -> bilinear x2 (align_corners=False) -> centre crop
+// to (H, W) of the (2H, 2W) map -> NHWC probabilities.  logits fp32 [N, H, W, C]; out fp32 [N, H, W, C].
+__global__ void __launch_bounds__(256) softmax_up2_crop_kernel(const float* __restrict__ lg, int Nimg, int H, int W, int C,
+                                                               float* __restrict__ out) {
+  const long long total = (long long)Nimg * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % W);
+    const int yo = (int)((i / W) % H);
+    const int img = (int)(i / ((long long)W * H));
+    // output pixel (yo, xo) of the crop = pixel (yo + H/2, xo + W/2) of the 2x map
+    const int Y = yo + H / 2, X = xo + W / 2;
+    // align_corners=False: src = (dst + 0.5)/2 - 0.5, clamped at 0
+    float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
+    int y0 = (int)sy, x0 = (int)sx;
+    int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float fy = sy - (float)y0, fx = sx - (float)x0;
+    float acc[8];
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+    const float wy[2] = {1.f - fy, fy}, wx[2] = {1.f - fx, fx};
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const float* p = lg + ((long long)(img * H + ys[a]) * W + xs[b]) * C;
+        float m = p[0];
+        for (int c = 1; c < C; ++c) m = fmaxf(m, p[c]);
+        float z = 0.f, e[8];
+        for (int c = 0; c < C; ++c) {
+          e[c] = expf(p[c] - m);
+          z += e[c];
+        }
+        const float wgt = wy[a] * wx[b] / z;
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(wgt, e[c], acc[c]);
+      }
+    for (int c = 0; c < C; ++c) out[i * C + c] = acc[c];
   }
 }
 
@@ -687,7 +753,8 @@ static int make_map_2d(tiab_ctx* h, CUtensorMap* map, const void* base, long lon
 }
 
 template <int BN>
-static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& tb, ConvParams& p, cudaStream_t s) {
+static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, ConvParams& p,
+                       cudaStream_t s) {
   using S = ConvSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -698,7 +765,7 @@ static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& tb
   p.num_n_tiles = p.N / BN;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = std::min(tiles, h->sm_count);
-  conv_gemm_kernel<BN><<<grid, CONV_THREADS, S::TOTAL, s>>>(ta, tb, p);
+  conv_gemm_kernel<BN><<<grid, CONV_THREADS, S::TOTAL, s>>>(ta, ta2, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     h->err = std::string("conv_gemm launch: ") + cudaGetErrorString(e);
@@ -736,21 +803,25 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
     h->err = "tiab_conv_gemm: N (output channels) must be a multiple of 32";
     return TIAB_E_INVALID;
   }
-  if (d->x_rows + 0 < 1 || d->Hin <= 0 || d->Win <= 0) {
+  if (d->x_rows < 1 || d->Hin <= 0 || d->Win <= 0) {
     h->err = "tiab_conv_gemm: invalid grid";
     return TIAB_E_INVALID;
   }
+  const int nseg = d->x_lo_off ? 3 : 1;
   const int kchunks = (d->cin + BLOCK_K - 1) / BLOCK_K;
-  if (d->w_ld < (long long)d->taps * kchunks * BLOCK_K) {
-    h->err = "tiab_conv_gemm: weight pitch smaller than taps*ceil64(cin)";
+  const long long kcols = (long long)d->taps * nseg * kchunks * BLOCK_K;
+  if (d->w_ld < kcols) {
+    h->err = "tiab_conv_gemm: weight pitch smaller than taps*segments*ceil64(cin)";
     return TIAB_E_INVALID;
   }
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   const int BN = (d->N % 256 == 0) ? 256 : (d->N % 128 == 0) ? 128 : (d->N % 64 == 0) ? 64 : 32;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, ta2, tb;
   int rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M);
   if (rc) return rc;
-  rc = make_map_2d(h, &tb, d->w, d->N, (int)std::min<long long>(d->w_ld, (long long)d->taps * kchunks * BLOCK_K), d->w_ld, BN);
+  rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map_2d(h, &tb, d->w, d->N, (int)kcols, d->w_ld, BN);
   if (rc) return rc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -758,17 +829,19 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   p.N = d->N;
   p.taps = d->taps;
   p.kchunks = kchunks;
+  p.nseg = nseg;
   for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t];
   p.Hin = d->Hin, p.Win = d->Win;
   p.y0 = d->y0, p.y1 = d->y1, p.x0 = d->x0, p.x1 = d->x1;
   p.Hd = d->Hd, p.Wd = d->Wd, p.dy = d->dy, p.dx = d->dx;
   p.Hr = d->Hr, p.Wr = d->Wr, p.ry = d->ry, p.rx = d->rx;
-  p.out16 = (__half*)d->out16, p.ld16 = d->ld16, p.coff16 = d->coff16;
+  p.out16 = (__half*)d->out16, p.ld16 = d->ld16, p.coff16 = d->coff16, p.lo16 = d->lo16;
   p.out32 = (float*)d->out32, p.ld32 = d->ld32, p.coff32 = d->coff32;
-  p.out16b = (__half*)d->out16b, p.ld16b = d->ld16b, p.coff16b = d->coff16b;
+  p.out16b = (__half*)d->out16b, p.ld16b = d->ld16b, p.coff16b = d->coff16b, p.lo16b = d->lo16b;
   p.scale2 = (const float*)d->scale2, p.shift2 = (const float*)d->shift2;
   p.bias = (const float*)d->bias;
   p.res32 = (const float*)d->res32, p.res16 = (const __half*)d->res16, p.ldres = d->ldres, p.coffres = d->coffres;
+  p.reslo = d->reslo;
   p.relu = d->relu;
   if (p.out16b && (!p.scale2 || !p.shift2)) {
     h->err = "tiab_conv_gemm: out16b needs scale2/shift2";
@@ -776,76 +849,83 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (BN) {
-    case 256: return launch_conv<256>(h, ta, tb, p, s);
-    case 128: return launch_conv<128>(h, ta, tb, p, s);
-    case 64: return launch_conv<64>(h, ta, tb, p, s);
-    default: return launch_conv<32>(h, ta, tb, p, s);
+    case 256: return launch_conv<256>(h, ta, ta2, tb, p, s);
+    case 128: return launch_conv<128>(h, ta, ta2, tb, p, s);
+    case 64: return launch_conv<64>(h, ta, ta2, tb, p, s);
+    default: return launch_conv<32>(h, ta, ta2, tb, p, s);
   }
 }
 
-int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int N, int H, int W, int C, int ldsrc,
-                int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int Kpad, void* stream) {
-  if (!h || !src || !out_f16 || Kpad < KH * KW * C) return TIAB_E_INVALID;
+int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int src_lo, int N, int H, int W, int C,
+                int ldsrc, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int ldout,
+                int Kpad, int out_lo, void* stream) {
+  if (!h || !src || !out_f16 || Kpad < KH * KW * C || ldout < Kpad) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   long long total = (long long)N * Ho * Wo * Kpad;
-  im2col_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_u8, u8_scale, N, H, W, C, ldsrc, KH, KW,
-                                                                           stride, pad_t, pad_l, Ho, Wo, (__half*)out_f16, Kpad);
+  im2col_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_u8, u8_scale, src_lo, N, H, W, C, ldsrc,
+                                                                           KH, KW, stride, pad_t, pad_l, Ho, Wo,
+                                                                           (__half*)out_f16, ldout, Kpad, out_lo);
   AUX_LAUNCH_CHECK(h, "im2col");
   return TIAB_OK;
 }
 
-int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, const float* scale,
-                 const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, void* stream) {
-  if (!h || !src || !dst_f16 || (C & 7) || (ldsrc & 7) || (lddst & 7) || (coffsrc & 7) || (coffdst & 7)) return TIAB_E_INVALID;
+int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, int coffsrc, int src_lo, const float* scale,
+                 const float* shift, int relu, long long rows, int C, void* dst_f16, int lddst, int coffdst, int dst_lo,
+                 void* stream) {
+  if (!h || !src || !dst_f16 || (C & 7) || (ldsrc & 7) || (lddst & 7) || (coffsrc & 7) || (coffdst & 7) || (src_lo & 7) || (dst_lo & 7))
+    return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
-  bn_relu_kernel<<<aux_grid(h, rows * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_f32, ldsrc, coffsrc, scale, shift,
-                                                                                       relu, rows, C, (__half*)dst_f16, lddst, coffdst);
+  bn_relu_kernel<<<aux_grid(h, rows * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_f32, ldsrc, coffsrc, src_lo, scale,
+                                                                                       shift, relu, rows, C, (__half*)dst_f16, lddst,
+                                                                                       coffdst, dst_lo);
   AUX_LAUNCH_CHECK(h, "bn_relu");
   return TIAB_OK;
 }
 
-int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Hag, int Wag, int ay, int ax, const void* b_f16,
-                      int Hb, int Wb, int by, int bx,
-                      int N, int C, const float* scale, const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy,
-                      int dx, void* dst_f32, void* stream) {
-  if (!h || !a_f16 || !dst_f16 || (C & 7)) return TIAB_E_INVALID;
+int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Hag, int Wag, int ay, int ax, int lda, int a_lo,
+                      const void* b_f16, int Hb, int Wb, int by, int bx, int ldb, int b_lo, int N, int C, const float* scale,
+                      const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy, int dx, int ldd, int dst_lo,
+                      void* stream) {
+  if (!h || !a_f16 || !dst_f16 || (C & 7) || (lda & 7) || (ldb & 7) || (ldd & 7)) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   long long total = (long long)N * 4 * Ha * Wa * (C >> 3);
   upsample_add_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)a_f16, Ha, Wa, Hag, Wag, ay, ax, (const __half*)b_f16, Hb, Wb, by, bx, N, C, scale, shift, relu, (__half*)dst_f16, Hd, Wd, dy, dx,
-      (float*)dst_f32);
+      (const __half*)a_f16, Ha, Wa, Hag, Wag, ay, ax, lda, a_lo, (const __half*)b_f16, Hb, Wb, by, bx, ldb, b_lo, N, C, scale, shift,
+      relu, (__half*)dst_f16, Hd, Wd, dy, dx, ldd, dst_lo);
   AUX_LAUNCH_CHECK(h, "upsample_add");
   return TIAB_OK;
 }
 
-int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, void* dst_f16, void* stream) {
-  if (!h || !src_f16 || !dst_f16 || (C & 7)) return TIAB_E_INVALID;
+int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, int lds, int src_lo, void* dst_f16,
+                      int Hd, int Wd, int dy, int dx, int ldd, int dst_lo, void* stream) {
+  if (!h || !src_f16 || !dst_f16 || (C & 7) || (lds & 7) || (ldd & 7)) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C >> 3);
-  maxpool3x3s2_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, N, H, W, C, (__half*)dst_f16, Ho, Wo);
+  maxpool3x3s2_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, N, H, W, C, lds, src_lo,
+                                                                                 (__half*)dst_f16, Ho, Wo, Hd, Wd, dy, dx, ldd, dst_lo);
   AUX_LAUNCH_CHECK(h, "maxpool");
   return TIAB_OK;
 }
 
-int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int C, int ldx, const float* scale,
+int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int C, int ldx, int x_lo, const float* scale,
                         const float* shift, int relu, const float* Wt, const float* bias, int nout, float* out, int ldout,
                         int coffout, void* stream) {
-  if (!h || !x_f16 || !Wt || !out || nout < 1 || nout > 16 || (C & 7) || (ldx & 7)) return TIAB_E_INVALID;
+  if (!h || !x_f16 || !Wt || !out || nout < 1 || nout > 16 || (C & 7) || (ldx & 7) || (x_lo & 7)) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   size_t sm = (size_t)(nout * C + 2 * C) * sizeof(float);
-  pointwise_head_kernel<<<aux_grid(h, rows, 128), 128, sm, (cudaStream_t)stream>>>((const __half*)x_f16, rows, C, ldx, scale, shift, relu,
-                                                                                    Wt, bias, nout, out, ldout, coffout);
+  pointwise_head_kernel<<<aux_grid(h, rows, 128), 128, sm, (cudaStream_t)stream>>>((const __half*)x_f16, rows, C, ldx, x_lo, scale, shift,
+                                                                                    relu, Wt, bias, nout, out, ldout, coffout);
   AUX_LAUNCH_CHECK(h, "pointwise_head");
   return TIAB_OK;
 }
 
-int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, const float* Wt, const float* bias, int ncls,
-                        float* feat_out, float* probs, void* stream) {
+int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, int ldx, int x_lo, const float* Wt,
+                        const float* bias, int ncls, float* feat_out, float* probs, void* stream) {
   if (!h || !x_f16 || !Wt || !bias || !probs || ncls < 1 || ncls > 1024) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   size_t sm = (size_t)(C + ncls) * sizeof(float);
-  gap_fc_softmax_kernel<<<N, 256, sm, (cudaStream_t)stream>>>((const __half*)x_f16, HW, C, Wt, bias, ncls, feat_out, probs);
+  gap_fc_softmax_kernel<<<N, 256, sm, (cudaStream_t)stream>>>((const __half*)x_f16, HW, C, ldx, x_lo, Wt, bias, ncls, feat_out, probs);
   AUX_LAUNCH_CHECK(h, "gap_fc_softmax");
   return TIAB_OK;
 }
@@ -860,13 +940,11 @@ int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv
   return TIAB_OK;
 }
 
-int tiab_u8_to_f16(tiab_handle_t h, const uint8_t* src, int N, int H, int W, int C, float scale, void* dst_f16, int Hd, int Wd,
-                   int dy, int dx, int Cd, void* stream) {
-  if (!h || !src || !dst_f16 || Cd < C) return TIAB_E_INVALID;
+int tiab_softmax_up2_crop(tiab_handle_t h, const float* logits, int N, int H, int W, int C, float* out, void* stream) {
+  if (!h || !logits || !out || C < 1 || C > 8) return TIAB_E_INVALID;
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
-  u8_to_f16_kernel<<<aux_grid(h, (long long)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(src, N, H, W, C, scale, (__half*)dst_f16, Hd,
-                                                                                             Wd, dy, dx, Cd);
-  AUX_LAUNCH_CHECK(h, "u8_to_f16");
+  softmax_up2_crop_kernel<<<aux_grid(h, (long long)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(logits, N, H, W, C, out);
+  AUX_LAUNCH_CHECK(h, "softmax_up2_crop");
   return TIAB_OK;
 }
 

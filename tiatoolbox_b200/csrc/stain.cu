@@ -422,6 +422,36 @@ __device__ __noinline__ void vah_finish_gc(const StainConst& C, StainState* st) 
   __syncthreads();
 }
 
+// Exact order statistics inside the selected coarse bins (fused path): the few hundred keys that fall into a target's
+// coarse bin are appended to a shared-memory list during the second pass and ranked by counting.  `lists` holds up to
+// 4 lists of LIST_CAP floats (the histogram region); target t uses list lst[t]; tgt_rank[t] is its rank inside the bin.
+constexpr int LIST_CAP = NB;
+__device__ __noinline__ void fin_exact_select(StainState* st, const float* lists, const unsigned* cnt, const int* lst) {
+  __syncthreads();
+  for (int l = 0; l < 4; ++l) {
+    bool used = false;
+    for (int t = 0; t < 4; ++t) used = used || (lst[t] == l);
+    if (!used) continue;
+    const unsigned n = cnt[l] < (unsigned)LIST_CAP ? cnt[l] : (unsigned)LIST_CAP;
+    const float* L = lists + l * LIST_CAP;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = L[i];
+      unsigned less = 0, eq = 0;
+      for (unsigned j = 0; j < n; ++j) {
+        const float w = L[j];
+        less += (w < v) ? 1u : 0u;
+        eq += (w == v) ? 1u : 0u;
+      }
+      for (int t = 0; t < 4; ++t)
+        if (lst[t] == l) {
+          const unsigned r = st->tgt_rank[t];
+          if (less <= r && r < less + eq) st->tgt_val[t] = (double)v;
+        }
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------
 // bulk-async (TMA 1-D) copy + mbarrier primitives
 // ------------------------------------------------------------------------------------------------
@@ -460,15 +490,23 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// FUSED kernel
+// FUSED kernel (v2)
+//   * optical density comes from MUFU.LG2 on the byte (no shared-memory LUT, no bank conflicts):
+//     L = log2(v) ; t = log2(255) - L = OD / ln2.  All linear forms (projections, concentrations,
+//     output exponents) are pre-scaled on the host side of each pass so the pixel loops consume L.
+//   * the tissue mask is computed once (pass B) and kept in two registers per thread (the same
+//     thread owns the same 16 quads = 64 pixels in every pass).
+//   * per-pixel bodies are branch-free; histogram atomics are predicated.
+//   r1a profile of v1 (profiles/r1a_stain_fused_v1.md): 67 % shared-pipe utilisation, 55 % of the
+//   wavefronts bank-conflict replays of LUT look-ups -> this rewrite.
 // ------------------------------------------------------------------------------------------------
 struct FusedSmem {
   // offsets into dynamic shared memory
   static constexpr int PATCH = 0;
   static constexpr int HIST = PATCH_BYTES_MAX;
-  static constexpr int LUT = HIST + HIST_WORDS * 4;
-  static constexpr int OD = LUT + 768 * 8;
-  static constexpr int STATE = OD + 256 * 4;
+  static constexpr int LUT = HIST + HIST_WORDS * 4;   // uint2[768] (general-path layout, built by fin_hist)
+  static constexpr int YL = LUT + 768 * 8;            // unsigned[768]: luminance contributions only
+  static constexpr int STATE = YL + 768 * 4;
   static constexpr int SCRATCH = STATE + 2560;
   static constexpr int MBAR = SCRATCH + 64 * 4;
   static constexpr int TOTAL = MBAR + NCHUNK * 8;
@@ -480,6 +518,35 @@ __device__ __forceinline__ void zero_words(unsigned* p, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0u;
 }
 
+constexpr float LOG2_255 = 7.9943534368588578f;
+constexpr float LN2_F = 0.69314718055994531f;
+
+// log2 of byte `sel & 3` of w: PRMT builds 0x4B0000vv (= 8388608 + v as a float), one FADD, one MUFU.LG2
+__device__ __forceinline__ float lg_byte(uint32_t w, uint32_t sel) {
+  return __log2f(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.f);
+}
+__device__ __forceinline__ void quad_logs(uint32_t w0, uint32_t w1, uint32_t w2, float (&L)[12]) {
+  L[0] = lg_byte(w0, 0x7650u), L[1] = lg_byte(w0, 0x7651u), L[2] = lg_byte(w0, 0x7652u), L[3] = lg_byte(w0, 0x7653u);
+  L[4] = lg_byte(w1, 0x7650u), L[5] = lg_byte(w1, 0x7651u), L[6] = lg_byte(w1, 0x7652u), L[7] = lg_byte(w1, 0x7653u);
+  L[8] = lg_byte(w2, 0x7650u), L[9] = lg_byte(w2, 0x7651u), L[10] = lg_byte(w2, 0x7652u), L[11] = lg_byte(w2, 0x7653u);
+}
+__device__ __forceinline__ unsigned byte_of(uint32_t w, int b) { return (w >> (8 * b)) & 255u; }
+
+// pseudo-angle key in coarse-bin units, branch-free (see pseudo_angle() in stain_math.cuh)
+__device__ __forceinline__ float phi_key_fast(float p0, float p1) {
+  float s = fabsf(p0) + fabsf(p1);
+  float r = __fdividef(p1, s);
+  float alt = copysignf(2.f, p1) - r;
+  r = p0 < 0.f ? alt : r;
+  return (r + 2.0f) * (float)(NB / 4);
+}
+
+struct LinForms {  // affine forms of L = log2(byte) used by the pixel loops
+  float e[6], pb[2];   // projections: p_k = pb_k + sum_ch L_ch * e[ch*2+k]
+  float a[6], cb[2];   // concentrations (already in coarse-bin units): u_j = cb_j + sum_ch L_ch * a[ch*2+j]
+  float w[9], eb[3];   // output exponents (base 2): x_c = eb_c + sum_ch L_ch * w[ch*3+c]
+};
+
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, const uint8_t* __restrict__ in,
                    uint8_t* __restrict__ out, int N, double* __restrict__ M_src_out, double* __restrict__ maxC_out,
@@ -488,7 +555,7 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
   uint32_t* s_patch = reinterpret_cast<uint32_t*>(smem + FusedSmem::PATCH);
   unsigned* s_hist = reinterpret_cast<unsigned*>(smem + FusedSmem::HIST);
   uint2* s_lut = reinterpret_cast<uint2*>(smem + FusedSmem::LUT);
-  float* s_od = reinterpret_cast<float*>(smem + FusedSmem::OD);
+  unsigned* s_yl = reinterpret_cast<unsigned*>(smem + FusedSmem::YL);
   StainState* st = reinterpret_cast<StainState*>(smem + FusedSmem::STATE);
   unsigned* s_scratch = reinterpret_cast<unsigned*>(smem + FusedSmem::SCRATCH);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + FusedSmem::MBAR);
@@ -499,13 +566,11 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
   const unsigned patch_bytes = (unsigned)P * 3u;
   const unsigned chunk_bytes = patch_bytes / NCHUNK;
   const int chunk_quads = nquads / NCHUNK;
-  const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_patch);
 
   if (tid == 0) {
     for (int c = 0; c < NCHUNK; ++c) mbar_init(&s_bar[c], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 256; i += FUSED_THREADS) s_od[i] = tab->od[i];
   __syncthreads();
 
   unsigned parity = 0;
@@ -524,6 +589,8 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
       for (int i = 0; i < 12; ++i) st->acc[i] = 0.0;
     }
     const bool need_mask = (C.method == M_MACENKO || C.method == M_VAHADANE);
+    uint32_t mlo = 0u, mhi = 0u;  // tissue bits of this thread's pixels: quad iteration `it`, pixel j -> bit 4*it + j
+    bool has_zero = true;
 
     if (need_mask) {
       // ---- pass A: exact histogram of all 3P uint8 values, overlapped with the copy ----
@@ -549,133 +616,209 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
         s_hist[tid] = s;  // replica-0 slot; only this thread ever reads bin `tid` of any replica
       }
       __syncthreads();
+      has_zero = s_hist[0] != 0u;
       fin_hist(C, tab, st, s_hist, s_lut);
+      for (int i = tid; i < 768; i += FUSED_THREADS) s_yl[i] = s_lut[i].y;
+      __syncthreads();
 
-      // ---- pass B: tissue mask + OD moments ----
+      // ---- pass B: tissue mask (kept in registers) + moments of t = OD/ln2 over tissue pixels ----
       {
-        PixelLut L{s_lut, s_od, C.ysum_limit};
         float a[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) a[i] = 0.f;
-        for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-          float o0, o1, o2;
-          if (L.tissue(r, g, b, o0, o1, o2)) {
-            a[0] += 1.f;
-            a[1] += o0;
-            a[2] += o1;
-            a[3] += o2;
-            a[4] += o0 * o0;
-            a[5] += o0 * o1;
-            a[6] += o0 * o2;
-            a[7] += o1 * o1;
-            a[8] += o1 * o2;
-            a[9] += o2 * o2;
+        const int ylimit = C.ysum_limit;
+        for (int q = tid, it = 0; q < nquads; q += FUSED_THREADS, ++it) {
+          const uint32_t w0 = s_patch[3 * q], w1 = s_patch[3 * q + 1], w2 = s_patch[3 * q + 2];
+          unsigned vb[12];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) vb[b] = byte_of(w0, b), vb[4 + b] = byte_of(w1, b), vb[8 + b] = byte_of(w2, b);
+          unsigned nib = 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ysum = (int)(s_yl[vb[3 * j]] + s_yl[256 + vb[3 * j + 1]] + s_yl[512 + vb[3 * j + 2]]);
+            const bool m = ysum < ylimit;
+            nib |= (m ? 1u : 0u) << j;
+            const float mf = m ? 1.f : 0.f;
+            const float t0 = LOG2_255 - __log2f(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j]) - 8388608.f, 1.f));
+            const float t1 = LOG2_255 - __log2f(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j + 1]) - 8388608.f, 1.f));
+            const float t2 = LOG2_255 - __log2f(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j + 2]) - 8388608.f, 1.f));
+            const float m0 = t0 * mf, m1 = t1 * mf, m2 = t2 * mf;
+            a[0] += mf, a[1] += m0, a[2] += m1, a[3] += m2;
+            a[4] = fmaf(m0, t0, a[4]), a[5] = fmaf(m0, t1, a[5]), a[6] = fmaf(m0, t2, a[6]);
+            a[7] = fmaf(m1, t1, a[7]), a[8] = fmaf(m1, t2, a[8]), a[9] = fmaf(m2, t2, a[9]);
           }
-        });
+          if (it < 8)
+            mlo |= nib << (4 * it);
+          else
+            mhi |= nib << (4 * (it - 8));
+        }
         block_accumulate<10>(a, st->acc);
       }
       __syncthreads();
-      fin_moments(C, st);
-
-      if (C.method == M_MACENKO && st->status == TIAB_STAIN_OK) {
-        // ---- pass C: coarse histogram of the pseudo-angle over tissue pixels ----
-        zero_words(s_hist, NB);
-        if (tid == 0) {
-          set_rank_targets(st, 0, 0, st->n_tissue, C.q_phi_lo);
-          set_rank_targets(st, 2, 1, st->n_tissue, C.q_phi_hi);
-        }
-        __syncthreads();
-        {
-          PixelLut L{s_lut, s_od, C.ysum_limit};
-          float E[6];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) E[i] = st->E[i];
-          for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-            float o0, o1, o2;
-            if (L.tissue(r, g, b, o0, o1, o2)) atomicAdd(&s_hist[coarse_bin(phi_key(E, o0, o1, o2))], 1u);
-          });
-        }
-        __syncthreads();
-        fin_coarse(st, s_hist, 0, 0, s_scratch);
-        // ---- pass D: fine histograms inside the selected coarse bins ----
-        zero_words(s_hist, 4 * NB);
-        __syncthreads();
-        {
-          PixelLut L{s_lut, s_od, C.ysum_limit};
-          float E[6];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) E[i] = st->E[i];
-          int tb[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) tb[t] = st->tgt_bin[t];
-          for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-            float o0, o1, o2;
-            if (L.tissue(r, g, b, o0, o1, o2)) {
-              float u = phi_key(E, o0, o1, o2);
-              int cb = coarse_bin(u);
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (cb == tb[t]) atomicAdd(&s_hist[t * NB + fine_bin(u, cb)], 1u);
-            }
-          });
-        }
-        __syncthreads();
-        fin_fine(st, s_hist, s_scratch);
-        fin_phi(C, st);
-      } else if (C.method == M_VAHADANE && st->status == TIAB_STAIN_OK) {
-        // ---- Vahadane: <= 2 dictionary updates, each = 2 norm passes + 1 (G, C) pass ----
-        while (st->status == TIAB_STAIN_OK && !st->vah.done) {
-          for (int half = 0; half < 2 && st->status == TIAB_STAIN_OK; ++half) {
-            vah_prepare_step(C, st);
-            if (st->status != TIAB_STAIN_OK) break;
-            PixelLut L{s_lut, s_od, C.ysum_limit};
-            const int nfull = st->vsteps;
-            float a[1] = {0.f};
-            for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-              float o0, o1, o2;
-              if (L.tissue(r, g, b, o0, o1, o2)) {
-                float d0, d1, pend;
-                vah_replay(st, nfull, true, o0, o1, o2, d0, d1, pend);
-                a[0] += pend * pend;
-              }
-            });
-            block_accumulate<1>(a, st->acc);
-            __syncthreads();
-            vah_finish_norm(st);
-          }
-          if (st->status != TIAB_STAIN_OK) break;
-          {
-            PixelLut L{s_lut, s_od, C.ysum_limit};
-            const int nfull = st->vsteps;
-            float a[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) a[i] = 0.f;
-            for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-              float o0, o1, o2;
-              if (L.tissue(r, g, b, o0, o1, o2)) {
-                float d0, d1, pend;
-                vah_replay(st, nfull, false, o0, o1, o2, d0, d1, pend);
-                a[0] += d0 * d0;
-                a[1] += d0 * d1;
-                a[2] += d1 * d1;
-                a[3] += d0 * o0;
-                a[4] += d0 * o1;
-                a[5] += d0 * o2;
-                a[6] += d1 * o0;
-                a[7] += d1 * o1;
-                a[8] += d1 * o2;
-              }
-            });
-            block_accumulate<9>(a, st->acc);
-            __syncthreads();
-            vah_finish_gc(C, st);
-          }
-        }
+      if (tid == 0) {  // t-moments -> OD moments (OD = ln2 * t)
+        const double l = 0.6931471805599453, l2 = l * l;
+        for (int i = 1; i < 4; ++i) st->acc[i] *= l;
+        for (int i = 4; i < 10; ++i) st->acc[i] *= l2;
       }
+      fin_moments(C, st);
     } else {
       for (int c = 0; c < NCHUNK; ++c) mbar_wait(&s_bar[c], parity);
       if (tid == 0) set_source_matrix(st, C.M_fixed);
       __syncthreads();
+    }
+
+    // zeros count as ones for the optical density (utils/transforms.py:229-230): fix them once in shared
+    // memory (after the mask, which the reference computes on the unmodified image) so that the
+    // remaining passes need no clamp.
+    if (has_zero && st->status == TIAB_STAIN_OK) {
+      for (int w = tid; w < nquads * 3; w += FUSED_THREADS) {
+        const uint32_t v = s_patch[w];
+        const uint32_t z = (v - 0x01010101u) & ~v & 0x80808080u;
+        if (z) s_patch[w] = v | (z >> 7);
+      }
+      __syncthreads();
+    }
+
+    auto tissue_nib = [&](int it) -> unsigned { return ((it < 8 ? mlo : mhi) >> (4 * (it & 7))) & 15u; };
+
+    if (need_mask && C.method == M_MACENKO && st->status == TIAB_STAIN_OK) {
+      // ---- pass C: coarse histogram of the pseudo-angle over tissue pixels ----
+      zero_words(s_hist, NB);
+      if (tid == 0) {
+        set_rank_targets(st, 0, 0, st->n_tissue, C.q_phi_lo);
+        set_rank_targets(st, 2, 1, st->n_tissue, C.q_phi_hi);
+      }
+      __syncthreads();
+      float e[6], pb[2];
+      {
+        float se0 = 0.f, se1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          e[ch * 2] = -LN2_F * st->E[ch * 2], e[ch * 2 + 1] = -LN2_F * st->E[ch * 2 + 1];
+          se0 += st->E[ch * 2], se1 += st->E[ch * 2 + 1];
+        }
+        pb[0] = LOG2_255 * LN2_F * se0, pb[1] = LOG2_255 * LN2_F * se1;
+      }
+      for (int q = tid, it = 0; q < nquads; q += FUSED_THREADS, ++it) {
+        float L[12];
+        quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+        const unsigned nib = tissue_nib(it);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float p0 = fmaf(L[3 * j], e[0], fmaf(L[3 * j + 1], e[2], fmaf(L[3 * j + 2], e[4], pb[0])));
+          const float p1 = fmaf(L[3 * j], e[1], fmaf(L[3 * j + 1], e[3], fmaf(L[3 * j + 2], e[5], pb[1])));
+          const int cbn = coarse_bin(phi_key_fast(p0, p1));
+          if ((nib >> j) & 1u) atomicAdd(&s_hist[cbn], 1u);
+        }
+      }
+      __syncthreads();
+      fin_coarse(st, s_hist, 0, 0, s_scratch);
+      // ---- pass D: exact selection inside the selected coarse bins (candidate lists; histogram fallback) ----
+      int tb[4], lst[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) tb[t] = st->tgt_bin[t];
+      lst[0] = 0, lst[1] = tb[1] == tb[0] ? 0 : 1, lst[2] = 2, lst[3] = tb[3] == tb[2] ? 2 : 3;
+      float* s_list = reinterpret_cast<float*>(s_hist);
+      unsigned* s_cnt = s_scratch + 40;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        if (attempt == 1) zero_words(s_hist, 4 * NB);
+        if (tid < 4) s_cnt[tid] = 0u;
+        __syncthreads();
+        for (int q = tid, it = 0; q < nquads; q += FUSED_THREADS, ++it) {
+          float L[12];
+          quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+          const unsigned nib = tissue_nib(it);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float p0 = fmaf(L[3 * j], e[0], fmaf(L[3 * j + 1], e[2], fmaf(L[3 * j + 2], e[4], pb[0])));
+            const float p1 = fmaf(L[3 * j], e[1], fmaf(L[3 * j + 1], e[3], fmaf(L[3 * j + 2], e[5], pb[1])));
+            const float u = phi_key_fast(p0, p1);
+            const int cbn = coarse_bin(u);
+            const bool m = (nib >> j) & 1u;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (m && cbn == tb[t] && lst[t] == t) {
+                if (attempt == 0) {
+                  const unsigned i = atomicAdd(&s_cnt[t], 1u);
+                  if (i < (unsigned)LIST_CAP) s_list[t * LIST_CAP + i] = u;
+                } else {
+                  atomicAdd(&s_hist[t * NB + fine_bin(u, cbn)], 1u);
+                }
+              }
+          }
+        }
+        __syncthreads();
+        if (attempt == 0) {
+          const bool overflow = s_cnt[0] > LIST_CAP || s_cnt[1] > LIST_CAP || s_cnt[2] > LIST_CAP || s_cnt[3] > LIST_CAP;
+          if (!overflow) {
+            fin_exact_select(st, s_list, s_cnt, lst);
+            break;
+          }
+          __syncthreads();
+        } else {
+          // histogram fallback: duplicate lists share their histogram
+          if (lst[1] != 1)
+            for (int i = tid; i < NB; i += FUSED_THREADS) s_hist[1 * NB + i] = s_hist[0 * NB + i];
+          if (lst[3] != 3)
+            for (int i = tid; i < NB; i += FUSED_THREADS) s_hist[3 * NB + i] = s_hist[2 * NB + i];
+          __syncthreads();
+          fin_fine(st, s_hist, s_scratch);
+        }
+      }
+      fin_phi(C, st);
+    } else if (need_mask && C.method == M_VAHADANE && st->status == TIAB_STAIN_OK) {
+      // ---- Vahadane: <= 2 dictionary updates, each = 2 norm passes + 1 (G, C) pass ----
+      while (st->status == TIAB_STAIN_OK && !st->vah.done) {
+        for (int half = 0; half < 2 && st->status == TIAB_STAIN_OK; ++half) {
+          vah_prepare_step(C, st);
+          if (st->status != TIAB_STAIN_OK) break;
+          const int nfull = st->vsteps;
+          float a[1] = {0.f};
+          for (int q = tid, it = 0; q < nquads; q += FUSED_THREADS, ++it) {
+            float L[12];
+            quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+            const unsigned nib = tissue_nib(it);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float o0 = fmaf(L[3 * j], -LN2_F, LOG2_255 * LN2_F), o1 = fmaf(L[3 * j + 1], -LN2_F, LOG2_255 * LN2_F),
+                          o2 = fmaf(L[3 * j + 2], -LN2_F, LOG2_255 * LN2_F);
+              float d0, d1, pend;
+              vah_replay(st, nfull, true, o0, o1, o2, d0, d1, pend);
+              a[0] += ((nib >> j) & 1u) ? pend * pend : 0.f;
+            }
+          }
+          block_accumulate<1>(a, st->acc);
+          __syncthreads();
+          vah_finish_norm(st);
+        }
+        if (st->status != TIAB_STAIN_OK) break;
+        {
+          const int nfull = st->vsteps;
+          float a[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) a[i] = 0.f;
+          for (int q = tid, it = 0; q < nquads; q += FUSED_THREADS, ++it) {
+            float L[12];
+            quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+            const unsigned nib = tissue_nib(it);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float o0 = fmaf(L[3 * j], -LN2_F, LOG2_255 * LN2_F), o1 = fmaf(L[3 * j + 1], -LN2_F, LOG2_255 * LN2_F),
+                          o2 = fmaf(L[3 * j + 2], -LN2_F, LOG2_255 * LN2_F);
+              float d0, d1, pend;
+              vah_replay(st, nfull, false, o0, o1, o2, d0, d1, pend);
+              const float mf = ((nib >> j) & 1u) ? 1.f : 0.f;
+              d0 *= mf, d1 *= mf;
+              a[0] = fmaf(d0, d0, a[0]), a[1] = fmaf(d0, d1, a[1]), a[2] = fmaf(d1, d1, a[2]);
+              a[3] = fmaf(d0, o0, a[3]), a[4] = fmaf(d0, o1, a[4]), a[5] = fmaf(d0, o2, a[5]);
+              a[6] = fmaf(d1, o0, a[6]), a[7] = fmaf(d1, o1, a[7]), a[8] = fmaf(d1, o2, a[8]);
+            }
+          }
+          block_accumulate<9>(a, st->acc);
+          __syncthreads();
+          vah_finish_gc(C, st);
+        }
+      }
     }
 
     if (st->status == TIAB_STAIN_OK) {
@@ -686,37 +829,82 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
         set_rank_targets(st, 2, 1, (unsigned)P, C.q_conc);
       }
       __syncthreads();
-      float A[6], clo[2], csc[2];
+      // u_j = (c_j - lo_j) * scale_j with c_j = sum_ch ln2*(K - L_ch) * A[ch][j]
+      float a[6], cbias[2];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) A[i] = st->A[i];
-      clo[0] = st->c_lo[0], clo[1] = st->c_lo[1], csc[0] = st->c_scale[0], csc[1] = st->c_scale[1];
-      for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-        float o0 = s_od[r], o1 = s_od[g], o2 = s_od[b];
-        float c0 = o0 * A[0] + o1 * A[2] + o2 * A[4];
-        float c1 = o0 * A[1] + o1 * A[3] + o2 * A[5];
-        atomicAdd(&s_hist[coarse_bin((c0 - clo[0]) * csc[0])], 1u);
-        atomicAdd(&s_hist[NB + coarse_bin((c1 - clo[1]) * csc[1])], 1u);
-      });
+      for (int j = 0; j < 2; ++j) {
+        float sa = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          a[ch * 2 + j] = -LN2_F * st->A[ch * 2 + j] * st->c_scale[j];
+          sa += st->A[ch * 2 + j];
+        }
+        cbias[j] = (LOG2_255 * LN2_F * sa - st->c_lo[j]) * st->c_scale[j];
+      }
+      for (int q = tid; q < nquads; q += FUSED_THREADS) {
+        float L[12];
+        quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float u0 = fmaf(L[3 * j], a[0], fmaf(L[3 * j + 1], a[2], fmaf(L[3 * j + 2], a[4], cbias[0])));
+          const float u1 = fmaf(L[3 * j], a[1], fmaf(L[3 * j + 1], a[3], fmaf(L[3 * j + 2], a[5], cbias[1])));
+          atomicAdd(&s_hist[coarse_bin(u0)], 1u);
+          atomicAdd(&s_hist[NB + coarse_bin(u1)], 1u);
+        }
+      }
       __syncthreads();
       fin_coarse(st, s_hist, 0, 1, s_scratch);
-      // ---- pass F: fine histograms ----
-      zero_words(s_hist, 4 * NB);
-      __syncthreads();
-      int tb[4];
+      // ---- pass F: exact selection inside the selected coarse bins (candidate lists; histogram fallback) ----
+      int tb[4], lst[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) tb[t] = st->tgt_bin[t];
-      for_pixels(s_bytes, 1, 0, P, tid, FUSED_THREADS, [&](unsigned r, unsigned g, unsigned b) {
-        float o0 = s_od[r], o1 = s_od[g], o2 = s_od[b];
-        float u0 = (o0 * A[0] + o1 * A[2] + o2 * A[4] - clo[0]) * csc[0];
-        float u1 = (o0 * A[1] + o1 * A[3] + o2 * A[5] - clo[1]) * csc[1];
-        int cb0 = coarse_bin(u0), cb1 = coarse_bin(u1);
-        if (cb0 == tb[0]) atomicAdd(&s_hist[0 * NB + fine_bin(u0, cb0)], 1u);
-        if (cb0 == tb[1]) atomicAdd(&s_hist[1 * NB + fine_bin(u0, cb0)], 1u);
-        if (cb1 == tb[2]) atomicAdd(&s_hist[2 * NB + fine_bin(u1, cb1)], 1u);
-        if (cb1 == tb[3]) atomicAdd(&s_hist[3 * NB + fine_bin(u1, cb1)], 1u);
-      });
-      __syncthreads();
-      fin_fine(st, s_hist, s_scratch);
+      lst[0] = 0, lst[1] = tb[1] == tb[0] ? 0 : 1, lst[2] = 2, lst[3] = tb[3] == tb[2] ? 2 : 3;
+      float* s_list = reinterpret_cast<float*>(s_hist);
+      unsigned* s_cnt = s_scratch + 40;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        if (attempt == 1) zero_words(s_hist, 4 * NB);
+        if (tid < 4) s_cnt[tid] = 0u;
+        __syncthreads();
+        for (int q = tid; q < nquads; q += FUSED_THREADS) {
+          float L[12];
+          quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float u0 = fmaf(L[3 * j], a[0], fmaf(L[3 * j + 1], a[2], fmaf(L[3 * j + 2], a[4], cbias[0])));
+            const float u1 = fmaf(L[3 * j], a[1], fmaf(L[3 * j + 1], a[3], fmaf(L[3 * j + 2], a[5], cbias[1])));
+            const int cb0 = coarse_bin(u0), cb1 = coarse_bin(u1);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float u = t < 2 ? u0 : u1;
+              const int cbn = t < 2 ? cb0 : cb1;
+              if (cbn == tb[t] && lst[t] == t) {
+                if (attempt == 0) {
+                  const unsigned i = atomicAdd(&s_cnt[t], 1u);
+                  if (i < (unsigned)LIST_CAP) s_list[t * LIST_CAP + i] = u;
+                } else {
+                  atomicAdd(&s_hist[t * NB + fine_bin(u, cbn)], 1u);
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (attempt == 0) {
+          const bool overflow = s_cnt[0] > LIST_CAP || s_cnt[1] > LIST_CAP || s_cnt[2] > LIST_CAP || s_cnt[3] > LIST_CAP;
+          if (!overflow) {
+            fin_exact_select(st, s_list, s_cnt, lst);
+            break;
+          }
+          __syncthreads();
+        } else {
+          if (lst[1] != 1)
+            for (int i = tid; i < NB; i += FUSED_THREADS) s_hist[1 * NB + i] = s_hist[0 * NB + i];
+          if (lst[3] != 3)
+            for (int i = tid; i < NB; i += FUSED_THREADS) s_hist[3 * NB + i] = s_hist[2 * NB + i];
+          __syncthreads();
+          fin_fine(st, s_hist, s_scratch);
+        }
+      }
       fin_conc(C, st);
     }
     __syncthreads();
@@ -735,26 +923,42 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
     // ---- pass G: recompose in place, chunk by chunk, each chunk leaving through a bulk store ----
     if (C.do_apply) {
       const bool ok = st->status == TIAB_STAIN_OK;
-      float W[9];
+      // log2(out_c) = eb_c + sum_ch L_ch * w[ch][c],  w = -W2 / log2(e)  (W2 is defined on OD)
+      float w[9], eb[3];
+      {
+        const float inv_log2e = 0.69314718055994531f;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) W[i] = st->W2[i];
-      const float l255 = 7.9943534368588578f;  // log2(255)
+        for (int c = 0; c < 3; ++c) {
+          float sq = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            w[ch * 3 + c] = -st->W2[ch * 3 + c] * inv_log2e;
+            sq += w[ch * 3 + c];
+          }
+          eb[c] = LOG2_255 * (1.f - sq);
+        }
+      }
       for (int c = 0; c < NCHUNK; ++c) {
         if (ok) {
           for (int q = c * chunk_quads + tid; q < (c + 1) * chunk_quads; q += FUSED_THREADS) {
-            uint32_t w0 = s_patch[3 * q], w1 = s_patch[3 * q + 1], w2 = s_patch[3 * q + 2];
+            float L[12];
+            quad_logs(s_patch[3 * q], s_patch[3 * q + 1], s_patch[3 * q + 2], L);
+            // rgb2od's floor max(OD, 1e-6) (transforms.py:231) only bites for v = 255, but there it decides between
+            // 254 and 255 after truncation: L <= log2(255) - 1e-6/ln2
+#pragma unroll
+            for (int i = 0; i < 12; ++i) L[i] = fminf(L[i], LOG2_255 - 1.4426950e-6f);
             unsigned o[12];
             float fo[12];
-            quad_pixels(w0, w1, w2, [&](int i, unsigned r, unsigned g, unsigned b) {
-              float o0 = s_od[r], o1 = s_od[g], o2 = s_od[b];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
               for (int ch = 0; ch < 3; ++ch) {
-                float e = fmaf(o0, W[ch], fmaf(o1, W[3 + ch], fmaf(o2, W[6 + ch], l255)));
-                float v = fminf(exp2f(e), 255.f);
-                fo[i * 3 + ch] = v;
-                o[i * 3 + ch] = __float2uint_rz(v);
+                const float x = fmaf(L[3 * j], w[ch], fmaf(L[3 * j + 1], w[3 + ch], fmaf(L[3 * j + 2], w[6 + ch], eb[ch])));
+                const float v = fminf(exp2f(x), 255.f);
+                fo[j * 3 + ch] = v;
+                o[j * 3 + ch] = __float2uint_rz(v);
               }
-            });
+            }
             s_patch[3 * q] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
             s_patch[3 * q + 1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
             s_patch[3 * q + 2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);

@@ -16,8 +16,8 @@ import torch
 class ParamSpec(OrderedDict):
     """name -> (shape, kind) with kind in {conv, bn_w, bn_b, bn_mean, bn_var, bn_n, fc_w, bias}."""
 
-    def conv(self, name, cout, cin, k, bias=False):
-        self[name + ".weight"] = ((cout, cin, k, k), "conv")
+    def conv(self, name, cout, cin, k, bias=False, gain=1.0):
+        self[name + ".weight"] = ((cout, cin, k, k), "conv" if gain == 1.0 else f"conv:{gain}")
         if bias:
             self[name + ".bias"] = ((cout,), "bias")
 
@@ -42,9 +42,13 @@ def seeded_state_dict(spec: ParamSpec, seed: int = 0) -> OrderedDict:
     for name, (shape, kind) in spec.items():
         key = int.from_bytes(hashlib.sha256(f"{seed}:{name}".encode()).digest()[:6], "little")
         g = torch.Generator().manual_seed(key)
-        if kind == "conv":
+        if kind.startswith("conv"):
+            # "conv:<gain>": the closing conv of a residual branch gets a small gain, as in trained ResNets
+            # (zero-init-residual / small last-BN gamma); with gain 1 a random residual network is chaotic and
+            # amplifies fp32 round-off differences (summation order!) by ~5x per block.
+            gain = float(kind.split(":")[1]) if ":" in kind else 1.0
             fan_in = shape[1] * shape[2] * shape[3]
-            t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+            t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5 * gain
         elif kind == "fc_w":
             t = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
         elif kind == "bn_w":

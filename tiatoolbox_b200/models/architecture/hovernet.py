@@ -41,7 +41,7 @@ def hovernet_spec(num_input_channels: int = 3, num_types: int | None = None, mod
             sp.bn(f"{u}.conv1/bn", c1)
             sp.conv(f"{u}.conv2", c2, c1, 3)
             sp.bn(f"{u}.conv2/bn", c2)
-            sp.conv(f"{u}.conv3", c3, c2, 1)
+            sp.conv(f"{u}.conv3", c3, c2, 1, gain=0.2)
             ch = c3
         if cin != c3 or stride != 1:
             sp.conv(f"{name}.shortcut", c3, cin, 1)
@@ -124,18 +124,24 @@ def _dense_block(x, sd, name, units):
     return F.relu(_bn(prev, sd, f"{name}.blk_bna.bn"))
 
 
-def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: int | None) -> OrderedDict:
+def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: int | None, capture: dict | None = None) -> OrderedDict:
     """fp32 PyTorch restatement of HoVerNet.forward (hovernet.py:405-454).  x in [0, 255]."""
     x = x_nchw / 255.0
     if mode == "fast":
         pb, pa = tf_same_pad(x.shape[2], 7, 1)
         x = F.pad(x, (pb, pa, pb, pa))
     d = F.relu(_bn(F.conv2d(x, sd["conv0./.weight"]), sd, "conv0.bn"))
+    if capture is not None:
+        capture["x0"] = d
     feats = []
     for name, _, _, units, stride in RES_CFG:
         d = _residual_block(d, sd, name, units, stride)
         feats.append(d)
+        if capture is not None:
+            capture[name] = d
     feats[3] = F.conv2d(feats[3], sd["conv_bot.weight"])
+    if capture is not None:
+        capture["dbot"] = feats[3]
     c0, c1 = (184, 72) if mode == "original" else (92, 36)
     d0 = feats[0][:, :, c0 // 2: feats[0].shape[2] - c0 // 2, c0 // 2: feats[0].shape[3] - c0 // 2]
     d1 = feats[1][:, :, c1 // 2: feats[1].shape[2] - c1 // 2, c1 // 2: feats[1].shape[3] - c1 // 2]
@@ -144,14 +150,28 @@ def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: i
     for b in (["tp"] if num_types is not None else []) + ["np", "hv"]:
         p = f"decoder.{b}"
         u3 = _up2(feats[3]) + feats[2]
+        if capture is not None:
+            capture["u3in"] = u3
         u3 = F.conv2d(u3, sd[f"{p}.u3.conva.weight"])
+        if capture is not None:
+            capture[f"{b}.u3.conva"] = u3
         u3 = F.conv2d(_dense_block(u3, sd, f"{p}.u3.dense", 8), sd[f"{p}.u3.convf.weight"])
+        if capture is not None:
+            capture[f"{b}.u3out"] = u3
         u2 = _up2(u3) + d1
+        if capture is not None:
+            capture[f"{b}.u2in"] = u2
         u2 = F.conv2d(u2, sd[f"{p}.u2.conva.weight"])
         u2 = F.conv2d(_dense_block(u2, sd, f"{p}.u2.dense", 4), sd[f"{p}.u2.convf.weight"])
+        if capture is not None:
+            capture[f"{b}.u2out"] = u2
         u1 = _up2(u2) + d0
+        if capture is not None:
+            capture[f"{b}.u1in"] = u1
         pb, pa = tf_same_pad(u1.shape[2], k, 1)
         u1 = F.conv2d(F.pad(u1, (pb, pa, pb, pa)), sd[f"{p}.u1.conva.weight"])
+        if capture is not None:
+            capture[f"{b}.u1"] = u1
         u0 = F.relu(_bn(u1, sd, f"{p}.u0.bn"))
         out[b] = F.conv2d(u0, sd[f"{p}.u0.conv.weight"], sd[f"{p}.u0.conv.bias"])
     return out

@@ -3,10 +3,14 @@
 Everything here is plumbing (pointers, pitches, geometry); the arithmetic is in csrc/conv.cu.
 Tensors are NHWC and live on one CUDA device; launches go to torch's current stream so that the
 whole network can be captured in a CUDA graph.
+
+`Act` describes an fp16 activation tensor: `C` channels per plane, row pitch `ld`, and an optional
+second plane at channel offset `lo` holding x - fp16(x) (split-precision mode; lo = 0 -> absent).
 """
 from __future__ import annotations
 
 import ctypes as C
+from dataclasses import dataclass
 
 import torch
 
@@ -21,19 +25,43 @@ def _ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
 
+@dataclass
+class Act:
+    t: torch.Tensor
+    C: int
+    ld: int
+    lo: int = 0
+
+    @property
+    def dev(self):
+        return self.t.device
+
+    def hi(self) -> torch.Tensor:
+        return self.t[..., : self.C]
+
+    def value(self) -> torch.Tensor:
+        """fp32 value (hi + lo) — for tests/debugging."""
+        v = self.t[..., : self.C].float()
+        if self.lo:
+            v = v + self.t[..., self.lo: self.lo + self.C].float()
+        return v
+
+
 class ConvOp:
     """One shifted-GEMM convolution launch (see tiab_conv_desc_t)."""
 
     def __init__(self, *, x: torch.Tensor, x_rows: int, x_ld: int, cin: int, w: torch.Tensor, taps: list[int],
                  M: int, N: int, grid: tuple[int, int], window: tuple[int, int, int, int],
-                 dst_geom: tuple[int, int, int, int], out16=None, ld16=0, coff16=0, out32=None, ld32=0, coff32=0,
-                 out16b=None, ld16b=0, coff16b=0, scale2=None, shift2=None, bias=None, res32=None, res16=None,
-                 ldres=0, coffres=0, res_geom=(1, 1, 0, 0), relu=False):
+                 dst_geom: tuple[int, int, int, int], x_lo_off: int = 0, out16=None, ld16=0, coff16=0, lo16=0, out32=None,
+                 ld32=0, coff32=0, out16b=None, ld16b=0, coff16b=0, lo16b=0, scale2=None, shift2=None, bias=None,
+                 res32=None, res16=None, ldres=0, coffres=0, reslo=0, res_geom=(1, 1, 0, 0), relu=False):
         d = _lib.ConvDesc()
-        d.x, d.x_rows, d.x_ld, d.cin = x.data_ptr(), x_rows, x_ld, cin
+        d.x, d.x_rows, d.x_ld, d.cin, d.x_lo_off = x.data_ptr(), x_rows, x_ld, cin, x_lo_off
         assert w.dtype == torch.float16 and w.dim() == 2 and w.is_contiguous()
         d.w, d.w_ld = w.data_ptr(), w.shape[1]
         assert w.shape[0] == N and len(taps) <= _lib.MAX_TAPS
+        nseg = 3 if x_lo_off else 1
+        assert w.shape[1] >= len(taps) * nseg * ((cin + 63) // 64) * 64, (w.shape, len(taps), nseg, cin)
         d.M, d.N, d.taps = M, N, len(taps)
         for i, t in enumerate(taps):
             d.tap_off[i] = int(t)
@@ -41,66 +69,67 @@ class ConvOp:
         d.y0, d.y1, d.x0, d.x1 = window
         d.Hd, d.Wd, d.dy, d.dx = dst_geom
         d.Hr, d.Wr, d.ry, d.rx = res_geom
-        d.out16, d.ld16, d.coff16 = _ptr(out16), ld16, coff16
+        d.out16, d.ld16, d.coff16, d.lo16 = _ptr(out16), ld16, coff16, lo16
         d.out32, d.ld32, d.coff32 = _ptr(out32), ld32, coff32
-        d.out16b, d.ld16b, d.coff16b = _ptr(out16b), ld16b, coff16b
+        d.out16b, d.ld16b, d.coff16b, d.lo16b = _ptr(out16b), ld16b, coff16b, lo16b
         d.scale2, d.shift2, d.bias = _ptr(scale2), _ptr(shift2), _ptr(bias)
-        d.res32, d.res16, d.ldres, d.coffres = _ptr(res32), _ptr(res16), ldres, coffres
+        d.res32, d.res16, d.ldres, d.coffres, d.reslo = _ptr(res32), _ptr(res16), ldres, coffres, reslo
         d.relu = int(bool(relu))
         self.desc = d
         self.dev = x.device
         self._keep = (x, w, out16, out32, out16b, scale2, shift2, bias, res32, res16)
         self.flops = 2.0 * M * N * len(taps) * cin
+        self.mma_flops = self.flops * nseg
 
     def __call__(self):
         h = _lib.handle(self.dev.index or 0)
         _lib.check(h, _lib.lib().tiab_conv_gemm(h, C.byref(self.desc), _stream(self.dev)))
 
 
-def im2col(src, src_is_u8, u8_scale, n, h_, w_, c, ldsrc, kh, kw, stride, pad_t, pad_l, ho, wo, out, kpad):
+def im2col(src, src_is_u8, u8_scale, src_lo, n, h_, w_, c, ldsrc, kh, kw, stride, pad_t, pad_l, ho, wo, out, ldout, kpad, out_lo):
     h = _lib.handle(src.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_im2col(h, src.data_ptr(), int(src_is_u8), float(u8_scale), n, h_, w_, c, ldsrc, kh, kw,
-                                         stride, pad_t, pad_l, ho, wo, out.data_ptr(), kpad, _stream(src.device)))
+    _lib.check(h, _lib.lib().tiab_im2col(h, src.data_ptr(), int(src_is_u8), float(u8_scale), src_lo, n, h_, w_, c, ldsrc, kh, kw,
+                                         stride, pad_t, pad_l, ho, wo, out.data_ptr(), ldout, kpad, out_lo, _stream(src.device)))
 
 
-def bn_relu(src, src_is_f32, ldsrc, coffsrc, scale, shift, relu, rows, c, dst, lddst, coffdst):
+def bn_relu(src, src_is_f32, ldsrc, coffsrc, src_lo, scale, shift, relu, rows, c, dst, lddst, coffdst, dst_lo):
     h = _lib.handle(src.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_bn_relu(h, src.data_ptr(), int(src_is_f32), ldsrc, coffsrc, _ptr(scale), _ptr(shift),
-                                          int(relu), rows, c, dst.data_ptr(), lddst, coffdst, _stream(src.device)))
+    _lib.check(h, _lib.lib().tiab_bn_relu(h, src.data_ptr(), int(src_is_f32), ldsrc, coffsrc, src_lo, _ptr(scale), _ptr(shift),
+                                          int(relu), rows, c, dst.data_ptr(), lddst, coffdst, dst_lo, _stream(src.device)))
 
 
-def upsample_add(a, ha, wa, hag, wag, ay, ax, b, hb, wb, by, bx, n, c, scale, shift, relu, dst, hd, wd, dy, dx, dst32=None):
-    h = _lib.handle(a.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_upsample_add(h, a.data_ptr(), ha, wa, hag, wag, ay, ax, _ptr(b), hb, wb, by, bx, n, c, _ptr(scale),
-                                               _ptr(shift), int(relu), dst.data_ptr(), hd, wd, dy, dx, _ptr(dst32),
-                                               _stream(a.device)))
+def upsample_add(a: Act, ha, wa, hag, wag, ay, ax, b: Act | None, hb, wb, by, bx, n, c, scale, shift, relu, dst: Act, hd, wd, dy, dx):
+    h = _lib.handle(a.dev.index or 0)
+    _lib.check(h, _lib.lib().tiab_upsample_add(
+        h, a.t.data_ptr(), ha, wa, hag, wag, ay, ax, a.ld, a.lo, None if b is None else b.t.data_ptr(), hb, wb, by, bx,
+        0 if b is None else b.ld, 0 if b is None else b.lo, n, c, _ptr(scale), _ptr(shift), int(relu), dst.t.data_ptr(), hd, wd,
+        dy, dx, dst.ld, dst.lo, _stream(a.dev)))
 
 
-def maxpool3x3s2(src, n, h_, w_, c, dst):
-    h = _lib.handle(src.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_maxpool3x3s2(h, src.data_ptr(), n, h_, w_, c, dst.data_ptr(), _stream(src.device)))
+def maxpool3x3s2(src: Act, n, h_, w_, c, dst: Act, hd, wd, dy, dx):
+    h = _lib.handle(src.dev.index or 0)
+    _lib.check(h, _lib.lib().tiab_maxpool3x3s2(h, src.t.data_ptr(), n, h_, w_, c, src.ld, src.lo, dst.t.data_ptr(), hd, wd, dy, dx,
+                                               dst.ld, dst.lo, _stream(src.dev)))
 
 
-def pointwise_head(x, rows, c, ldx, scale, shift, relu, wt, bias, nout, out, ldout, coffout):
-    h = _lib.handle(x.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_pointwise_head(h, x.data_ptr(), rows, c, ldx, _ptr(scale), _ptr(shift), int(relu),
-                                                 wt.data_ptr(), _ptr(bias), nout, out.data_ptr(), ldout, coffout,
-                                                 _stream(x.device)))
+def pointwise_head(x: Act, rows, c, scale, shift, relu, wt, bias, nout, out, ldout, coffout):
+    h = _lib.handle(x.dev.index or 0)
+    _lib.check(h, _lib.lib().tiab_pointwise_head(h, x.t.data_ptr(), rows, c, x.ld, x.lo, _ptr(scale), _ptr(shift), int(relu),
+                                                 wt.data_ptr(), _ptr(bias), nout, out.data_ptr(), ldout, coffout, _stream(x.dev)))
 
 
-def gap_fc_softmax(x, n, hw, c, wt, bias, ncls, feat_out, probs):
-    h = _lib.handle(x.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_gap_fc_softmax(h, x.data_ptr(), n, hw, c, wt.data_ptr(), bias.data_ptr(), ncls,
-                                                 _ptr(feat_out), probs.data_ptr(), _stream(x.device)))
-
-
-def u8_to_f16(src, n, h_, w_, c, scale, dst, hd, wd, dy, dx, cd):
-    h = _lib.handle(src.device.index or 0)
-    _lib.check(h, _lib.lib().tiab_u8_to_f16(h, src.data_ptr(), n, h_, w_, c, float(scale), dst.data_ptr(), hd, wd, dy, dx, cd,
-                                            _stream(src.device)))
+def gap_fc_softmax(x: Act, n, hw, c, wt, bias, ncls, feat_out, probs):
+    h = _lib.handle(x.dev.index or 0)
+    _lib.check(h, _lib.lib().tiab_gap_fc_softmax(h, x.t.data_ptr(), n, hw, c, x.ld, x.lo, wt.data_ptr(), bias.data_ptr(), ncls,
+                                                 _ptr(feat_out), probs.data_ptr(), _stream(x.dev)))
 
 
 def hovernet_heads(npl, hvl, tpl, nt, rows, np_out, hv_out, tp_out):
     h = _lib.handle(npl.device.index or 0)
     _lib.check(h, _lib.lib().tiab_hovernet_heads(h, npl.data_ptr(), hvl.data_ptr(), _ptr(tpl), nt, rows, np_out.data_ptr(),
                                                  hv_out.data_ptr(), _ptr(tp_out), _stream(npl.device)))
+
+
+def softmax_up2_crop(logits, n, h_, w_, c, out):
+    h = _lib.handle(logits.device.index or 0)
+    _lib.check(h, _lib.lib().tiab_softmax_up2_crop(h, logits.data_ptr(), n, h_, w_, c, out.data_ptr(), _stream(logits.device)))

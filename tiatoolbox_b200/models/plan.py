@@ -6,6 +6,13 @@ BatchNorm that FOLLOWS a convolution is folded into the packed fp16 weights (+ f
 epilogue); BatchNorm+ReLU that PRECEDES a convolution (pre-activation blocks) is produced by the
 epilogue of the layer that writes the tensor (second output `out16b`) or, when a tensor is consumed
 under several different BNs (HoVer-Net dense blocks), by a small elementwise kernel.
+
+Precision modes
+  "fp16"    one tensor-core pass, fp16 operands (11-bit mantissa == TF32, what cuDNN uses by default
+            for the reference's own CUDA path).  ~3e-4 relative error PER conv layer.
+  "fp16x3"  every activation is carried as hi + lo fp16 planes and every weight as W_hi + W_lo; the
+            GEMM runs A_hi*W_hi + A_lo*W_hi + A_hi*W_lo as one K-concatenated contraction (3x the MMA
+            work, ~22-bit operands).  This is the mode that meets 1e-3 end-to-end through 60 layers.
 """
 from __future__ import annotations
 
@@ -13,19 +20,32 @@ import torch
 
 from tiatoolbox_b200.models import ops
 from tiatoolbox_b200.models.architecture._params import bn_scale_shift
+from tiatoolbox_b200.models.ops import Act
 
 
 def ceil_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-def pack_weight(w: torch.Tensor, out_scale: torch.Tensor | None = None, groups: int = 1, extra_k: torch.Tensor | None = None,
-                device=None) -> torch.Tensor:
-    """[Cout, Cin/groups, KH, KW] fp32 -> [Cout, taps * ceil64(Cin)] fp16, tap-major, BN scale folded.
+def _split_pack(packed64: torch.Tensor, split: bool) -> torch.Tensor:
+    """[Cout, taps, Cpad] float64 -> fp16 [Cout, taps*Cpad] or, split, [Cout, taps*3*Cpad] = per tap [W_hi | W_hi | W_lo]."""
+    co, taps, cp = packed64.shape
+    hi = packed64.to(torch.float16)
+    if not split:
+        return hi.reshape(co, taps * cp).contiguous()
+    lo = (packed64 - hi.double()).to(torch.float16)
+    return torch.stack([hi, hi, lo], dim=2).reshape(co, taps * 3 * cp).contiguous()
 
+
+def pack_weight(w: torch.Tensor, out_scale: torch.Tensor | None = None, groups: int = 1, split: bool = False, device=None,
+                im2col: bool = False) -> torch.Tensor:
+    """[Cout, Cin/groups, KH, KW] fp32 -> packed fp16 K-major weight matrix with the BN scale folded.
+
+    Default layout: tap-major, each tap's channels zero padded to a multiple of 64 (shifted-GEMM path).
+    im2col=True: one "tap" whose K = KH*KW*Cin (order kh, kw, c) padded to a multiple of 64.
     Grouped convolutions are expanded to a dense block-diagonal matrix (HoVer-Net's g=4 3x3 convs
     are 1 % of the FLOPs)."""
-    w = w.detach().double()
+    w = w.detach().double().cpu()
     co, cig, kh, kw = w.shape
     cin = cig * groups
     if groups > 1:
@@ -35,23 +55,33 @@ def pack_weight(w: torch.Tensor, out_scale: torch.Tensor | None = None, groups: 
             full[g * cog:(g + 1) * cog, g * cig:(g + 1) * cig] = w[g * cog:(g + 1) * cog]
         w = full
     if out_scale is not None:
-        w = w * out_scale.double().view(-1, 1, 1, 1)
-    cp = ceil_to(cin, 64)
-    packed = torch.zeros(co, kh * kw, cp, dtype=torch.float64)
-    packed[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, cin)
-    packed = packed.reshape(co, kh * kw * cp)
-    return packed.to(torch.float16).contiguous().to(device)
+        w = w * out_scale.double().cpu().view(-1, 1, 1, 1)
+    if im2col:
+        k = kh * kw * cin
+        packed = torch.zeros(co, 1, ceil_to(k, 64), dtype=torch.float64)
+        packed[:, 0, :k] = w.permute(0, 2, 3, 1).reshape(co, k)
+    else:
+        cp = ceil_to(cin, 64)
+        packed = torch.zeros(co, kh * kw, cp, dtype=torch.float64)
+        packed[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, cin)
+    return _split_pack(packed, split).to(device)
 
 
 class Plan:
     """A list of launches + the buffers they touch."""
 
-    def __init__(self, device, batch: int):
+    def __init__(self, device, batch: int, precision: str = "fp16x3"):
+        if precision not in ("fp16", "fp16x3"):
+            msg = f"unknown precision {precision!r}"
+            raise ValueError(msg)
         self.dev = torch.device(device)
         self.B = batch
+        self.precision = precision
+        self.split = precision == "fp16x3"
         self.ops: list = []
         self.bufs: dict[str, torch.Tensor] = {}
-        self.flops = 0.0
+        self.flops = 0.0       # useful (algorithmic) FLOPs of one forward
+        self.mma_flops = 0.0   # FLOPs actually issued to the tensor cores (incl. split segments, discarded rows)
         self.graph = None
         self._keep: list = []
 
@@ -61,10 +91,24 @@ class Plan:
         self.bufs[name] = t
         return t
 
+    def act(self, name: str, lead_shape, C: int) -> Act:
+        """fp16 activation buffer [*lead_shape, planes*C] (hi plane, then lo plane in split mode)."""
+        planes = 2 if self.split else 1
+        t = self.buf(name, (*lead_shape, planes * C))
+        return Act(t, C, planes * C, C if self.split else 0)
+
     def const(self, t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
         t = t.detach().to(dtype).contiguous().to(self.dev)
         self._keep.append(t)
         return t
+
+    def weight(self, w, out_scale=None, groups=1, im2col=False) -> torch.Tensor:
+        return pack_weight(w, out_scale, groups, self.split, self.dev, im2col)
+
+    def fold_bn(self, sd, conv_name: str, bn_name: str, groups: int = 1, im2col: bool = False):
+        """conv followed by BN: packed weight with the BN scale folded + fp32 bias (= BN shift)."""
+        scale, shift = bn_scale_shift(sd, bn_name)
+        return self.weight(sd[conv_name + ".weight"], scale, groups, im2col), self.const(shift)
 
     def bytes_allocated(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
@@ -73,30 +117,48 @@ class Plan:
     def add(self, fn) -> None:
         self.ops.append(fn)
 
-    def conv(self, *, x: torch.Tensor, grid, cin: int, w: torch.Tensor, k: int, centered: bool, N: int, window,
-             x_ld: int | None = None, x_rows: int | None = None, dst_geom=None, **kw) -> ops.ConvOp:
-        """Shifted-GEMM conv over the (H, W) grid of the NHWC buffer `x` (batch = self.B)."""
+    @staticmethod
+    def _out_kw(kw: dict) -> dict:
+        """Expand Act-valued out16 / out16b / res16 keyword arguments into raw descriptor fields."""
+        for key, ld, lo in (("out16", "ld16", "lo16"), ("out16b", "ld16b", "lo16b"), ("res16", "ldres", "reslo")):
+            a = kw.get(key)
+            if isinstance(a, Act):
+                kw[key] = a.t
+                kw[ld] = a.ld
+                kw[lo] = a.lo
+        return kw
+
+    def conv(self, *, x: Act, grid, cin: int, w: torch.Tensor, k: int, centered: bool, N: int, window, dst_geom=None, **kw) -> ops.ConvOp:
+        """Shifted-GEMM conv over the (H, W) grid of the NHWC activation `x` (batch = self.B)."""
         H, W = grid
         M = self.B * H * W
         if centered:
             taps = [(kh - k // 2) * W + (kw_ - k // 2) for kh in range(k) for kw_ in range(k)]
         else:
             taps = [kh * W + kw_ for kh in range(k) for kw_ in range(k)]
-        op = ops.ConvOp(x=x, x_rows=x_rows if x_rows is not None else M, x_ld=x_ld if x_ld is not None else x.shape[-1], cin=cin,
-                        w=w, taps=taps, M=M, N=N, grid=(H, W), window=window, dst_geom=dst_geom or (H, W, 0, 0), **kw)
-        # useful FLOPs: only the valid output window
+        op = ops.ConvOp(x=x.t, x_rows=M, x_ld=x.ld, x_lo_off=x.lo, cin=cin, w=w, taps=taps, M=M, N=N, grid=(H, W), window=window,
+                        dst_geom=dst_geom or (H, W, 0, 0), **self._out_kw(kw))
         y0, y1, x0, x1 = window
         self.flops += 2.0 * self.B * (y1 - y0) * (x1 - x0) * N * (k * k) * cin
+        self.mma_flops += op.mma_flops
         self.ops.append(op)
         return op
 
-    def gemm(self, *, x: torch.Tensor, rows: int, cin: int, w: torch.Tensor, N: int, x_ld: int | None = None, **kw) -> ops.ConvOp:
+    def gemm(self, *, x: Act, rows: int, cin: int, w: torch.Tensor, N: int, **kw) -> ops.ConvOp:
         """Plain [rows, cin] x [N, cin]^T GEMM (1x1 conv on a dense matrix / im2col output)."""
-        op = ops.ConvOp(x=x, x_rows=rows, x_ld=x_ld if x_ld is not None else x.shape[-1], cin=cin, w=w, taps=[0], M=rows, N=N,
-                        grid=(1, rows), window=(0, 1, 0, rows), dst_geom=kw.pop("dst_geom", (1, rows, 0, 0)), **kw)
+        op = ops.ConvOp(x=x.t, x_rows=rows, x_ld=x.ld, x_lo_off=x.lo, cin=cin, w=w, taps=[0], M=rows, N=N, grid=(1, rows),
+                        window=(0, 1, 0, rows), dst_geom=kw.pop("dst_geom", (1, rows, 0, 0)), **self._out_kw(kw))
         self.flops += 2.0 * rows * N * cin
+        self.mma_flops += op.mma_flops
         self.ops.append(op)
         return op
+
+    def im2col(self, src, src_is_u8, u8_scale, src_lo, n, h, w, c, ldsrc, k, stride, pad, ho, out: Act, kpad):
+        self.add(lambda: ops.im2col(src, src_is_u8, u8_scale, src_lo, n, h, w, c, ldsrc, k, k, stride, pad, pad, ho, ho, out.t, out.ld,
+                                    kpad, out.lo))
+
+    def bn_relu(self, src: Act, c: int, scale, shift, rows: int, dst: Act, relu=True):
+        self.add(lambda: ops.bn_relu(src.t, False, src.ld, 0, src.lo, scale, shift, relu, rows, c, dst.t, dst.ld, 0, dst.lo))
 
     # ---- execution ----
     def run_eager(self) -> None:
@@ -125,10 +187,3 @@ class Plan:
     @property
     def num_launches(self) -> int:
         return len(self.ops)
-
-
-def fold_bn(sd, conv_name: str, bn_name: str, groups: int = 1, device=None):
-    """conv followed by BN: packed fp16 weight with the BN scale folded + fp32 bias (= BN shift)."""
-    scale, shift = bn_scale_shift(sd, bn_name)
-    w = pack_weight(sd[conv_name + ".weight"], scale, groups, device=device)
-    return w, shift.to(device)
