@@ -169,6 +169,19 @@ int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv
 /* UNetModel.infer_batch tail (unet.py:458-465): softmax -> bilinear x2 -> centre crop */
 int tiab_softmax_up2_crop(tiab_handle_t h, const float* logits, int N, int H, int W, int C, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * HoVer-Net post-processing on the device: HoVerNet._proc_np_hv + get_instance_info (without contours)
+ * (tiatoolbox/models/architecture/hovernet.py:502-748).  np_map N*H*W*1, hv_map N*H*W*2, tp_map N*H*W*1 (or NULL),
+ * all float32 device pointers as returned by infer_batch.  Outputs (device): inst_map N*H*W int32;
+ * optional instance table (pass inst_count = NULL to skip): per image up to max_inst rows in ascending id order:
+ * inst_id, inst_box [x0,y0,x1,y1) , inst_centroid [x,y] float64, inst_type, inst_prob float64.
+ * ------------------------------------------------------------------------------------------- */
+int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
+                           int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id, int32_t* inst_box,
+                           double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream);
+int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]);
+int tiab_dbg_postproc_fetch(tiab_handle_t h, int which, void* host_out, void* stream);
+
 /* Force one of the two device paths (testing / benchmarking): 0 = auto, 1 = fused one-CTA-per-patch
  * kernel (requires H*W*3 <= 196608 and H*W % 16 == 0), 2 = multi-pass general path. */
 int tiab_stain_set_path(tiab_handle_t h, int path);

@@ -1,0 +1,155 @@
+"""CPU oracle of HoVer-Net's post-processing (architecture/hovernet.py:502-748 of the reference).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Two layers:
+  * `remove_small_objects` and `watershed` restate the two scikit-image (>= 0.26, pinned in
+    requirements/requirements.txt:29 of the reference, NOT installed / not vendored) functions that
+    `_proc_np_hv` calls (hovernet.py:544, 614, 616).  scikit-image's algorithm is restated from its
+    published implementation (skimage/morphology/misc.py remove_small_objects; skimage/segmentation/
+    _watershed.py + _watershed_cy.pyx watershed_raveled: priority flood, 4-connectivity, heap key
+    (image value, insertion age), pixels are labelled when they are PUSHED, markers outside the
+    mask are dropped, neighbour order (-row, -1, +1, +row)).
+    Parity status of these two: **unpinned** — every reference test that exercises them needs remote
+    weights/images, so they are pinned only by hand-built known-answer cases and
+    property tests (tests/test_oracle_postproc.py).  Exact float ties between different markers
+    depend on scikit-image's heap internals and are treated as unspecified.
+  * `proc_np_hv` / `get_instance_info` are a numpy + cv2 + scipy restatement of the rest of
+    hovernet.py:536-748; when /root/reference is present the tests run the reference's own
+    unmodified `_proc_np_hv` / `get_instance_info` (through oracle/ref_shim.py, with the two
+    restated functions injected) against it.
+"""
+from __future__ import annotations
+
+import heapq
+import math
+
+import cv2
+import numpy as np
+from scipy import ndimage
+
+
+def remove_small_objects(label_img: np.ndarray, max_size: int) -> np.ndarray:
+    """skimage.morphology.remove_small_objects(ar, max_size=...) for an integer label image:
+    zero every label whose pixel count is <= max_size; no relabelling."""
+    out = label_img.copy()
+    sizes = np.bincount(label_img.ravel())
+    too_small = sizes <= max_size
+    out[too_small[label_img]] = 0
+    return out
+
+
+def watershed(image: np.ndarray, markers: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """skimage.segmentation.watershed(image, markers=markers, mask=mask) with the defaults
+    (connectivity=1, compactness=0, watershed_line=False)."""
+    img = np.asarray(image, dtype=np.float64)
+    msk = np.asarray(mask).astype(bool)
+    out = (np.asarray(markers) * msk).astype(np.int32)
+    h, w = img.shape
+    heap: list = []
+    age = 0
+    for idx in np.flatnonzero(out):
+        heapq.heappush(heap, (img.flat[idx], 0, int(idx)))
+    flat_out = out.ravel()
+    flat_img = img.ravel()
+    flat_msk = msk.ravel()
+    while heap:
+        _, _, p = heapq.heappop(heap)
+        y, x = divmod(p, w)
+        lab = flat_out[p]
+        for q, ok in ((p - w, y > 0), (p - 1, x > 0), (p + 1, x < w - 1), (p + w, y < h - 1)):
+            if not ok or not flat_msk[q] or flat_out[q]:
+                continue
+            age += 1
+            flat_out[q] = lab
+            heapq.heappush(heap, (flat_img[q], age, q))
+    return out
+
+
+def proc_np_hv(np_map: np.ndarray, hv_map: np.ndarray, *, debug: dict | None = None) -> np.ndarray:
+    """HoVerNet._proc_np_hv with scale_factor = 1 (hovernet.py:536-616)."""
+    blb_raw = np_map[..., 0]
+    h_dir_raw = hv_map[..., 0]
+    v_dir_raw = hv_map[..., 1]
+    blb = np.array(blb_raw >= 0.5, dtype=np.int32)
+    blb = ndimage.label(blb)[0]
+    blb = remove_small_objects(blb, max_size=9)
+    blb[blb > 0] = 1
+    h_dir = cv2.normalize(h_dir_raw, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    v_dir = cv2.normalize(v_dir_raw, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    ksize = 21
+    obj_size = math.ceil(10 * 1.0)
+    sobel_h = cv2.Sobel(h_dir, cv2.CV_64F, 1, 0, ksize=ksize)
+    sobel_v = cv2.Sobel(v_dir, cv2.CV_64F, 0, 1, ksize=ksize)
+    sobel_h = 1 - cv2.normalize(sobel_h, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    sobel_v = 1 - cv2.normalize(sobel_v, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    overall = np.maximum(sobel_h, sobel_v)
+    overall = overall - (1 - blb)
+    overall[overall < 0] = 0
+    dist = (1.0 - overall) * blb
+    dist = -cv2.GaussianBlur(dist, (3, 3), 0)
+    overall = np.array(overall >= 0.4, dtype=np.int32)
+    marker = blb - overall
+    marker[marker < 0] = 0
+    marker = ndimage.binary_fill_holes(marker).astype("uint8")
+    kernel = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (5, 5))
+    marker = cv2.morphologyEx(marker, cv2.MORPH_OPEN, kernel)
+    marker = ndimage.label(marker)[0]
+    marker = remove_small_objects(marker, max_size=obj_size - 1)
+    if debug is not None:
+        debug.update(blb=blb.copy(), dist=dist.copy(), marker=marker.copy(), h_dir=h_dir, v_dir=v_dir)
+    return watershed(dist, markers=marker, mask=blb)
+
+
+def get_bounding_box(img: np.ndarray) -> np.ndarray:
+    """utils/misc.py:898-922: [start_x, start_y, end_x, end_y], end exclusive."""
+    rows = np.any(img, axis=1)
+    cols = np.any(img, axis=0)
+    r_min, r_max = np.where(rows)[0][[0, -1]]
+    c_min, c_max = np.where(cols)[0][[0, -1]]
+    return np.array([c_min, r_min, c_max + 1, r_max + 1])
+
+
+def get_instance_info(pred_inst: np.ndarray, pred_type: np.ndarray | None = None, offset=(0, 0)) -> dict:
+    """HoVerNet.get_instance_info (hovernet.py:670-748)."""
+    offset = np.asarray(offset)
+    info = {}
+    for inst_id in np.unique(pred_inst)[1:]:
+        inst_map = pred_inst == inst_id
+        box = get_bounding_box(inst_map)
+        tl = box[:2] + offset
+        crop = inst_map[box[1]:box[3], box[0]:box[2]].astype(np.uint8)
+        mom = cv2.moments(crop)
+        contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].astype(np.int32)
+        contour = np.squeeze(contour)
+        if contour.shape[0] < 3 or len(contour.shape) != 2:
+            continue
+        centroid = np.array([mom["m10"] / mom["m00"], mom["m01"] / mom["m00"]]) + tl
+        contour = contour + tl[None]
+        box = box.copy()
+        box[:2] += offset
+        box[2:] += offset
+        info[int(inst_id)] = {"box": box, "centroid": centroid, "contours": contour, "prob": None, "type": None}
+    if pred_type is not None:
+        for inst_id, rec in info.items():
+            b = rec["box"].copy()
+            b[:2] -= offset
+            b[2:] -= offset
+            c0, r0, c1, r1 = b
+            m = pred_inst[r0:r1, c0:c1] == inst_id
+            types = pred_type[r0:r1, c0:c1][m]
+            tl_, cnt = np.unique(types, return_counts=True)
+            order = sorted(zip(tl_, cnt), key=lambda x: x[1], reverse=True)
+            t = order[0][0]
+            if t == 0 and len(order) > 1:
+                t = order[1][0]
+            rec["type"] = int(t)
+            rec["prob"] = float(dict(order)[t] / (np.sum(m) + 1.0e-6))
+    return info
+
+
+def postproc(np_map, hv_map, tp_map=None, offset=(0, 0)):
+    """HoVerNet.postproc (hovernet.py:751-859) -> (inst_map int32, info dict)."""
+    pred_type = None if tp_map is None else np.around(tp_map).astype("uint8")
+    inst = proc_np_hv(np_map, hv_map)
+    return inst, get_instance_info(inst, pred_type, offset)

@@ -96,6 +96,9 @@ SIGNATURES = {
     "tiab_gap_fc_softmax": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tiab_hovernet_heads": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_longlong, _vp, _vp, _vp, _vp]),
     "tiab_softmax_up2_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "tiab_hovernet_postproc": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tiab_dbg_sobel_kernels": (C.c_int, [_vp, _vp]),
+    "tiab_dbg_postproc_fetch": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "tiab_stain_set_path": (C.c_int, [_vp, C.c_int]),
     "tiab_last_launch_count": (C.c_int, [_vp]),
     "tiab_dbg_percentile_u8": (C.c_int, [_vp, C.c_double, _dp]),

@@ -37,7 +37,7 @@ void tiab_destroy(tiab_handle_t h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-  void* dev[] = {h->stain_work, h->stain_state, h->stain_lut, h->dev_in, h->dev_out, h->dev_small};
+  void* dev[] = {h->stain_work, h->stain_state, h->stain_lut, h->dev_in, h->dev_out, h->dev_small, h->pp_work};
   for (void* p : dev)
     if (p) cudaFree(p);
   void* pin[] = {h->pin_in, h->pin_out, h->pin_small};

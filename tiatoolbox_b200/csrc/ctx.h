@@ -26,6 +26,12 @@ struct tiab_ctx {
   void* dev_small = nullptr;    // N*(6+2) doubles + N ints
   void* pin_small = nullptr;
   size_t small_bytes = 0;
+  // HoVer-Net post-processing workspace
+  void* pp_work = nullptr;
+  size_t pp_bytes = 0;
+  int pp_const_set = 0;
+  size_t pp_dbg_off[8] = {0};
+  size_t pp_dbg_bytes[8] = {0};
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
 };

@@ -1,0 +1,756 @@
+// postproc.cu — HoVer-Net post-processing on the device (sm_100a).
+//
+// Reference: HoVerNet._proc_np_hv + get_instance_info, tiatoolbox/models/architecture/hovernet.py:502-748
+// (CPU: scipy.ndimage.label / binary_fill_holes, cv2.normalize / Sobel(ksize=21, CV_64F) / GaussianBlur /
+// morphologyEx, skimage remove_small_objects / watershed).  Every stage is restated as a kernel over
+// all pixels of all maps of the batch:
+//
+//   threshold -> CCL (union-find, ids in raster order of the first pixel = ndimage.label) -> drop <= 9 px
+//   min-max normalise h, v -> separable 21-tap Sobel in float64 (REFLECT_101, OpenCV's summation order)
+//   -> min-max normalise -> energy / distance maps -> 3x3 Gaussian (float64) -> marker seeds
+//   -> fill holes (background CCL not touching the border) -> 5x5 elliptic opening -> CCL -> drop <= 9 px
+//   -> marker-controlled watershed: one thread per foreground component runs the sequential priority
+//      flood (key = (value, insertion age), label on push, neighbours -row,-1,+1,+row) in a private heap
+//   -> per-instance table (box, centroid, majority type, type probability).
+//
+// This is integer / index work bounded by latency, not bandwidth (20 B/px algorithmic).
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tiab200.h"
+#include "ctx.h"
+
+namespace tiab {
+
+constexpr int PP_THREADS = 256;
+constexpr int PP_MAX_TYPES = 16;
+
+struct HeapItem {
+  double v;
+  unsigned age;
+  unsigned idx;
+};
+
+struct PPWork {  // all arrays are [N * P] unless noted
+  int* lab;            // union-find labels / component root (local pixel index), -1 background
+  int* size;           // pixels per root
+  int* cid;            // raster-order component id (1-based) stored at the root pixel
+  int* roots;          // [N * P] list of roots in raster order
+  int* ncomp;          // [N]
+  int* bbox;           // [N * P * 4] per-root bounding box (x0, y0, x1, y1 inclusive), used for foreground comps
+  uint8_t* blb;        // foreground after small-object removal
+  uint8_t* fg;         // scratch binary map (CCL input)
+  uint8_t* mk;         // marker seeds (binary)
+  uint8_t* tmp;        // morphology scratch
+  uint8_t* border;     // [N * P] per-root "touches the border" flag (fill holes)
+  float* hn;           // normalised h / later 1 - normalised sobel_h
+  float* vn;
+  double* rowh;        // row-filtered
+  double* rowv;
+  double* sobh;
+  double* sobv;
+  double* dist0;       // (1 - overall) * blb
+  double* dist;        // -GaussianBlur(dist0)
+  float* mm;           // [N * 8] min/max scratch: h min,max, v min,max ; as doubles in mm64
+  double* mm64;        // [N * 4] sobel_h min,max, sobel_v min,max
+  int* marker;         // labelled markers (ids kept, small removed)
+  HeapItem* heap;      // [N * P]
+  int* heap_off;       // [N * P] heap slice offset per foreground root
+  // instance accumulators, [N * maxI ...]
+  int* iarea;
+  int* ibox;           // [N*maxI*4]
+  unsigned long long* isx;
+  unsigned long long* isy;
+  int* itype;          // [N*maxI*PP_MAX_TYPES]
+};
+
+__constant__ double c_sobel_d[21];
+__constant__ double c_sobel_s[21];
+
+__device__ __forceinline__ int refl101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// ---- union-find ----
+__device__ __forceinline__ int uf_find(const int* L, int i) {
+  int p = L[i];
+  while (p != i) {
+    i = p;
+    p = L[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a < b) {
+      int old = atomicMin(&L[b], a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(&L[a], b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+#define PP_GRID_LOOP(i, total) \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (total); i += (long long)gridDim.x * blockDim.x)
+
+__global__ void pp_threshold(const float* __restrict__ npm, long long total, uint8_t* __restrict__ fg) {
+  PP_GRID_LOOP(i, total) fg[i] = npm[i] >= 0.5f ? 1 : 0;
+}
+__global__ void pp_ccl_init(const uint8_t* __restrict__ fg, int P, long long total, int* __restrict__ lab, int* __restrict__ size,
+                            int* __restrict__ bbox, uint8_t* __restrict__ border) {
+  PP_GRID_LOOP(i, total) {
+    const int p = (int)(i % P);
+    lab[i] = fg[i] ? p : -1;
+    size[i] = 0;
+    border[i] = 0;
+    if (bbox) {
+      bbox[4 * i] = 0x7fffffff, bbox[4 * i + 1] = 0x7fffffff, bbox[4 * i + 2] = -1, bbox[4 * i + 3] = -1;
+    }
+  }
+}
+__global__ void pp_ccl_merge(const uint8_t* __restrict__ fg, int H, int W, long long total, int* __restrict__ lab) {
+  const int P = H * W;
+  PP_GRID_LOOP(i, total) {
+    if (!fg[i]) continue;
+    const int p = (int)(i % P);
+    const long long base = i - p;
+    const int x = p % W, y = p / W;
+    int* L = lab + base;
+    if (x + 1 < W && fg[i + 1]) uf_union(L, p, p + 1);
+    if (y + 1 < H && fg[i + W]) uf_union(L, p, p + W);
+  }
+}
+__global__ void pp_ccl_flatten(int H, int W, long long total, int* __restrict__ lab, int* __restrict__ size, int* __restrict__ bbox,
+                               uint8_t* __restrict__ border) {
+  const int P = H * W;
+  PP_GRID_LOOP(i, total) {
+    const int p = (int)(i % P);
+    if (lab[i] < 0) continue;
+    const long long base = i - p;
+    const int r = uf_find(lab + base, p);
+    lab[i] = r;  // safe: a root keeps L[r] == r, non-roots only ever point to smaller indices
+    atomicAdd(&size[base + r], 1);
+    const int x = p % W, y = p / W;
+    if (bbox) {
+      int* b = bbox + 4 * (base + r);
+      atomicMin(&b[0], x), atomicMin(&b[1], y), atomicMax(&b[2], x), atomicMax(&b[3], y);
+    }
+    if (x == 0 || y == 0 || x == W - 1 || y == H - 1) border[base + r] = 1;
+  }
+}
+// raster-order ids of the roots: one CTA per image
+__global__ void __launch_bounds__(1024) pp_rank_roots(const int* __restrict__ lab, int P, int* __restrict__ cid, int* __restrict__ roots,
+                                                      int* __restrict__ ncomp) {
+  __shared__ int s_cnt[1024];
+  const int n = blockIdx.x;
+  const long long base = (long long)n * P;
+  const int chunk = (P + 1023) / 1024;
+  const int p0 = threadIdx.x * chunk, p1 = min(P, p0 + chunk);
+  int c = 0;
+  for (int p = p0; p < p1; ++p) c += (lab[base + p] == p) ? 1 : 0;
+  s_cnt[threadIdx.x] = c;
+  __syncthreads();
+  // inclusive scan (Hillis-Steele)
+  for (int d = 1; d < 1024; d <<= 1) {
+    int v = threadIdx.x >= d ? s_cnt[threadIdx.x - d] : 0;
+    __syncthreads();
+    s_cnt[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = s_cnt[threadIdx.x] - c;
+  for (int p = p0; p < p1; ++p)
+    if (lab[base + p] == p) {
+      roots[base + run] = p;
+      cid[base + p] = ++run;
+    }
+  if (threadIdx.x == 1023) ncomp[n] = s_cnt[1023];
+}
+// keep[p] = component has more than max_size pixels ; optionally write labelled output (id or 0)
+__global__ void pp_keep_large(const int* __restrict__ lab, const int* __restrict__ size, const int* __restrict__ cid, int P, long long total,
+                              int max_size, uint8_t* __restrict__ keep, int* __restrict__ labelled) {
+  PP_GRID_LOOP(i, total) {
+    const int r = lab[i];
+    const long long base = i - (i % P);
+    const bool k = r >= 0 && size[base + r] > max_size;
+    if (keep) keep[i] = k ? 1 : 0;
+    if (labelled) labelled[i] = k ? cid[base + r] : 0;
+  }
+}
+
+// ---- min / max per image (float and double variants) ----
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+  // works for any sign: compare-and-swap loop
+  float old = *a;
+  while (v < old) {
+    int assumed = __float_as_int(old);
+    int prev = atomicCAS(reinterpret_cast<int*>(a), assumed, __float_as_int(v));
+    if (prev == assumed) break;
+    old = __int_as_float(prev);
+  }
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+  float old = *a;
+  while (v > old) {
+    int assumed = __float_as_int(old);
+    int prev = atomicCAS(reinterpret_cast<int*>(a), assumed, __float_as_int(v));
+    if (prev == assumed) break;
+    old = __int_as_float(prev);
+  }
+}
+__device__ __forceinline__ void atomic_min_d(double* a, double v) {
+  double old = *a;
+  while (v < old) {
+    unsigned long long assumed = __double_as_longlong(old);
+    unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(a), assumed, (unsigned long long)__double_as_longlong(v));
+    if (prev == assumed) break;
+    old = __longlong_as_double(prev);
+  }
+}
+__device__ __forceinline__ void atomic_max_d(double* a, double v) {
+  double old = *a;
+  while (v > old) {
+    unsigned long long assumed = __double_as_longlong(old);
+    unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(a), assumed, (unsigned long long)__double_as_longlong(v));
+    if (prev == assumed) break;
+    old = __longlong_as_double(prev);
+  }
+}
+__global__ void pp_mm_init(int N, float* mm, double* mm64) {
+  PP_GRID_LOOP(i, N) {
+    mm[4 * i] = FLT_MAX, mm[4 * i + 1] = -FLT_MAX, mm[4 * i + 2] = FLT_MAX, mm[4 * i + 3] = -FLT_MAX;
+    mm64[4 * i] = DBL_MAX, mm64[4 * i + 1] = -DBL_MAX, mm64[4 * i + 2] = DBL_MAX, mm64[4 * i + 3] = -DBL_MAX;
+  }
+}
+// grid = (blocks, N)
+__global__ void __launch_bounds__(PP_THREADS) pp_minmax_hv(const float* __restrict__ hv, int P, float* __restrict__ mm) {
+  const int n = blockIdx.y;
+  float a = FLT_MAX, b = -FLT_MAX, c = FLT_MAX, d = -FLT_MAX;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const float h = hv[((long long)n * P + p) * 2], v = hv[((long long)n * P + p) * 2 + 1];
+    a = fminf(a, h), b = fmaxf(b, h), c = fminf(c, v), d = fmaxf(d, v);
+  }
+  for (int o = 16; o; o >>= 1) {
+    a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o)), b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o)), d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_f(&mm[4 * n], a), atomic_max_f(&mm[4 * n + 1], b), atomic_min_f(&mm[4 * n + 2], c), atomic_max_f(&mm[4 * n + 3], d);
+  }
+}
+__global__ void __launch_bounds__(PP_THREADS) pp_minmax_sobel(const double* __restrict__ sh, const double* __restrict__ sv, int P,
+                                                              double* __restrict__ mm64) {
+  const int n = blockIdx.y;
+  double a = DBL_MAX, b = -DBL_MAX, c = DBL_MAX, d = -DBL_MAX;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const double h = sh[(long long)n * P + p], v = sv[(long long)n * P + p];
+    a = fmin(a, h), b = fmax(b, h), c = fmin(c, v), d = fmax(d, v);
+  }
+  for (int o = 16; o; o >>= 1) {
+    a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o)), b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    c = fmin(c, __shfl_xor_sync(0xffffffffu, c, o)), d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_d(&mm64[4 * n], a), atomic_max_d(&mm64[4 * n + 1], b), atomic_min_d(&mm64[4 * n + 2], c), atomic_max_d(&mm64[4 * n + 3], d);
+  }
+}
+// cv2.normalize(src32f, NORM_MINMAX, 0, 1, CV_32F): scale = (float)(1/(max-min)), shift = 0.f - (float)(min*scale); dst = src*scale + shift
+__global__ void pp_normalize_hv(const float* __restrict__ hv, int P, long long total, const float* __restrict__ mm, float* __restrict__ hn,
+                                float* __restrict__ vn) {
+  PP_GRID_LOOP(i, total) {
+    const int n = (int)(i / P);
+    const double hmin = mm[4 * n], hmax = mm[4 * n + 1], vmin = mm[4 * n + 2], vmax = mm[4 * n + 3];
+    const float hs = (float)((hmax - hmin > DBL_EPSILON) ? 1.0 / (hmax - hmin) : 0.0);
+    const float vs = (float)((vmax - vmin > DBL_EPSILON) ? 1.0 / (vmax - vmin) : 0.0);
+    const float hsh = 0.f - (float)(hmin * (double)hs), vsh = 0.f - (float)(vmin * (double)vs);
+    // OpenCV's 32F->32F convertTo rounds src*scale + shift once (fused); verified bit-exact against cv2 4.13
+    hn[i] = fmaf(hv[2 * i], hs, hsh);
+    vn[i] = fmaf(hv[2 * i + 1], vs, vsh);
+  }
+}
+// Sobel rows: rowh = deriv along x of h, rowv = smooth along x of v   (generic RowFilter: s = k[0]*S[0]; s += k[i]*S[i])
+__global__ void pp_sobel_rows(const float* __restrict__ hn, const float* __restrict__ vn, int H, int W, long long total,
+                              double* __restrict__ rowh, double* __restrict__ rowv) {
+  PP_GRID_LOOP(i, total) {
+    const int x = (int)(i % W);
+    const long long rowbase = i - x;
+    double sh = 0.0, sv = 0.0;
+#pragma unroll
+    for (int k = 0; k < 21; ++k) {
+      const int xx = refl101(x + k - 10, W);
+      const double a = (double)hn[rowbase + xx], b = (double)vn[rowbase + xx];
+      if (k == 0) {
+        sh = __dmul_rn(c_sobel_d[0], a);
+        sv = __dmul_rn(c_sobel_s[0], b);
+      } else {
+        sh = __dadd_rn(sh, __dmul_rn(c_sobel_d[k], a));
+        sv = __dadd_rn(sv, __dmul_rn(c_sobel_s[k], b));
+      }
+    }
+    rowh[i] = sh;
+    rowv[i] = sv;
+  }
+}
+// Sobel columns: sobel_h = smooth along y of rowh (symmetric), sobel_v = deriv along y of rowv (anti-symmetric)
+__global__ void pp_sobel_cols(const double* __restrict__ rowh, const double* __restrict__ rowv, int H, int W, long long total,
+                              double* __restrict__ sobh, double* __restrict__ sobv) {
+  const int P = H * W;
+  PP_GRID_LOOP(i, total) {
+    const int p = (int)(i % P);
+    const long long base = i - p;
+    const int x = p % W, y = p / W;
+    double sh = __dmul_rn(c_sobel_s[10], rowh[i]);
+    double sv = 0.0;
+#pragma unroll
+    for (int k = 1; k <= 10; ++k) {
+      const int ya = refl101(y + k, H), yb = refl101(y - k, H);
+      const double ha = rowh[base + (long long)ya * W + x], hb = rowh[base + (long long)yb * W + x];
+      const double va = rowv[base + (long long)ya * W + x], vb = rowv[base + (long long)yb * W + x];
+      sh = __dadd_rn(sh, __dmul_rn(c_sobel_s[10 + k], __dadd_rn(ha, hb)));
+      sv = __dadd_rn(sv, __dmul_rn(c_sobel_d[10 + k], __dadd_rn(va, -vb)));
+    }
+    sobh[i] = sh;
+    sobv[i] = sv;
+  }
+}
+// 1 - normalize(sobel) (float32), overall, dist0, marker seeds
+__global__ void pp_energy(const double* __restrict__ sobh, const double* __restrict__ sobv, const double* __restrict__ mm64,
+                          const uint8_t* __restrict__ blb, int P, long long total, double* __restrict__ dist0, uint8_t* __restrict__ mk) {
+  PP_GRID_LOOP(i, total) {
+    const int n = (int)(i / P);
+    const double hmin = mm64[4 * n], hmax = mm64[4 * n + 1], vmin = mm64[4 * n + 2], vmax = mm64[4 * n + 3];
+    const double hs = (hmax - hmin > DBL_EPSILON) ? 1.0 / (hmax - hmin) : 0.0;
+    const double vs = (vmax - vmin > DBL_EPSILON) ? 1.0 / (vmax - vmin) : 0.0;
+    // rtype == CV_32F: scale = (float)scale; shift = (float)dmin - (float)(smin*scale)
+    const float hsf = (float)hs, vsf = (float)vs;
+    const float hshift = 0.f - (float)(hmin * (double)hsf), vshift = 0.f - (float)(vmin * (double)vsf);
+    // convertTo 64F -> 32F: saturate_cast<float>(src * (double)scale + (double)shift)
+    const float hn = (float)__dadd_rn(__dmul_rn(sobh[i], (double)hsf), (double)hshift);
+    const float vn = (float)__dadd_rn(__dmul_rn(sobv[i], (double)vsf), (double)vshift);
+    const float sh = __fadd_rn(1.f, -hn), sv = __fadd_rn(1.f, -vn);
+    const float mx = fmaxf(sh, sv);
+    const int b = blb[i];
+    double overall = (double)mx - (double)(1 - b);
+    if (overall < 0.0) overall = 0.0;
+    dist0[i] = __dmul_rn(__dadd_rn(1.0, -overall), (double)b);
+    const int ov = overall >= 0.4 ? 1 : 0;
+    const int m = b - ov;
+    mk[i] = m > 0 ? 1 : 0;
+  }
+}
+// dist = -GaussianBlur(dist0, (3,3), 0) in float64, REFLECT_101: rows then columns, out = c*k0 + (l + r)*k1
+__global__ void pp_blur_rows(const double* __restrict__ src, int W, long long total, double* __restrict__ dst) {
+  PP_GRID_LOOP(i, total) {
+    const int x = (int)(i % W);
+    const long long rb = i - x;
+    const double l = src[rb + refl101(x - 1, W)], r = src[rb + refl101(x + 1, W)];
+    // generic row filter: ((k0*l + k1*c) + k2*r)  (bit-exact against cv2.GaussianBlur on float64)
+    dst[i] = __dadd_rn(__dadd_rn(__dmul_rn(l, 0.25), __dmul_rn(src[i], 0.5)), __dmul_rn(r, 0.25));
+  }
+}
+__global__ void pp_blur_cols(const double* __restrict__ src, int H, int W, long long total, double* __restrict__ dst) {
+  const int P = H * W;
+  PP_GRID_LOOP(i, total) {
+    const int p = (int)(i % P);
+    const long long base = i - p;
+    const int x = p % W, y = p / W;
+    const double u = src[base + (long long)refl101(y - 1, H) * W + x], d = src[base + (long long)refl101(y + 1, H) * W + x];
+    dst[i] = -__dadd_rn(__dmul_rn(src[i], 0.5), __dmul_rn(__dadd_rn(u, d), 0.25));
+  }
+}
+__global__ void pp_invert(const uint8_t* __restrict__ a, long long total, uint8_t* __restrict__ b) {
+  PP_GRID_LOOP(i, total) b[i] = a[i] ? 0 : 1;
+}
+// filled = marker | (background component that does not touch the border)
+__global__ void pp_fill_holes(const uint8_t* __restrict__ mk, const int* __restrict__ lab, const uint8_t* __restrict__ border, int P,
+                              long long total, uint8_t* __restrict__ out) {
+  PP_GRID_LOOP(i, total) {
+    const long long base = i - (i % P);
+    const int r = lab[i];
+    out[i] = (mk[i] || (r >= 0 && !border[base + r])) ? 1 : 0;
+  }
+}
+// cv2 MORPH_ELLIPSE (5,5): rows 00100 / 11111 / 11111 / 11111 / 00100 ; erosion ignores out-of-image, dilation treats it as 0
+__device__ __forceinline__ bool in_ellipse5(int dy, int dx) { return (dy == -2 || dy == 2) ? dx == 0 : true; }
+__global__ void pp_morph(const uint8_t* __restrict__ src, int H, int W, long long total, int dilate, uint8_t* __restrict__ dst) {
+  const int P = H * W;
+  PP_GRID_LOOP(i, total) {
+    const int p = (int)(i % P);
+    const long long base = i - p;
+    const int x = p % W, y = p / W;
+    int acc = dilate ? 0 : 1;
+    for (int dy = -2; dy <= 2; ++dy)
+      for (int dx = -2; dx <= 2; ++dx) {
+        if (!in_ellipse5(dy, dx)) continue;
+        const int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const int v = src[base + (long long)yy * W + xx];
+        acc = dilate ? (acc | v) : (acc & v);
+      }
+    dst[i] = (uint8_t)acc;
+  }
+}
+
+// heap slice offsets of the foreground components: one thread per image (components are few)
+__global__ void pp_heap_offsets(const int* __restrict__ roots, const int* __restrict__ ncomp, const int* __restrict__ size, int P, int N,
+                                int* __restrict__ heap_off) {
+  PP_GRID_LOOP(n, N) {
+    const long long base = (long long)n * P;
+    int off = 0;
+    for (int c = 0; c < ncomp[n]; ++c) {
+      const int r = roots[base + c];
+      heap_off[base + r] = off;
+      off += size[base + r];
+    }
+  }
+}
+
+__device__ __forceinline__ bool heap_less(const HeapItem& a, const HeapItem& b) {
+  return a.v != b.v ? a.v < b.v : a.age < b.age;
+}
+__device__ __forceinline__ void heap_push(HeapItem* h, int& n, HeapItem e) {
+  int c = n++;
+  while (c > 0) {
+    const int par = (c - 1) >> 1;
+    if (heap_less(e, h[par])) {
+      h[c] = h[par];
+      c = par;
+    } else {
+      break;
+    }
+  }
+  h[c] = e;
+}
+__device__ __forceinline__ HeapItem heap_pop(HeapItem* h, int& n) {
+  const HeapItem top = h[0];
+  const HeapItem last = h[--n];
+  int p = 0;
+  while (true) {
+    int c = 2 * p + 1;
+    if (c >= n) break;
+    if (c + 1 < n && heap_less(h[c + 1], h[c])) ++c;
+    if (heap_less(h[c], last)) {
+      h[p] = h[c];
+      p = c;
+    } else {
+      break;
+    }
+  }
+  if (n > 0) h[p] = last;
+  return top;
+}
+// marker-controlled watershed, one thread per (image, foreground component)
+__global__ void __launch_bounds__(64) pp_watershed(const int* __restrict__ roots, const int* __restrict__ ncomp, const int* __restrict__ lab,
+                                                   const int* __restrict__ size, const int* __restrict__ bbox, const int* __restrict__ heap_off,
+                                                   const uint8_t* __restrict__ blb, const int* __restrict__ marker,
+                                                   const double* __restrict__ dist, int H, int W, int N, int maxcomp,
+                                                   HeapItem* __restrict__ heap, int* __restrict__ inst) {
+  const int P = H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (int)(t / maxcomp), c = (int)(t % maxcomp);
+  if (n >= N || c >= ncomp[n]) return;
+  const long long base = (long long)n * P;
+  const int r = roots[base + c];
+  if (size[base + r] <= 9) return;  // removed small object: not part of the mask
+  HeapItem* hp = heap + base + heap_off[base + r];
+  int hn = 0;
+  const int* bb = bbox + 4 * (base + r);
+  // markers of this component, in raveled order, all with age 0
+  for (int y = bb[1]; y <= bb[3]; ++y)
+    for (int x = bb[0]; x <= bb[2]; ++x) {
+      const int p = y * W + x;
+      if (lab[base + p] != r) continue;
+      const int m = marker[base + p];
+      if (m > 0) {
+        inst[base + p] = m;
+        heap_push(hp, hn, HeapItem{dist[base + p], 0u, (unsigned)p});
+      }
+    }
+  unsigned age = 0;
+  while (hn > 0) {
+    const HeapItem e = heap_pop(hp, hn);
+    const int p = (int)e.idx;
+    const int x = p % W, y = p / W;
+    const int l = inst[base + p];
+    const int nb[4] = {p - W, p - 1, p + 1, p + W};
+    const bool ok[4] = {y > 0, x > 0, x < W - 1, y < H - 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const int q = nb[k];
+      if (!blb[base + q] || inst[base + q]) continue;
+      ++age;
+      inst[base + q] = l;
+      heap_push(hp, hn, HeapItem{dist[base + q], age, (unsigned)q});
+    }
+  }
+}
+
+// ---- instance table ----
+__global__ void pp_inst_init(long long totalI, int* iarea, int* ibox, unsigned long long* isx, unsigned long long* isy, int* itype) {
+  PP_GRID_LOOP(i, totalI) {
+    iarea[i] = 0;
+    ibox[4 * i] = 0x7fffffff, ibox[4 * i + 1] = 0x7fffffff, ibox[4 * i + 2] = -1, ibox[4 * i + 3] = -1;
+    isx[i] = 0ull, isy[i] = 0ull;
+    for (int k = 0; k < PP_MAX_TYPES; ++k) itype[i * PP_MAX_TYPES + k] = 0;
+  }
+}
+__global__ void pp_inst_accum(const int* __restrict__ inst, const float* __restrict__ tp, int H, int W, long long total, int maxI,
+                              int* iarea, int* ibox, unsigned long long* isx, unsigned long long* isy, int* itype) {
+  const int P = H * W;
+  PP_GRID_LOOP(i, total) {
+    const int id = inst[i];
+    if (id <= 0 || id > maxI) continue;
+    const int n = (int)(i / P), p = (int)(i % P);
+    const int x = p % W, y = p / W;
+    const long long s = (long long)n * maxI + (id - 1);
+    atomicAdd(&iarea[s], 1);
+    atomicMin(&ibox[4 * s], x), atomicMin(&ibox[4 * s + 1], y), atomicMax(&ibox[4 * s + 2], x), atomicMax(&ibox[4 * s + 3], y);
+    atomicAdd(&isx[s], (unsigned long long)x), atomicAdd(&isy[s], (unsigned long long)y);
+    if (tp) {
+      int t = (int)(uint8_t)rintf(tp[i]);  // np.around(tp).astype("uint8")
+      if (t >= PP_MAX_TYPES) t = PP_MAX_TYPES - 1;
+      atomicAdd(&itype[s * PP_MAX_TYPES + t], 1);
+    }
+  }
+}
+// compact rows in ascending id order: one thread per image
+__global__ void pp_inst_finalize(int N, int maxI, int has_type, const int* __restrict__ iarea, const int* __restrict__ ibox,
+                                 const unsigned long long* __restrict__ isx, const unsigned long long* __restrict__ isy,
+                                 const int* __restrict__ itype, int* __restrict__ count, int* __restrict__ ids, int* __restrict__ box,
+                                 double* __restrict__ centroid, int* __restrict__ type, double* __restrict__ prob) {
+  PP_GRID_LOOP(n, N) {
+    int k = 0;
+    for (int id = 1; id <= maxI; ++id) {
+      const long long s = (long long)n * maxI + (id - 1);
+      const int a = iarea[s];
+      if (a <= 0) continue;
+      const long long o = (long long)n * maxI + k;
+      ids[o] = id;
+      box[4 * o] = ibox[4 * s], box[4 * o + 1] = ibox[4 * s + 1], box[4 * o + 2] = ibox[4 * s + 2] + 1, box[4 * o + 3] = ibox[4 * s + 3] + 1;
+      // cv2.moments on the crop: m10/m00 + box origin == mean absolute coordinate
+      centroid[2 * o] = (double)(isx[s] - (unsigned long long)ibox[4 * s] * a) / (double)a + (double)ibox[4 * s];
+      centroid[2 * o + 1] = (double)(isy[s] - (unsigned long long)ibox[4 * s + 1] * a) / (double)a + (double)ibox[4 * s + 1];
+      if (has_type) {
+        // sorted by count descending, stable -> ties keep ascending type id
+        int best = -1, bc = -1, second = -1, sc = -1;
+        for (int t = 0; t < PP_MAX_TYPES; ++t) {
+          const int c = itype[s * PP_MAX_TYPES + t];
+          if (c <= 0) continue;
+          if (c > bc) {
+            second = best, sc = bc;
+            best = t, bc = c;
+          } else if (c > sc) {
+            second = t, sc = c;
+          }
+        }
+        int ty = best, tc = bc;
+        if (best == 0 && second >= 0) ty = second, tc = sc;
+        type[o] = ty;
+        prob[o] = (double)tc / ((double)a + 1.0e-6);
+      } else {
+        type[o] = -1;
+        prob[o] = 0.0;
+      }
+      ++k;
+    }
+    count[n] = k;
+  }
+}
+
+}  // namespace tiab
+
+using namespace tiab;
+
+static void sobel_kernels(double d[21], double s[21]) {
+  // binomial smoothing (1+x)^20 and derivative (1+x)^19 * (x-1)  (cv2.getDerivKernels(1, 0, 21), un-normalised)
+  long long a[22] = {0}, b[22] = {0};
+  a[0] = 1;
+  for (int it = 0; it < 20; ++it)
+    for (int k = it + 1; k >= 1; --k) a[k] += a[k - 1];
+  for (int k = 0; k < 21; ++k) s[k] = (double)a[k];
+  b[0] = 1;
+  for (int it = 0; it < 19; ++it)
+    for (int k = it + 1; k >= 1; --k) b[k] += b[k - 1];
+  for (int k = 0; k < 21; ++k) d[k] = (double)((k >= 1 ? b[k - 1] : 0) - (k <= 19 ? b[k] : 0));
+}
+
+struct PPAlloc {
+  std::vector<std::pair<void**, size_t>> items;
+};
+
+static int pp_ensure(tiab_ctx* h, size_t bytes) {
+  if (h->pp_bytes >= bytes) return TIAB_OK;
+  if (h->pp_work) cudaFree(h->pp_work);
+  h->pp_work = nullptr;
+  h->pp_bytes = 0;
+  TIAB_CUDA_OK(h, cudaMalloc(&h->pp_work, bytes));
+  h->pp_bytes = bytes;
+  return TIAB_OK;
+}
+
+#define PP_LAUNCH(h, name, grid, block, ...)                                  \
+  do {                                                                        \
+    name<<<grid, block, 0, s>>>(__VA_ARGS__);                                 \
+    cudaError_t _e = cudaGetLastError();                                      \
+    if (_e != cudaSuccess) {                                                  \
+      (h)->err = std::string(#name " launch: ") + cudaGetErrorString(_e);     \
+      return TIAB_E_CUDA;                                                     \
+    }                                                                         \
+    (h)->last_launches++;                                                     \
+  } while (0)
+
+extern "C" {
+
+int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]) {
+  sobel_kernels(deriv, smooth);
+  return TIAB_OK;
+}
+
+// copy an intermediate of the LAST tiab_hovernet_postproc call to the host (tests only):
+// 0 blb u8, 1 h_dir f32, 2 v_dir f32, 3 sobel_h f64, 4 sobel_v f64, 5 dist f64, 6 marker i32, 7 opened seeds u8
+int tiab_dbg_postproc_fetch(tiab_handle_t h, int which, void* host_out, void* stream) {
+  if (!h || which < 0 || which > 7 || !host_out || !h->pp_work || !h->pp_dbg_bytes[which]) return TIAB_E_INVALID;
+  TIAB_CUDA_OK(h, cudaMemcpyAsync(host_out, (uint8_t*)h->pp_work + h->pp_dbg_off[which], h->pp_dbg_bytes[which], cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+  TIAB_CUDA_OK(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return TIAB_OK;
+}
+
+int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
+                           int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id, int32_t* inst_box,
+                           double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream) {
+  if (!h) return TIAB_E_INVALID;
+  if (!np_map || !hv_map || !inst_map || N <= 0 || H < 11 || W < 11 || (long long)H * W > (1 << 24) || max_inst <= 0) {
+    h->err = "tiab_hovernet_postproc: invalid argument";
+    return TIAB_E_INVALID;
+  }
+  const bool want_table = inst_count != nullptr;
+  if (want_table && (!inst_id || !inst_box || !inst_centroid || !inst_type || !inst_prob)) {
+    h->err = "tiab_hovernet_postproc: incomplete instance table outputs";
+    return TIAB_E_INVALID;
+  }
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->pp_const_set) {
+    double d[21], sm[21];
+    sobel_kernels(d, sm);
+    TIAB_CUDA_OK(h, cudaMemcpyToSymbol(c_sobel_d, d, sizeof(d)));
+    TIAB_CUDA_OK(h, cudaMemcpyToSymbol(c_sobel_s, sm, sizeof(sm)));
+    h->pp_const_set = 1;
+  }
+  const int P = H * W;
+  const long long T = (long long)N * P;
+  const long long TI = (long long)N * max_inst;
+  // carve the workspace
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = (off + bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_lab = take(T * 4), o_size = take(T * 4), o_cid = take(T * 4), o_roots = take(T * 4), o_ncomp = take((size_t)N * 4);
+  const size_t o_bbox = take(T * 16), o_blb = take(T), o_fg = take(T), o_mk = take(T), o_tmp = take(T), o_border = take(T);
+  const size_t o_hn = take(T * 4), o_vn = take(T * 4), o_rowh = take(T * 8), o_rowv = take(T * 8), o_sobh = take(T * 8), o_sobv = take(T * 8);
+  const size_t o_dist0 = take(T * 8), o_dist = take(T * 8), o_mm = take((size_t)N * 16), o_mm64 = take((size_t)N * 32);
+  const size_t o_marker = take(T * 4), o_heap = take(T * sizeof(HeapItem)), o_hoff = take(T * 4);
+  const size_t o_roots2 = take(T * 4), o_ncomp2 = take((size_t)N * 4), o_lab2 = take(T * 4), o_size2 = take(T * 4);
+  const size_t o_iarea = take(TI * 4), o_ibox = take(TI * 16), o_isx = take(TI * 8), o_isy = take(TI * 8), o_itype = take(TI * 4 * PP_MAX_TYPES);
+  int rc = pp_ensure(h, off);
+  if (rc) return rc;
+  uint8_t* B = (uint8_t*)h->pp_work;
+  PPWork w;
+  w.lab = (int*)(B + o_lab), w.size = (int*)(B + o_size), w.cid = (int*)(B + o_cid), w.roots = (int*)(B + o_roots), w.ncomp = (int*)(B + o_ncomp);
+  w.bbox = (int*)(B + o_bbox), w.blb = B + o_blb, w.fg = B + o_fg, w.mk = B + o_mk, w.tmp = B + o_tmp, w.border = B + o_border;
+  w.hn = (float*)(B + o_hn), w.vn = (float*)(B + o_vn), w.rowh = (double*)(B + o_rowh), w.rowv = (double*)(B + o_rowv);
+  w.sobh = (double*)(B + o_sobh), w.sobv = (double*)(B + o_sobv), w.dist0 = (double*)(B + o_dist0), w.dist = (double*)(B + o_dist);
+  w.mm = (float*)(B + o_mm), w.mm64 = (double*)(B + o_mm64), w.marker = (int*)(B + o_marker), w.heap = (HeapItem*)(B + o_heap);
+  w.heap_off = (int*)(B + o_hoff);
+  int* roots2 = (int*)(B + o_roots2);
+  int* ncomp2 = (int*)(B + o_ncomp2);
+  int* lab2 = (int*)(B + o_lab2);
+  int* size2 = (int*)(B + o_size2);
+  w.iarea = (int*)(B + o_iarea), w.ibox = (int*)(B + o_ibox), w.isx = (unsigned long long*)(B + o_isx), w.isy = (unsigned long long*)(B + o_isy);
+  w.itype = (int*)(B + o_itype);
+
+  {
+    const size_t offs[8] = {o_blb, o_hn, o_vn, o_sobh, o_sobv, o_dist, o_marker, o_mk};
+    const size_t byt[8] = {(size_t)T, (size_t)T * 4, (size_t)T * 4, (size_t)T * 8, (size_t)T * 8, (size_t)T * 8, (size_t)T * 4, (size_t)T};
+    for (int i = 0; i < 8; ++i) h->pp_dbg_off[i] = offs[i], h->pp_dbg_bytes[i] = byt[i];
+  }
+  h->last_launches = 0;
+  const int g = (int)std::min<long long>((T + PP_THREADS - 1) / PP_THREADS, (long long)h->sm_count * 32);
+  const dim3 g2(std::max(1, std::min(64, (P + PP_THREADS - 1) / PP_THREADS)), N);
+  const int gN = (N + PP_THREADS - 1) / PP_THREADS;
+
+  // 1. foreground: threshold -> CCL -> keep components > 9 px  (hovernet.py:541-545)
+  PP_LAUNCH(h, pp_threshold, g, PP_THREADS, np_map, T, w.fg);
+  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.fg, P, T, w.lab, w.size, w.bbox, w.border);
+  PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.fg, H, W, T, w.lab);
+  PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, w.lab, w.size, w.bbox, w.border);
+  PP_LAUNCH(h, pp_rank_roots, N, 1024, w.lab, P, w.cid, w.roots, w.ncomp);
+  PP_LAUNCH(h, pp_keep_large, g, PP_THREADS, w.lab, w.size, w.cid, P, T, 9, w.blb, (int*)nullptr);
+  // 2. normalised gradients (hovernet.py:547-590)
+  PP_LAUNCH(h, pp_mm_init, gN, PP_THREADS, N, w.mm, w.mm64);
+  PP_LAUNCH(h, pp_minmax_hv, g2, PP_THREADS, hv_map, P, w.mm);
+  PP_LAUNCH(h, pp_normalize_hv, g, PP_THREADS, hv_map, P, T, w.mm, w.hn, w.vn);
+  PP_LAUNCH(h, pp_sobel_rows, g, PP_THREADS, w.hn, w.vn, H, W, T, w.rowh, w.rowv);
+  PP_LAUNCH(h, pp_sobel_cols, g, PP_THREADS, w.rowh, w.rowv, H, W, T, w.sobh, w.sobv);
+  PP_LAUNCH(h, pp_minmax_sobel, g2, PP_THREADS, w.sobh, w.sobv, P, w.mm64);
+  // 3. energy, distance, seeds (hovernet.py:592-603)
+  PP_LAUNCH(h, pp_energy, g, PP_THREADS, w.sobh, w.sobv, w.mm64, w.blb, P, T, w.dist0, w.mk);
+  PP_LAUNCH(h, pp_blur_rows, g, PP_THREADS, w.dist0, W, T, w.rowh);
+  PP_LAUNCH(h, pp_blur_cols, g, PP_THREADS, w.rowh, H, W, T, w.dist);
+  // 4. fill holes (hovernet.py:604): CCL of the complement, holes = components that do not touch the border
+  PP_LAUNCH(h, pp_invert, g, PP_THREADS, w.mk, T, w.fg);
+  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.fg, P, T, lab2, size2, (int*)nullptr, w.border);
+  PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.fg, H, W, T, lab2);
+  PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, lab2, size2, (int*)nullptr, w.border);
+  PP_LAUNCH(h, pp_fill_holes, g, PP_THREADS, w.mk, lab2, w.border, P, T, w.tmp);
+  // 5. opening with the 5x5 ellipse (hovernet.py:605-606)
+  PP_LAUNCH(h, pp_morph, g, PP_THREADS, w.tmp, H, W, T, 0, w.fg);
+  PP_LAUNCH(h, pp_morph, g, PP_THREADS, w.fg, H, W, T, 1, w.mk);
+  // 6. label the seeds, drop <= 9 px, keep ids (hovernet.py:607-614)
+  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.mk, P, T, lab2, size2, (int*)nullptr, w.border);
+  PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.mk, H, W, T, lab2);
+  PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, lab2, size2, (int*)nullptr, w.border);
+  PP_LAUNCH(h, pp_rank_roots, N, 1024, lab2, P, w.cid, roots2, ncomp2);
+  PP_LAUNCH(h, pp_keep_large, g, PP_THREADS, lab2, size2, w.cid, P, T, 9, (uint8_t*)nullptr, w.marker);
+  // 7. watershed (hovernet.py:616)
+  TIAB_CUDA_OK(h, cudaMemsetAsync(inst_map, 0, (size_t)T * 4, s));
+  PP_LAUNCH(h, pp_heap_offsets, gN, PP_THREADS, w.roots, w.ncomp, w.size, P, N, w.heap_off);
+  {
+    // one thread per possible component rank (ranks >= ncomp[n] and removed small components exit immediately)
+    const int mc = P;
+    const long long nthreads = (long long)N * mc;
+    PP_LAUNCH(h, pp_watershed, (unsigned)((nthreads + 63) / 64), 64, w.roots, w.ncomp, w.lab, w.size, w.bbox, w.heap_off, w.blb, w.marker,
+              w.dist, H, W, N, mc, w.heap, inst_map);
+  }
+  // 8. instance table (hovernet.py:670-748, without contours)
+  if (want_table) {
+    const int gi = (int)std::min<long long>((TI + PP_THREADS - 1) / PP_THREADS, (long long)h->sm_count * 32);
+    PP_LAUNCH(h, pp_inst_init, gi, PP_THREADS, TI, w.iarea, w.ibox, w.isx, w.isy, w.itype);
+    PP_LAUNCH(h, pp_inst_accum, g, PP_THREADS, inst_map, tp_map, H, W, T, max_inst, w.iarea, w.ibox, w.isx, w.isy, w.itype);
+    PP_LAUNCH(h, pp_inst_finalize, gN, PP_THREADS, N, max_inst, tp_map ? 1 : 0, w.iarea, w.ibox, w.isx, w.isy, w.itype, inst_count, inst_id,
+              inst_box, inst_centroid, inst_type, inst_prob);
+  }
+  return TIAB_OK;
+}
+
+}  // extern "C"

@@ -521,9 +521,25 @@ __device__ __forceinline__ void zero_words(unsigned* p, int n) {
 constexpr float LOG2_255 = 7.9943534368588578f;
 constexpr float LN2_F = 0.69314718055994531f;
 
+// single-instruction MUFU wrappers (the CUDA intrinsics add denormal-range fix-up code around the MUFU op)
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // log2 of byte `sel & 3` of w: PRMT builds 0x4B0000vv (= 8388608 + v as a float), one FADD, one MUFU.LG2
 __device__ __forceinline__ float lg_byte(uint32_t w, uint32_t sel) {
-  return __log2f(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.f);
+  return mufu_lg2(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.f);
 }
 __device__ __forceinline__ void quad_logs(uint32_t w0, uint32_t w1, uint32_t w2, float (&L)[12]) {
   L[0] = lg_byte(w0, 0x7650u), L[1] = lg_byte(w0, 0x7651u), L[2] = lg_byte(w0, 0x7652u), L[3] = lg_byte(w0, 0x7653u);
@@ -535,7 +551,7 @@ __device__ __forceinline__ unsigned byte_of(uint32_t w, int b) { return (w >> (8
 // pseudo-angle key in coarse-bin units, branch-free (see pseudo_angle() in stain_math.cuh)
 __device__ __forceinline__ float phi_key_fast(float p0, float p1) {
   float s = fabsf(p0) + fabsf(p1);
-  float r = __fdividef(p1, s);
+  float r = p1 * mufu_rcp(s);
   float alt = copysignf(2.f, p1) - r;
   r = p0 < 0.f ? alt : r;
   return (r + 2.0f) * (float)(NB / 4);
@@ -639,9 +655,9 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
             const bool m = ysum < ylimit;
             nib |= (m ? 1u : 0u) << j;
             const float mf = m ? 1.f : 0.f;
-            const float t0 = LOG2_255 - __log2f(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j]) - 8388608.f, 1.f));
-            const float t1 = LOG2_255 - __log2f(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j + 1]) - 8388608.f, 1.f));
-            const float t2 = LOG2_255 - __log2f(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j + 2]) - 8388608.f, 1.f));
+            const float t0 = LOG2_255 - mufu_lg2(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j]) - 8388608.f, 1.f));
+            const float t1 = LOG2_255 - mufu_lg2(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j + 1]) - 8388608.f, 1.f));
+            const float t2 = LOG2_255 - mufu_lg2(fmaxf(__uint_as_float(0x4B000000u | vb[3 * j + 2]) - 8388608.f, 1.f));
             const float m0 = t0 * mf, m1 = t1 * mf, m2 = t2 * mf;
             a[0] += mf, a[1] += m0, a[2] += m1, a[3] += m2;
             a[4] = fmaf(m0, t0, a[4]), a[5] = fmaf(m0, t1, a[5]), a[6] = fmaf(m0, t2, a[6]);
@@ -735,9 +751,10 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
             const float u = phi_key_fast(p0, p1);
             const int cbn = coarse_bin(u);
             const bool m = (nib >> j) & 1u;
+            if (!(m && (cbn == tb[0] || cbn == tb[1] || cbn == tb[2] || cbn == tb[3]))) continue;  // rare path below
 #pragma unroll
             for (int t = 0; t < 4; ++t)
-              if (m && cbn == tb[t] && lst[t] == t) {
+              if (cbn == tb[t] && lst[t] == t) {
                 if (attempt == 0) {
                   const unsigned i = atomicAdd(&s_cnt[t], 1u);
                   if (i < (unsigned)LIST_CAP) s_list[t * LIST_CAP + i] = u;
@@ -873,6 +890,7 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
             const float u0 = fmaf(L[3 * j], a[0], fmaf(L[3 * j + 1], a[2], fmaf(L[3 * j + 2], a[4], cbias[0])));
             const float u1 = fmaf(L[3 * j], a[1], fmaf(L[3 * j + 1], a[3], fmaf(L[3 * j + 2], a[5], cbias[1])));
             const int cb0 = coarse_bin(u0), cb1 = coarse_bin(u1);
+            if (!(cb0 == tb[0] || cb0 == tb[1] || cb1 == tb[2] || cb1 == tb[3])) continue;  // rare path below
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float u = t < 2 ? u0 : u1;
@@ -954,7 +972,7 @@ stain_fused_kernel(const StainConst C, const StainTables* __restrict__ tab, cons
 #pragma unroll
               for (int ch = 0; ch < 3; ++ch) {
                 const float x = fmaf(L[3 * j], w[ch], fmaf(L[3 * j + 1], w[3 + ch], fmaf(L[3 * j + 2], w[6 + ch], eb[ch])));
-                const float v = fminf(exp2f(x), 255.f);
+                const float v = fminf(mufu_ex2(x), 255.f);
                 fo[j * 3 + ch] = v;
                 o[j * 3 + ch] = __float2uint_rz(v);
               }

@@ -1,0 +1,84 @@
+"""HoVer-Net post-processing through libtiab200.so (device) + the small host-side tail.
+
+`proc_np_hv_batch` = HoVerNet._proc_np_hv for a batch (hovernet.py:502-616) entirely on the GPU;
+`instance_info` assembles get_instance_info's dictionary (hovernet.py:618-748): box / centroid /
+type / prob come from the device table, contours from cv2.findContours on the host (SURVEY §8f item 2
+keeps contour tracing as the next step to move on-device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from tiatoolbox_b200 import _lib
+
+
+def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.Tensor | None = None, max_inst: int | None = None,
+                     want_table: bool = True):
+    """np_map (N,H,W,1), hv_map (N,H,W,2), tp_map (N,H,W,1) float32 CUDA tensors ->
+    inst_map (N,H,W) int32 CUDA tensor and (optionally) the per-image instance table as CUDA tensors."""
+    assert np_map.is_cuda and np_map.dtype == torch.float32
+    n, h_, w_ = np_map.shape[:3]
+    dev = np_map.device
+    np_map, hv_map = np_map.contiguous(), hv_map.contiguous()
+    tp_map = None if tp_map is None else tp_map.contiguous()
+    inst = torch.empty((n, h_, w_), dtype=torch.int32, device=dev)
+    if max_inst is None:
+        max_inst = max(16, (h_ * w_) // 10 + 1)  # every kept marker has >= 10 pixels
+    table = None
+    if want_table:
+        table = {
+            "count": torch.empty((n,), dtype=torch.int32, device=dev),
+            "id": torch.empty((n, max_inst), dtype=torch.int32, device=dev),
+            "box": torch.empty((n, max_inst, 4), dtype=torch.int32, device=dev),
+            "centroid": torch.empty((n, max_inst, 2), dtype=torch.float64, device=dev),
+            "type": torch.empty((n, max_inst), dtype=torch.int32, device=dev),
+            "prob": torch.empty((n, max_inst), dtype=torch.float64, device=dev),
+        }
+    hd = _lib.handle(dev.index or 0)
+    rc = _lib.lib().tiab_hovernet_postproc(
+        hd, np_map.data_ptr(), hv_map.data_ptr(), None if tp_map is None else tp_map.data_ptr(), n, h_, w_, inst.data_ptr(), max_inst,
+        None if table is None else table["count"].data_ptr(), None if table is None else table["id"].data_ptr(),
+        None if table is None else table["box"].data_ptr(), None if table is None else table["centroid"].data_ptr(),
+        None if table is None else table["type"].data_ptr(), None if table is None else table["prob"].data_ptr(),
+        torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(hd, rc)
+    return inst, table
+
+
+def fetch_debug(which: int, shape, dtype, device=0) -> np.ndarray:
+    out = np.empty(shape, dtype)
+    hd = _lib.handle(device)
+    _lib.check(hd, _lib.lib().tiab_dbg_postproc_fetch(hd, which, out.ctypes.data, torch.cuda.current_stream(device).cuda_stream))
+    return out
+
+
+def instance_info(inst_map: np.ndarray, table_row: dict, offset=(0, 0), with_contours: bool = True) -> dict:
+    """get_instance_info's dict for ONE image from the device table (numpy views of one image's rows)."""
+    import cv2
+
+    offset = np.asarray(offset)
+    info = {}
+    for k in range(int(table_row["count"])):
+        inst_id = int(table_row["id"][k])
+        box = table_row["box"][k].astype(np.int64).copy()
+        rec = {"box": None, "centroid": None, "contours": None, "prob": None, "type": None}
+        if with_contours:
+            crop = (inst_map[box[1]:box[3], box[0]:box[2]] == inst_id).astype(np.uint8)
+            contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].astype(np.int32)
+            contour = np.squeeze(contour)
+            if contour.shape[0] < 3 or len(contour.shape) != 2:  # hovernet.py:696-701
+                continue
+            rec["contours"] = contour + (box[:2] + offset)[None]
+        rec["centroid"] = table_row["centroid"][k] + offset
+        box[:2] += offset
+        box[2:] += offset
+        rec["box"] = box
+        t = int(table_row["type"][k])
+        if t >= 0:
+            rec["type"] = t
+            rec["prob"] = float(table_row["prob"][k])
+        info[inst_id] = rec
+    return info
