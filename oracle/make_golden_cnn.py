@@ -47,7 +47,48 @@ def make_hovernet() -> None:
 def make_cnn() -> None:
     GOLDEN.mkdir(parents=True, exist_ok=True)
     make_hovernet()
+    make_resnet18()
+    make_unet()
 
 
 def make_postproc() -> None:
     pass
+
+
+def make_resnet18() -> None:
+    from oracle import ref_shim
+    from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
+    from tiatoolbox_b200.models.architecture.vanilla import cnn_forward_reference, cnn_spec
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    m = ref_shim.load_models()
+    sd = seeded_state_dict(cnn_spec("resnet18", 9), seed=0)
+    xcal = torch.from_numpy(he_tiles(8, 224, 224, seed=100)).permute(0, 3, 1, 2).float() / 255.0
+    stats = calibrate(sd, lambda s, x: cnn_forward_reference(s, x, "resnet18"), xcal)
+    np.savez_compressed(GOLDEN / "resnet18_bn_calib.npz", **{k: v.numpy() for k, v in stats.items()})
+    net = m.vanilla.CNNModel("resnet18", 9).eval()
+    net.load_state_dict(sd)
+    tiles = he_tiles(16, 224, 224, seed=0)
+    # the engine feeds ToTensor-scaled float32 NHWC in [0, 1] (dataset/classification.py:30-63)
+    probs = m.vanilla.CNNModel.infer_batch(net, torch.from_numpy(tiles.astype(np.float32) / 255.0), device="cpu")
+    np.savez_compressed(GOLDEN / "resnet18_golden.npz", probs=np.asarray(probs, np.float32))
+    print("resnet18 golden:", probs.shape, probs[0])
+
+
+def make_unet() -> None:
+    from oracle import ref_shim
+    from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
+    from tiatoolbox_b200.models.architecture.unet import unet_forward_reference, unet_spec
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    m = ref_shim.load_models()
+    sd = seeded_state_dict(unet_spec(3, 2, (3,)), seed=0)
+    xcal = torch.from_numpy(he_tiles(2, 256, 256, seed=100)).permute(0, 3, 1, 2).float()
+    stats = calibrate(sd, lambda s, x: unet_forward_reference(s, x), xcal)
+    np.savez_compressed(GOLDEN / "unet_bn_calib.npz", **{k: v.numpy() for k, v in stats.items()})
+    net = m.unet.UNetModel(3, 2, "resnet50", decoder_block=[3]).eval()
+    net.load_state_dict(sd)
+    tiles = he_tiles(2, 256, 256, seed=0)
+    probs = m.unet.UNetModel.infer_batch(net, torch.from_numpy(tiles), device="cpu")
+    np.savez_compressed(GOLDEN / "unet_golden.npz", probs=np.asarray(probs, np.float32))
+    print("unet golden:", probs.shape, probs.mean(axis=(0, 1, 2)))

@@ -21,8 +21,8 @@ class ParamSpec(OrderedDict):
         if bias:
             self[name + ".bias"] = ((cout,), "bias")
 
-    def bn(self, name, c):
-        self[name + ".weight"] = ((c,), "bn_w")
+    def bn(self, name, c, gain=1.0):
+        self[name + ".weight"] = ((c,), "bn_w" if gain == 1.0 else f"bn_w:{gain}")
         self[name + ".bias"] = ((c,), "bn_b")
         self[name + ".running_mean"] = ((c,), "bn_mean")
         self[name + ".running_var"] = ((c,), "bn_var")
@@ -51,8 +51,10 @@ def seeded_state_dict(spec: ParamSpec, seed: int = 0) -> OrderedDict:
             t = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5 * gain
         elif kind == "fc_w":
             t = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
-        elif kind == "bn_w":
-            t = torch.rand(shape, generator=g) * 0.4 + 0.8
+        elif kind.startswith("bn_w"):
+            # "bn_w:<gain>": small gamma on the BN that closes a residual branch (zero-init-residual practice)
+            gain = float(kind.split(":")[1]) if ":" in kind else 1.0
+            t = (torch.rand(shape, generator=g) * 0.4 + 0.8) * gain
         elif kind in ("bn_b", "bias", "bn_mean"):
             t = torch.randn(shape, generator=g) * 0.1
         elif kind == "bn_var":
