@@ -186,3 +186,94 @@ def hovernet_heads_reference(out: OrderedDict) -> tuple[torch.Tensor, ...]:
         tp = torch.argmax(F.softmax(o["tp"], dim=-1), dim=-1, keepdim=True).type(torch.float32)
         return o["np"], o["hv"], tp
     return o["np"], o["hv"]
+
+
+# =================================================================================================
+# Model class (API mirror of tiatoolbox/models/architecture/hovernet.py:264-910)
+# =================================================================================================
+from tiatoolbox_b200.models.models_abc import ModelABC  # noqa: E402
+
+
+class HoVerNet(ModelABC):
+    """HoVer-Net on the B200.  Same constructor / `infer_batch` / `postproc` contract as the reference."""
+
+    def __init__(self, num_input_channels: int = 3, num_types: int | None = None, mode: str = "original",
+                 nuc_type_dict: dict | None = None) -> None:
+        super().__init__()
+        if mode not in ["original", "fast"]:
+            msg = f"Invalid mode {mode} for HoVerNet. Only support `original` or `fast`."
+            raise ValueError(msg)
+        self.mode = mode
+        self.num_types = num_types
+        self.nuc_type_dict = nuc_type_dict
+        self.tasks = ["nuclei_segmentation"]
+        self.class_dict = {self.tasks[0]: nuc_type_dict}
+        self.num_input_channels = num_input_channels
+        self._sd = seeded_state_dict(hovernet_spec(num_input_channels, num_types, mode), seed=0)
+
+    def forward(self, input_tensor: torch.Tensor) -> OrderedDict:
+        """fp32 PyTorch forward (NCHW in [0, 255]) — the parity reference, not the hot path."""
+        sd = {k: v.to(input_tensor.device) for k, v in self._sd.items()}
+        return hovernet_forward_reference(sd, input_tensor, self.mode, self.num_types)
+
+    def _build_plan(self, batch, device, shape):
+        from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan
+
+        size = None if shape is None else int(shape[0])
+        return HoVerNetPlan(self._sd, batch=batch, device=device, mode=self.mode, num_types=self.num_types, in_size=size,
+                            precision=self.precision)
+
+    @staticmethod
+    def infer_batch_device(model: "HoVerNet", batch_data, *, device) -> tuple[torch.Tensor, ...]:
+        """Like infer_batch but the head maps stay on the device (views valid until the next call)."""
+        x = ModelABC._as_device_u8(batch_data, device)
+        n = x.shape[0]
+        plan_b = getattr(model, "_plan_batch", None) or n
+        if n > plan_b:
+            msg = f"batch of {n} exceeds the plan batch {plan_b}"
+            raise ValueError(msg)
+        plan = model.plan_for(plan_b, device, x.shape[1:3])
+        if n < plan_b:
+            pad = torch.zeros((plan_b - n, *x.shape[1:]), dtype=torch.uint8, device=x.device)
+            x = torch.cat([x, pad])
+        outs = plan.forward(x)
+        return tuple(o[:n] for o in outs)
+
+    @staticmethod
+    def infer_batch(model: "HoVerNet", batch_data, *, device) -> tuple[np.ndarray, ...]:
+        """hovernet.py:861-910: (np, hv[, tp]) float32 numpy arrays, NHWC."""
+        outs = HoVerNet.infer_batch_device(model, batch_data, device=device)
+        return tuple(o.cpu().numpy() for o in outs)
+
+    def postproc(self, raw_maps, offset: tuple[int, int] = (0, 0)) -> tuple[dict, ...]:
+        """hovernet.py:751-859 for one image: device watershed + instance table, host contours."""
+        from tiatoolbox_b200.models import postproc as pp
+
+        dev = self._device
+        if len(raw_maps) == 3:
+            np_map, hv_map, tp_map = raw_maps
+        else:
+            np_map, hv_map = raw_maps
+            tp_map = None
+        t = [torch.as_tensor(np.asarray(a), dtype=torch.float32).to(dev)[None] for a in (np_map, hv_map)]
+        tt = None if tp_map is None else torch.as_tensor(np.asarray(tp_map), dtype=torch.float32).to(dev)[None]
+        inst, table = pp.proc_np_hv_batch(t[0], t[1], tt)
+        pred_inst = inst[0].cpu().numpy()
+        row = {k: v[0].cpu().numpy() for k, v in table.items()}
+        info = pp.instance_info(pred_inst, row, offset)
+        return (pack_instance_result(self.tasks[0], pred_inst, info),)
+
+
+def pack_instance_result(task: str, pred_inst: np.ndarray, info: dict) -> dict:
+    """The reference's per-image result dict (hovernet.py:828-859 + _inst_dict_for_dask_processing :913-932)."""
+    if not info:
+        empty = np.empty(shape=0)
+        info_ = {"box": empty, "centroid": empty, "contours": empty, "prob": empty, "type": empty}
+    else:
+        info_ = {}
+        for key in ("box", "centroid", "contours", "prob", "type"):
+            col = np.empty(len(info), dtype=object)
+            for i, rec in enumerate(info.values()):
+                col[i] = rec[key]
+            info_[key] = col
+    return {"task_type": task, "predictions": pred_inst, "info_dict": info_, "seg_type": "instance"}

@@ -57,3 +57,62 @@ def unet_infer_tail_reference(logits: torch.Tensor) -> torch.Tensor:
     ch, cw = (2 * h) // 2, (2 * w) // 2  # crop_shape = [H_in // 2, W_in // 2] with H_in = 2h
     t, l_ = (2 * h - ch) // 2, (2 * w - cw) // 2
     return probs[:, :, t:t + ch, l_:l_ + cw].permute(0, 2, 3, 1).contiguous()
+
+
+# =================================================================================================
+# Model class (API mirror of tiatoolbox/models/architecture/unet.py:231-476)
+# =================================================================================================
+import numpy as np  # noqa: E402
+
+from tiatoolbox_b200.models.architecture._params import seeded_state_dict  # noqa: E402
+from tiatoolbox_b200.models.models_abc import ModelABC  # noqa: E402
+
+
+class UNetModel(ModelABC):
+    """U-Net with a ResNet-50 encoder (`fcn-tissue_mask`)."""
+
+    def __init__(self, num_input_channels: int = 2, num_output_channels: int = 2, encoder: str = "resnet50",
+                 encoder_levels: list[int] | None = None, decoder_block: tuple[int] | None = None, skip_type: str = "add") -> None:
+        super().__init__()
+        if encoder.lower() not in {"resnet50", "unet"}:
+            msg = f"Unknown encoder `{encoder}`"
+            raise ValueError(msg)
+        if skip_type.lower() not in {"add", "concat"}:
+            msg = f"Unknown type of skip connection: `{skip_type}`"
+            raise ValueError(msg)
+        if encoder.lower() != "resnet50" or skip_type.lower() != "add" or num_input_channels != 3:
+            msg = "the B200 path implements UNetModel(3, C, encoder='resnet50', skip_type='add') (fcn-tissue_mask)"
+            raise NotImplementedError(msg)
+        self.decoder_block = tuple(decoder_block) if decoder_block is not None else (3, 3)
+        self.num_output_channels = num_output_channels
+        self.skip_type = skip_type.lower()
+        self._sd = seeded_state_dict(unet_spec(num_input_channels, num_output_channels, self.decoder_block), seed=0)
+
+    def forward(self, imgs: torch.Tensor, *args, **kwargs) -> torch.Tensor:  # noqa: ARG002
+        sd = {k: v.to(imgs.device) for k, v in self._sd.items()}
+        return unet_forward_reference(sd, imgs, self.decoder_block)
+
+    def _build_plan(self, batch, device, shape):
+        from tiatoolbox_b200.models.resnet_plan import UNetPlan
+
+        return UNetPlan(self._sd, batch=batch, device=device, in_size=int(shape[0]), num_output_channels=self.num_output_channels,
+                        decoder_block=self.decoder_block, precision=self.precision)
+
+    def postproc(self, image: np.ndarray) -> np.ndarray:
+        """argmax along the last axis (unet.py:470-476)."""
+        return np.argmax(image, axis=-1)
+
+    @staticmethod
+    def infer_batch_device(model: "UNetModel", batch_data, *, device) -> torch.Tensor:
+        x = ModelABC._as_device_u8(batch_data, device)
+        n = x.shape[0]
+        plan_b = getattr(model, "_plan_batch", None) or n
+        plan = model.plan_for(plan_b, device, x.shape[1:3])
+        if n < plan_b:
+            x = torch.cat([x, torch.zeros((plan_b - n, *x.shape[1:]), dtype=torch.uint8, device=x.device)])
+        return plan.forward(x)[:n]
+
+    @staticmethod
+    def infer_batch(model: "UNetModel", batch_data, *, device) -> np.ndarray:
+        """unet.py:420-468 -> (N, H/2, W/2, C) float32 probabilities."""
+        return UNetModel.infer_batch_device(model, batch_data, device=device).cpu().numpy()

@@ -1,0 +1,183 @@
+"""EngineABC — patch-mode orchestration on the B200.
+
+Keeps the constructor and `run()` surface of tiatoolbox/models/engine/engine_abc.py:280-335, 1684-1829
+(`predict` is kept as an alias of `run`: the 1.x name BASELINE.json remembers).  What changes is the data
+flow of `_run_patch_mode` (:1374-1488): the reference does one H2D + one blocking D2H per batch and keeps
+everything downstream on the CPU; here a batch goes pinned host -> device once, stain normalisation (when
+the model's `preproc_func` is a B200 `StainNormalizer.transform`), the network and the post-processing all
+run on the device, and only the final results come back.
+
+Multi-GPU (one process per GPU, torchrun): patches are sharded in contiguous index blocks (row-major grid
+order of tools/patchextraction.py:576-591 is preserved) with zero traffic during compute and ONE all-gather
+of the results at the end (NCCL).
+
+Scope: `patch_mode=True`, `output_type="dict"`.  WSI mode / zarr / AnnotationStore outputs
+are the callers and data formats around the hot path and raise NotImplementedError here.
+"""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from tiatoolbox_b200.models.architecture import get_pretrained_model
+from tiatoolbox_b200.models.models_abc import ModelABC
+
+logger = logging.getLogger(__name__)
+
+
+def cast_to_min_dtype(array: np.ndarray) -> np.ndarray:
+    """utils/misc.py:1925-1961: bool if max == 1 else the smallest unsigned integer type."""
+    max_value = np.max(array) if array.size else 0
+    if max_value == 1:
+        return array.astype(bool)
+    for max_allowed, dtype in ((255, np.uint8), (65535, np.uint16), (2**32 - 1, np.uint32), (2**64 - 1, np.uint64)):
+        if max_value <= max_allowed:
+            return array.astype(dtype)
+    return array
+
+
+class EngineABC:
+    """Template: run -> shard -> batches -> model on device -> post-process -> gather -> dict."""
+
+    def __init__(self, model: str | ModelABC, batch_size: int = 8, num_workers: int = 0, weights: str | Path | None = None, *,
+                 device: str = "cuda", verbose: bool = False) -> None:
+        self.batch_size = batch_size
+        self.num_workers = num_workers  # kept for API compatibility: patches are fed from host arrays, no DataLoader
+        self.verbose = verbose
+        self.ioconfig = None
+        if isinstance(model, str):
+            self.model, self.ioconfig = get_pretrained_model(model, weights)
+        elif isinstance(model, ModelABC):
+            self.model = model
+            if weights is not None:
+                self.model.load_weights_from_file(weights)
+        else:
+            msg = "model must be a registry name or a tiatoolbox_b200 ModelABC (no CPU / generic nn.Module fallback on this path)"
+            raise TypeError(msg)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            msg = "tiatoolbox_b200 engines need a CUDA device: the hot path has no CPU fallback"
+            raise ValueError(msg)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.device = dev
+        self.model.to(dev)
+        self.return_probabilities = False
+        self.return_labels = False
+        self.labels = None
+        self.drop_keys: list[str] = []
+
+    # ---- distributed helpers ----
+    @staticmethod
+    def _dist():
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist, dist.get_rank(), dist.get_world_size()
+        return None, 0, 1
+
+    @staticmethod
+    def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+        """Contiguous block [r*ceil(n/R), (r+1)*ceil(n/R))."""
+        per = -(-n // world)
+        return min(n, rank * per), min(n, (rank + 1) * per)
+
+    @staticmethod
+    def _all_gather_rows(t: torch.Tensor, n_total: int) -> torch.Tensor:
+        """All-gather per-patch result rows (dim 0) of every rank's contiguous shard (one collective;
+        NCCL on GPUs, gloo in the CPU tests).  A rank whose shard is empty learns the row shape first."""
+        dist, rank, world = EngineABC._dist()
+        if dist is None:
+            return t
+        shape = torch.zeros(8, dtype=torch.long, device=t.device)
+        shape[0] = t.dim()
+        for i, d in enumerate(t.shape[1:]):
+            shape[1 + i] = d if t.shape[0] else 0
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+        if t.shape[0] == 0:
+            t = torch.zeros((0, *[int(v) for v in shape[1:int(shape[0])]]), dtype=t.dtype, device=t.device)
+        per = -(-n_total // world)
+        pad = per - t.shape[0]
+        if pad:
+            t = torch.cat([t, torch.zeros((pad, *t.shape[1:]), dtype=t.dtype, device=t.device)])
+        out = torch.empty((world * per, *t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out[:n_total]
+
+    # ---- input handling ----
+    @staticmethod
+    def _as_patch_array(images) -> np.ndarray:
+        if isinstance(images, np.ndarray):
+            arr = images
+        elif isinstance(images, (list, tuple)) and len(images) and isinstance(images[0], np.ndarray):
+            arr = np.stack(images)
+        else:
+            msg = "patch_mode expects a (N, H, W, 3) array or a list of HxWx3 arrays (file / WSI inputs are outside the B200 path)"
+            raise NotImplementedError(msg)
+        if arr.ndim != 4 or arr.shape[-1] != 3:
+            msg = f"expected (N, H, W, 3) patches, got {arr.shape}"
+            raise ValueError(msg)
+        if arr.dtype != np.uint8:
+            arr = np.clip(np.rint(arr), 0, 255).astype(np.uint8)
+        return np.ascontiguousarray(arr)
+
+    def _device_preproc(self, x: torch.Tensor) -> torch.Tensor:
+        """Apply model.preproc_func on the device when it is a B200 stain normaliser's transform
+        (the wiring of examples/inference-pipelines/slide-graph.ipynb); other callables run per patch on the host
+        like the reference's dataset does (dataset_abc.py:439, 522)."""
+        from tiatoolbox_b200.tools.stainnorm import StainNormalizer
+
+        func = self.model.preproc_func
+        owner = getattr(func, "__self__", None)
+        if isinstance(owner, StainNormalizer) and getattr(func, "__name__", "") == "transform":
+            return owner.transform_batch(x, raise_on_error=False)
+        if func is self.model.preproc or func is ModelABC.preproc:
+            return x
+        host = x.cpu().numpy()
+        return torch.from_numpy(np.stack([np.asarray(func(p)) for p in host])).to(x.device)
+
+    # ---- the public entry point ----
+    def run(self, images, *, masks=None, input_resolutions=None, patch_input_shape=None, ioconfig=None,  # noqa: ARG002
+            patch_mode: bool = True, save_dir=None, overwrite: bool = False, output_type: str = "dict", **kwargs):  # noqa: ARG002
+        if not patch_mode:
+            msg = "WSI mode (stitching / tile de-duplication) is the next row of the hot-path scope (SURVEY.md §8f), not built yet"
+            raise NotImplementedError(msg)
+        if output_type.lower() != "dict":
+            msg = "only output_type='dict' is produced on the B200 path (zarr / AnnotationStore are result persistence)"
+            raise NotImplementedError(msg)
+        for k, v in kwargs.items():  # the reference sets every kwarg as an attribute (engine_abc.py:1306-1307)
+            setattr(self, k, v)
+        patches = self._as_patch_array(images)
+        n_total = len(patches)
+        dist, rank, world = self._dist()
+        lo, hi = self.shard_bounds(n_total, rank, world)
+        self.model._plan_batch = self.batch_size
+        raw = self.infer_patches(patches[lo:hi])
+        out = self.post_process_patches(raw, n_total)
+        if self.labels is not None:
+            out["labels"] = np.asarray(self.labels)
+        return out
+
+    predict = run  # tiatoolbox 1.x name
+
+    # ---- to be specialised ----
+    def infer_patches(self, patches: np.ndarray):
+        raise NotImplementedError
+
+    def post_process_patches(self, raw, n_total: int) -> dict:
+        raise NotImplementedError
+
+    def _batches(self, patches: np.ndarray):
+        """Yield device uint8 batches (pinned staging, async H2D) after the device-side preproc."""
+        n = len(patches)
+        if n == 0:
+            return
+        pin = torch.empty((min(self.batch_size, n), *patches.shape[1:]), dtype=torch.uint8).pin_memory()
+        for i in range(0, n, self.batch_size):
+            chunk = patches[i:i + self.batch_size]
+            pin[: len(chunk)].copy_(torch.from_numpy(chunk))
+            x = pin[: len(chunk)].to(self.device, non_blocking=True)
+            yield self._device_preproc(x)

@@ -1,0 +1,69 @@
+"""NucleusInstanceSegmentor / MultiTaskSegmentor (mirror of tiatoolbox/models/engine/multi_task_segmentor.py,
+nucleus_instance_segmentor.py; patch mode): `hovernet_fast-pannuke`.
+
+The reference runs HoVerNet.postproc per patch in a Python loop on the CPU (multi_task_segmentor.py:825-828);
+here the watershed + instance table run on the device for the whole batch, the instance maps are all-gathered
+over NCCL, and only contour tracing (cv2.findContours) remains on the host."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from tiatoolbox_b200.models import postproc as pp
+from tiatoolbox_b200.models.engine.engine_abc import EngineABC
+
+
+class MultiTaskSegmentor(EngineABC):
+    """run(...) -> single task flattened (multi_task_segmentor.py:1697-1704):
+    {"predictions": (N, h, w) int32, "box", "centroid", "contours", "prob", "type": length-N lists,
+     ["probabilities": [np, hv, tp]]}."""
+
+    with_contours = True
+
+    def infer_patches(self, patches: np.ndarray):
+        insts, tables, heads = [], [], []
+        for x in self._batches(patches):
+            outs = type(self.model).infer_batch_device(self.model, x, device=self.device)
+            np_map, hv_map = outs[0], outs[1]
+            tp_map = outs[2] if len(outs) > 2 else None
+            inst, table = pp.proc_np_hv_batch(np_map, hv_map, tp_map)
+            insts.append(inst)
+            tables.append({k: v.cpu().numpy() for k, v in table.items()})
+            if self.return_probabilities:
+                heads.append([o.clone() for o in outs])
+        return insts, tables, heads
+
+    def post_process_patches(self, raw, n_total: int) -> dict:
+        insts, tables, heads = raw
+        dist, rank, world = self._dist()
+        local = torch.cat(insts) if insts else torch.empty((0, 1, 1), dtype=torch.int32, device=self.device)
+        inst_all = self._all_gather_rows(local, n_total).cpu().numpy()
+        lo, _ = self.shard_bounds(n_total, rank, world)
+        infos = []
+        k = lo
+        for t in tables:
+            for i in range(len(t["count"])):
+                row = {key: v[i] for key, v in t.items()}
+                infos.append(pp.instance_info(inst_all[k], row, with_contours=self.with_contours))
+                k += 1
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, infos)
+            infos = [x for part in gathered for x in part]
+        out = {"predictions": inst_all}
+        from tiatoolbox_b200.models.architecture.hovernet import pack_instance_result
+
+        cols = {key: [] for key in ("box", "centroid", "contours", "prob", "type")}
+        for i, info in enumerate(infos):
+            packed = pack_instance_result("nuclei_segmentation", inst_all[i], info)["info_dict"]
+            for key in cols:
+                cols[key].append(packed[key])
+        out.update(cols)
+        if self.return_probabilities and heads:
+            out["probabilities"] = [self._all_gather_rows(torch.cat([h[j] for h in heads]), n_total).cpu().numpy()
+                                    for j in range(len(heads[0]))]
+        return out
+
+
+class NucleusInstanceSegmentor(MultiTaskSegmentor):
+    """Thin subclass kept for API compatibility (nucleus_instance_segmentor.py:103-174)."""
