@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py — the driver's benchmark contract for the stain + patch-CNN hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload macenko_hovernet|macenko]
 
-One "step" = one pass of the hot path over one batch of synthetic 256x256x3 uint8 tiles
-(SURVEY.md §8d generator, seeded).  At N>1 the driver launches this file under torchrun, one rank
-per GPU; tiles are sharded across ranks (weak scaling: per-GPU batch fixed) with no data-path
-collective except the final all-gather of the per-tile results.  Rank 0 prints ONE JSON line.
+Metric (BASELINE.json): patches/sec on 256x256x3 tiles for Macenko stain normalisation + HoVer-Net
+(hovernet_fast-pannuke architecture, seeded weights) incl. the on-device watershed post-processing.
+One "step" = one pass of that path over one batch of synthetic tiles per GPU (SURVEY.md §8d generator).
+At N>1 the driver launches this file under torchrun, one rank per GPU; tiles are sharded across ranks
+(weak scaling: per-GPU batch fixed), no data-path collective except the all-gather of the final instance
+maps.  Rank 0 prints ONE JSON line.
 
-`value`     device-timed whole-job patches/s with inputs resident in HBM (CUDA events, max over ranks)
-`e2e`       the same metric through the public API with HOST buffers (H2D + kernels + D2H timed)
-`roofline`  the dominant kernel's algorithmic bytes / its measured duration vs MEASURED_PEAKS.json
-`cpu_baseline` the numpy oracle (a port of the reference's CPU path) timed on this box's host cores
+`value`        device-timed whole-job patches/s, inputs resident in HBM (CUDA events, max over ranks)
+`e2e`          same metric through the public engine API (NucleusInstanceSegmentor.run with the stain
+               normaliser installed as preproc_func) with HOST numpy buffers: H2D + kernels + D2H + host tail
+`roofline`     the dominant kernel (conv_gemm_kernel, tensor-bound): algorithmic FLOPs / its summed launch
+               durations (CUDA events per launch, measured live) vs MEASURED_PEAKS.json
+`roofline_stain` the fused stain kernel (HBM-bound) measured the same way
+`cpu_baseline` the CPU port of the reference path (numpy oracle + fp32 torch forward + post-proc oracle)
 """
 from __future__ import annotations
 
@@ -31,16 +36,21 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 PATCH = 256
-BYTES_PER_PATCH_ALGO = 2 * PATCH * PATCH * 3  # read u8 once + write u8 once
-METRIC = "patches/sec (256x256x3) Macenko stain-normalisation transform"
+STAIN_BYTES_PER_PATCH = 2 * PATCH * PATCH * 3      # read u8 once + write u8 once
+HOVERNET_GFLOP_PER_PATCH = 297.87                    # SURVEY.md Appendix C (2*MAC of all convs)
+METRICS = {
+    "macenko_hovernet": "patches/sec (256x256x3) Macenko + HoVer-Net (hovernet_fast) incl. on-device post-processing",
+    "macenko": "patches/sec (256x256x3) Macenko stain-normalisation transform",
+}
 
 
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]), "tf_sustained": float(d["bf16_tflops_sustained"]),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -100,85 +110,113 @@ def _tiles(n_unique: int, seed: int = 0) -> np.ndarray:
     return he_tiles(n_unique, PATCH, PATCH, seed=seed)
 
 
-def _oracle_worker(args):
-    import numpy as np  # noqa: F811
+def _hovernet_weights():
+    from tiatoolbox_b200.models.architecture._params import seeded_state_dict, with_calibration
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
 
+    return with_calibration(seeded_state_dict(hovernet_spec(3, 6, "fast"), seed=0), ROOT / "tests" / "golden" / "hovernet_fast_bn_calib.npz")
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: a port of the reference's CPU path (the Python reference cannot travel to the GPU box)
+# ---------------------------------------------------------------------------------------------------
+def _cpu_stain_worker(args):
     from oracle import stain_oracle as so
 
     tiles, mt, mc = args
-    return [so.transform("macenko", t.copy(), mt, mc).sum() for t in tiles]
+    return np.stack([so.transform("macenko", t.copy(), mt, mc) for t in tiles])
 
 
-def cpu_baseline(sample: int, procs: int):
-    """Time the numpy oracle (a restatement of tiatoolbox's CPU Macenko transform) on host cores."""
+def cpu_pipeline(workload: str, sample: int, procs: int, threads: int):
+    """Macenko (numpy oracle, `procs` processes) [+ HoVer-Net fp32 torch forward (`threads` threads) + post-proc oracle]."""
+    import torch
+
     from oracle import stain_oracle as so
     from tiatoolbox_b200.synthetic import he_target
 
     tiles = _tiles(sample, seed=0)
     mt, mc = so.fit("macenko", he_target(PATCH, PATCH))
+    t0 = time.perf_counter()
     if procs <= 1:
-        t0 = time.perf_counter()
-        _oracle_worker((tiles, mt, mc))
-        dt = time.perf_counter() - t0
+        norm = _cpu_stain_worker((tiles, mt, mc))
     else:
         import multiprocessing as mp
 
         chunks = [c for c in np.array_split(tiles, procs) if len(c)]
         with mp.get_context("fork").Pool(len(chunks)) as pool:
-            pool.map(_oracle_worker, [(c[:1], mt, mc) for c in chunks])  # warm the workers
-            t0 = time.perf_counter()
-            pool.map(_oracle_worker, [(c, mt, mc) for c in chunks])
-            dt = time.perf_counter() - t0
-    return sample / dt, dt
+            norm = np.concatenate(pool.map(_cpu_stain_worker, [(c, mt, mc) for c in chunks]))
+    t_stain = time.perf_counter() - t0
+    t_net = t_post = 0.0
+    if workload == "macenko_hovernet":
+        from oracle import hovernet_postproc_oracle as po
+        from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_heads_reference
+
+        torch.set_num_threads(threads)
+        sd = _hovernet_weights()
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            outs = []
+            for i in range(0, sample, 4):
+                x = torch.from_numpy(norm[i:i + 4]).permute(0, 3, 1, 2).float()
+                outs.append([o.numpy() for o in hovernet_heads_reference(hovernet_forward_reference(sd, x, "fast", 6))])
+        t_net = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for o in outs:
+            for j in range(len(o[0])):
+                po.postproc(o[0][j], o[1][j], o[2][j])
+        t_post = time.perf_counter() - t0
+    total = t_stain + t_net + t_post
+    return sample / total, {"stain_s": t_stain, "forward_s": t_net, "postproc_s": t_post}
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel
-    to the GPU box) with every host core, on the same workload / metric."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(64, 8 * cores)
-    total = 0
-    t_all = 0.0
-    for _ in range(args.warmup and 1):
-        cpu_baseline(min(sample, 2 * cores), cores)
-    for _ in range(args.steps):
-        v, dt = cpu_baseline(sample, cores)
-        total += sample
-        t_all += dt
-    value = total / t_all
+    sample = 8 if args.workload == "macenko_hovernet" else max(64, 8 * cores)
+    total_s, n = 0.0, 0
+    parts = {}
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        _, parts = cpu_pipeline(args.workload, sample, min(cores, sample), cores)
+        if i >= args.warmup:
+            total_s += time.perf_counter() - t0
+            n += sample
+    value = n / total_s
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "macenko_transform_256", "sample_tiles_per_step": sample},
+        "impl": "reference", "metric": METRICS[args.workload], "value": value, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": args.workload, "sample_tiles_per_step": sample, "last_step_split_s": parts},
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} seeded 256x256x3 tiles per step, multiprocessing over {cores} cores"},
+                         "sample": f"{sample} seeded 256x256x3 tiles per step; numpy Macenko oracle over {min(cores, sample)} processes"
+                                   + ("; fp32 torch HoVer-Net forward on all cores; post-proc oracle (cv2/scipy + restated skimage)"
+                                      if args.workload == "macenko_hovernet" else "")},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=8192, help="tiles per GPU per step (device-resident leg)")
-    ap.add_argument("--e2e-batch", type=int, default=1024, help="tiles per GPU per step (host-buffer leg)")
-    ap.add_argument("--method", default="macenko")
+    ap.add_argument("--workload", default="macenko_hovernet", choices=sorted(METRICS))
+    ap.add_argument("--batch", type=int, default=None, help="tiles per GPU per step (device-resident leg)")
+    ap.add_argument("--e2e-batch", type=int, default=None, help="tiles per GPU per step (host-buffer leg)")
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -187,6 +225,9 @@ def main():
 
     ge.build()
     from tiatoolbox_b200 import _lib
+    from tiatoolbox_b200.models import postproc as pp
+    from tiatoolbox_b200.models.architecture.hovernet import HoVerNet
+    from tiatoolbox_b200.models.engine import NucleusInstanceSegmentor
     from tiatoolbox_b200.synthetic import he_target
     from tiatoolbox_b200.tools.stainnorm import get_normalizer
 
@@ -195,31 +236,48 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    norm = get_normalizer(args.method)
-    norm.device = local_rank
-    norm.fit(he_target(PATCH, PATCH))
-
-    # ---- device-resident leg: B tiles per GPU (inputs + outputs >> 126 MB L2) ----
-    B = args.batch
-    uniq = torch.from_numpy(_tiles(128, seed=rank)).to(dev)
-    x = uniq.repeat((B + 127) // 128, 1, 1, 1)[:B].contiguous()
-    del uniq
+    combined = args.workload == "macenko_hovernet"
+    B = args.batch or (16 if combined else 8192)
+    Be = args.e2e_batch or (32 if combined else 1024)
     lib = _lib.lib()
     h = _lib.handle(local_rank)
 
+    norm = get_normalizer("macenko")
+    norm.device = local_rank
+    norm.fit(he_target(PATCH, PATCH))
+    uniq = torch.from_numpy(_tiles(min(128, max(B, 16)), seed=rank)).to(dev)
+    x = uniq.repeat((B + len(uniq) - 1) // len(uniq), 1, 1, 1)[:B].contiguous()
+
+    plan = None
+    if combined:
+        model = HoVerNet(num_types=6, mode="fast")
+        model.load_state_dict(_hovernet_weights())
+        model.precision = args.precision
+        model.to(dev)
+        plan = model.plan_for(B, dev, (PATCH, PATCH))
+
+    launches = {}
+
     def step():
         out, info = norm.transform_batch(x, return_info=True, raise_on_error=False)
-        if world > 1:  # final result gather: per-tile stain matrices + status (the tile map itself stays sharded)
-            gathered = [torch.empty_like(info["stain_matrix_source"]) for _ in range(world)]
-            dist.all_gather(gathered, info["stain_matrix_source"].contiguous())
-        return out, info
+        launches["stain"] = lib.tiab_last_launch_count(h)
+        if not combined:
+            res = info["stain_matrix_source"]
+        else:
+            np_m, hv_m, tp_m = plan.forward(out)
+            inst, _table = pp.proc_np_hv_batch(np_m, hv_m, tp_m)
+            launches["postproc"] = lib.tiab_last_launch_count(h)
+            res = inst
+        if world > 1:  # the only collective: all-gather of the final result map
+            gathered = torch.empty((world * res.shape[0], *res.shape[1:]), dtype=res.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, res.contiguous())
+        return out, info, res
 
     for _ in range(args.warmup):
-        out, info = step()
+        out, info, res = step()
     torch.cuda.synchronize()
-    launches_per_step = lib.tiab_last_launch_count(h)
     assert int(info["status"].sum().item()) == 0, "synthetic tiles must all normalise"
+    launches_per_step = launches.get("stain", 0) + launches.get("postproc", 0) + (plan.num_launches if plan else 0)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -227,16 +285,15 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for i in range(args.steps):
-        out, info = step()
-        ev[i + 1].record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -244,51 +301,116 @@ def main():
     total_ms = float(t.item())
     value = world * B * args.steps / (total_ms / 1e3)
 
-    # ---- e2e leg: numpy host buffers through the public API (pinned staging, H2D, kernels, D2H) ----
-    Be = args.e2e_batch
-    host_tiles = np.ascontiguousarray(x[:Be].cpu().numpy())
+    # ---- per-kernel timings for the rooflines (CUDA events around every launch; rank 0 only) ----
+    roof = {}
+    if rank == 0:
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+        a, b = ev(), ev()
+        ts = []
+        for _ in range(5):
+            a.record()
+            norm.transform_batch(x, raise_on_error=False)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        roof["stain_ms"] = statistics.median(ts)
+        if combined:
+            conv_ms, conv_fl, conv_mma, aux_ms = 0.0, 0.0, 0.0, 0.0
+            for op in plan.ops:
+                a.record()
+                op()
+                b.record()
+                torch.cuda.synchronize()
+                dt = a.elapsed_time(b)
+                if hasattr(op, "desc"):
+                    conv_ms += dt
+                    conv_fl += op.flops
+                    conv_mma += op.mma_flops
+                else:
+                    aux_ms += dt
+            a.record()
+            pp.proc_np_hv_batch(*plan.forward(out))
+            b.record()
+            torch.cuda.synchronize()
+            roof.update(conv_ms=conv_ms, conv_flops=conv_fl, conv_mma_flops=conv_mma, aux_ms=aux_ms)
+
+    # ---- e2e leg: numpy host buffers through the public API ----
+    host_tiles = np.ascontiguousarray(x[:min(Be, B)].cpu().numpy())
+    if len(host_tiles) < Be:
+        host_tiles = np.concatenate([host_tiles] * (-(-Be // len(host_tiles))))[:Be]
+    if combined:
+        eng = NucleusInstanceSegmentor(model, batch_size=B, device=str(dev))
+        model.preproc_func = norm.transform
+        e2e_call = lambda: eng.run(host_tiles)  # noqa: E731
+        d2h = Be * 164 * 164 * 4
+    else:
+        e2e_call = lambda: norm.transform_batch(host_tiles, raise_on_error=False)  # noqa: E731
+        d2h = Be * PATCH * PATCH * 3 + Be * 68
     for _ in range(2):
-        norm.transform_batch(host_tiles, raise_on_error=False)
+        r = e2e_call()
     if world > 1:
         dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = norm.transform_batch(host_tiles, raise_on_error=False)
+        r = e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Be * args.steps / float(te.item())
-    assert res.shape == host_tiles.shape
+    # under torchrun eng.run shards host_tiles across ranks itself (strong over Be): total work = Be per step
+    e2e_units = Be if (combined and world > 1) else world * Be
+    e2e_value = e2e_units * args.steps / float(te.item())
 
     if rank == 0:
-        peak, peak_src = _peaks()
-        med_ms = statistics.median(kernel_ms)
-        achieved = B * BYTES_PER_PATCH_ALGO / (med_ms / 1e3) / 1e9
+        pk = _peaks()
+        line = {
+            "metric": METRICS[args.workload], "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16x3 (split-fp16 operands, fp32 accumulate)" if args.precision == "fp16x3" else "f16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "tiles_per_gpu_per_step": B, "tile": [PATCH, PATCH, 3],
+                       "model": "hovernet_fast (num_types=6), seeded+calibrated random weights" if combined else None,
+                       "precision": args.precision if combined else "f32",
+                       "l2_policy": ("activations %.1f GB per step >> 126 MB L2" % (plan.bytes_allocated() / 1e9)) if combined else
+                                    f"inputs+outputs {2 * B * PATCH * PATCH * 3 / 1e6:.0f} MB per step > 126 MB L2",
+                       "parallelism": f"patch-shard x{world}, all-gather of the result map"},
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": Be * PATCH * PATCH * 3, "d2h_bytes_per_step": d2h,
+                    "tiles_per_step": Be, "api": "NucleusInstanceSegmentor.run(numpy tiles), preproc_func = MacenkoNormalizer.transform"
+                    if combined else "StainNormalizer.transform_batch(numpy)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        stain_ach = B * STAIN_BYTES_PER_PATCH / (roof["stain_ms"] / 1e3) / 1e9
         traffic = None
         tp = ROOT / "profiles" / "stain_fused_traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-        line = {
-            "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.method}_transform_256", "tiles_per_gpu_per_step": B, "tile": [PATCH, PATCH, 3],
-                       "l2_policy": f"inputs+outputs {2 * B * PATCH * PATCH * 3 / 1e6:.0f} MB per step > 126 MB L2",
-                       "parallelism": f"patch-shard x{world}"},
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": Be * PATCH * PATCH * 3,
-                    "d2h_bytes_per_step": Be * PATCH * PATCH * 3 + Be * 68, "tiles_per_gpu_per_step": Be},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "stain_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": B * BYTES_PER_PATCH_ALGO, "kernel_ms": med_ms},
-            "clocks": clocks,
-        }
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_tile")
+            traffic = None if traffic is None else traffic * B
+        stain_roof = {"bound": "hbm", "kernel": "stain_fused_kernel", "achieved": stain_ach, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": stain_ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
+                      "algorithmic_bytes_per_launch": B * STAIN_BYTES_PER_PATCH, "kernel_ms": roof["stain_ms"]}
+        if combined:
+            ach = roof["conv_flops"] / (roof["conv_ms"] / 1e3) / 1e12
+            line["roofline"] = {
+                "bound": "tensor", "kernel": "conv_gemm_kernel (all launches of one step)", "achieved": ach, "peak": pk["tf_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "algorithmic_flops_per_step": roof["conv_flops"], "kernel_ms_per_step": roof["conv_ms"],
+                "mma_issue_rate_tflops": roof["conv_mma_flops"] / (roof["conv_ms"] / 1e3) / 1e12,
+                "note": "fp16x3 issues 3 tensor-core passes per algorithmic FLOP; aux (memory-bound glue) kernels take "
+                        f"{roof['aux_ms']:.2f} ms per step",
+            }
+            line["roofline_stain"] = stain_roof
+        else:
+            line["roofline"] = stain_roof
         if not args.no_cpu_baseline and world == 1:
-            v, dt = cpu_baseline(64, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": 1, "kind": "port",
-                                    "sample": f"64 seeded 256x256x3 tiles, single process numpy oracle, {dt:.2f} s"}
+            sample = 4 if combined else 64
+            v, parts = cpu_pipeline(args.workload, sample, 1, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": os.cpu_count() if combined else 1, "kind": "port",
+                                    "sample": f"{sample} seeded tiles: numpy Macenko oracle (1 process)"
+                                              + (", fp32 torch HoVer-Net forward (all cores), post-proc oracle" if combined else ""),
+                                    "split_s": parts}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -93,3 +93,13 @@ def calibrate(sd, forward_fn, x):
     finally:
         del sd["__calibrate__"]
     return {k: v.clone() for k, v in sd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+
+
+def with_calibration(sd, npz_path):
+    """Overlay committed BatchNorm running statistics (see `calibrate`) on a seeded state dict."""
+    import numpy as np
+
+    calib = np.load(npz_path)
+    for k in calib.files:
+        sd[k] = torch.from_numpy(calib[k])
+    return sd
