@@ -49,6 +49,10 @@ if len(sys.argv) > 3:  # per-op timing
         d = getattr(op, "desc", None)
         info = f"M={d.M} N={d.N} taps={d.taps} cin={d.cin}" if d is not None else "aux"
         times.append((s.elapsed_time(e) / 3, i, info, fl, mm))
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump([{"ms": t, "op": i, "info": info, "flops": fl, "mma": mm, "name": getattr(plan.ops[i], "__name__", type(plan.ops[i]).__name__)}
+               for t, i, info, fl, mm in times], open(f"gpurun_out/ops_B{batch}_{prec}.json", "w"))
     tot = sum(t[0] for t in times)
     print(f"sum of per-op times {tot:.3f} ms")
     for t, i, info, fl, mm in sorted(times, reverse=True)[:40]:

@@ -39,7 +39,7 @@ namespace tiab {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // fp16: 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int CONV_THREADS = 256;
+constexpr int CONV_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle ; warps 4-11: epilogue (2 per TMEM lane quadrant)
 constexpr int MAX_STAGES = 8;
 
 struct ConvParams {
@@ -185,7 +185,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbarrier_init(&tfull_bar[b], 1);
-      mbarrier_init(&tempty_bar[b], 4);
+      mbarrier_init(&tempty_bar[b], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -268,7 +268,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;    // the two warps of a quadrant take alternate 32-column chunks
     int ab = 0;
     uint32_t aph = 0;
     const int grid_px = p.Hin * p.Win;
@@ -291,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
@@ -477,6 +478,37 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ sr
     const __half hi = __float2half_rn(v);
     out[m * ldout + k] = hi;
     if (out_lo) out[m * ldout + out_lo + k] = __float2half_rn(v - __half2float(hi));
+  }
+}
+
+// 3-channel uint8 stem (7x7 etc.): one thread per 8 consecutive K elements of an output pixel -> one 16-byte store per plane
+__global__ void __launch_bounds__(256) im2col_u8c3_kernel(const uint8_t* __restrict__ src, float u8_scale, int Nimg, int H, int W, int KH,
+                                                          int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, __half* __restrict__ out,
+                                                          int ldout, int Kpad, int out_lo) {
+  const int k8n = Kpad >> 3;
+  const long long total = (long long)Nimg * Ho * Wo * k8n;
+  const int K = KH * KW * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(i % k8n) * 8;
+    const long long m = i / k8n;
+    const int xo = (int)(m % Wo);
+    const int yo = (int)((m / Wo) % Ho);
+    const int img = (int)(m / ((long long)Wo * Ho));
+    const int ybase = yo * stride - pad_t, xbase = xo * stride - pad_l;
+    const uint8_t* sp = src + (long long)img * H * W * 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k % 3, t = k / 3, kw = t % KW, kh = t / KW;
+        const int y = ybase + kh, x = xbase + kw;
+        if (y >= 0 && y < H && x >= 0 && x < W) val = (float)sp[((long long)y * W + x) * 3 + c] * u8_scale;
+      }
+      v[e] = val;
+    }
+    store8(out + m * ldout + k0, out_lo, v);
   }
 }
 
@@ -896,6 +928,13 @@ int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale,
                                                                                   stride, pad_t, pad_l, Ho, Wo, (__half*)out_f16, ldout,
                                                                                   Kpad, out_lo);
     AUX_LAUNCH_CHECK(h, "im2col_vec8");
+    return TIAB_OK;
+  }
+  if (src_is_u8 && C == 3 && ldsrc == 3 && (Kpad % 8) == 0 && (ldout % 8) == 0 && (out_lo % 8) == 0 && ((uintptr_t)out_f16 & 15) == 0) {
+    long long t3 = (long long)N * Ho * Wo * (Kpad >> 3);
+    im2col_u8c3_kernel<<<aux_grid(h, t3, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, u8_scale, N, H, W, KH, KW, stride, pad_t,
+                                                                             pad_l, Ho, Wo, (__half*)out_f16, ldout, Kpad, out_lo);
+    AUX_LAUNCH_CHECK(h, "im2col_u8c3");
     return TIAB_OK;
   }
   long long total = (long long)N * Ho * Wo * Kpad;
