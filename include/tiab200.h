@@ -116,8 +116,8 @@ typedef struct {
   long long x_ld;
   int cin;
   int x_lo_off;         /* 0: fp16 operands.  >0: element offset of the residual plane x_lo = x - fp16(x); the GEMM
-                           then runs the 3-term split A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (w holds [W_hi|W_hi|W_lo] per tap) */
-  const void* w;        /* fp16 [N, taps*segments*ceil64(cin)] K-major (BN folded), row pitch w_ld elements */
+                           then runs the 3-term split A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (w holds [W_hi | W_lo] per tap) */
+  const void* w;        /* fp16 [N, taps*planes*ceil64(cin)] K-major (BN folded), row pitch w_ld elements */
   long long w_ld;
   int M, N, taps;
   int tap_off[TIAB_MAX_TAPS];

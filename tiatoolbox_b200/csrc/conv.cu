@@ -143,22 +143,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BLOCK_N>
+// One pipeline stage holds everything ONE K-chunk of one tap needs:
+//   NSEG == 1 : [A 16 KB][B]                      -> 4 UMMAs  (A*W)
+//   NSEG == 3 : [A_hi 16 KB][A_lo 16 KB][W_hi][W_lo] -> 12 UMMAs (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo), every operand loaded once
+template <int BLOCK_N, int NSEG>
 struct ConvSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NPLANES = NSEG == 3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (200 * 1024 / STAGE_BYTES);
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr, + slack for 1024 B alignment
   static constexpr int TMEM_COLS = (2 * BLOCK_N) <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int NSEG>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-  using S = ConvSmem<BLOCK_N>;
+  using S = ConvSmem<BLOCK_N, NSEG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -171,7 +175,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int kiters = p.taps * p.nseg * p.kchunks;
+  const int kiters = p.taps * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -210,19 +214,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         for (int t = 0; t < p.taps; ++t) {
           const int row = m0 + p.tap_off[t];
-          for (int seg = 0; seg < p.nseg; ++seg) {
-            const CUtensorMap* am = (seg == 1) ? &tmA2 : &tmA;  // segment 1 multiplies the residual plane A_lo
-            const int kbase = (t * p.nseg + seg) * p.kchunks;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbarrier_wait(&empty_bar[s], ph ^ 1u);
-              mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
-              uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-              tma_load_2d(a_dst, am, kc * BLOCK_K, row, &full_bar[s]);
-              tma_load_2d(a_dst + S::A_BYTES, &tmB, (kbase + kc) * BLOCK_K, n0, &full_bar[s]);
-              if (++s == S::STAGES) {
-                s = 0;
-                ph ^= 1u;
-              }
+          // weights of tap t: NSEG == 3 -> [W_hi | W_lo], each kchunks*64 columns
+          const int wbase = t * S::NPLANES * p.kchunks;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbarrier_wait(&empty_bar[s], ph ^ 1u);
+            mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
+            uint8_t* st = smem + s * S::STAGE_BYTES;
+            tma_load_2d(st, &tmA, kc * BLOCK_K, row, &full_bar[s]);
+            if (NSEG == 3) {
+              tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, &full_bar[s]);
+              tma_load_2d(st + 2 * S::A_BYTES, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
+              tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB, (wbase + p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
+            } else {
+              tma_load_2d(st + S::A_BYTES, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
+            }
+            if (++s == S::STAGES) {
+              s = 0;
+              ph ^= 1u;
             }
           }
         }
@@ -244,14 +252,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int k = 0; k < kiters; ++k) {
           mbarrier_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = cvta_smem(smem + s * S::STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + S::A_BYTES);
+          const uint32_t base = cvta_smem(smem + s * S::STAGE_BYTES);
+          if (NSEG == 3) {
+            const uint64_t ahi = make_smem_desc(base), alo = make_smem_desc(base + S::A_BYTES);
+            const uint64_t bhi = make_smem_desc(base + 2 * S::A_BYTES), blo = make_smem_desc(base + 2 * S::A_BYTES + S::B_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-            tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                            (k > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)  // +2 in (addr >> 4) units = 32 bytes = 16 fp16 along K
+              tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+              tcgen05_mma_f16(tmem_d, alo + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, 1u);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+              tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), blo + (uint64_t)(kk * 2), idesc, 1u);
+          } else {
+            const uint64_t adesc = make_smem_desc(base), bdesc = make_smem_desc(base + S::A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+              tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[s]);  // frees the smem stage when these MMAs have consumed it
           if (++s == S::STAGES) {
@@ -812,20 +830,20 @@ static int make_map_2d(tiab_ctx* h, CUtensorMap* map, const void* base, long lon
   return TIAB_OK;
 }
 
-template <int BN>
+template <int BN, int NSEG>
 static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, ConvParams& p,
                        cudaStream_t s) {
-  using S = ConvSmem<BN>;
+  using S = ConvSmem<BN, NSEG>;
   static bool attr_set = false;
   if (!attr_set) {
-    TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN, NSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_tiles = p.N / BN;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = std::min(tiles, h->sm_count);
-  conv_gemm_kernel<BN><<<grid, CONV_THREADS, S::TOTAL, s>>>(ta, ta2, tb, p);
+  conv_gemm_kernel<BN, NSEG><<<grid, CONV_THREADS, S::TOTAL, s>>>(ta, ta2, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     h->err = std::string("conv_gemm launch: ") + cudaGetErrorString(e);
@@ -869,9 +887,9 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   }
   const int nseg = d->x_lo_off ? 3 : 1;
   const int kchunks = (d->cin + BLOCK_K - 1) / BLOCK_K;
-  const long long kcols = (long long)d->taps * nseg * kchunks * BLOCK_K;
+  const long long kcols = (long long)d->taps * (nseg == 3 ? 2 : 1) * kchunks * BLOCK_K;  // per tap: [W_hi | W_lo] in split mode
   if (d->w_ld < kcols) {
-    h->err = "tiab_conv_gemm: weight pitch smaller than taps*segments*ceil64(cin)";
+    h->err = "tiab_conv_gemm: weight pitch smaller than taps*planes*ceil64(cin)";
     return TIAB_E_INVALID;
   }
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
@@ -908,11 +926,19 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
     return TIAB_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (nseg == 3) {
+    switch (BN) {
+      case 256: return launch_conv<256, 3>(h, ta, ta2, tb, p, s);
+      case 128: return launch_conv<128, 3>(h, ta, ta2, tb, p, s);
+      case 64: return launch_conv<64, 3>(h, ta, ta2, tb, p, s);
+      default: return launch_conv<32, 3>(h, ta, ta2, tb, p, s);
+    }
+  }
   switch (BN) {
-    case 256: return launch_conv<256>(h, ta, ta2, tb, p, s);
-    case 128: return launch_conv<128>(h, ta, ta2, tb, p, s);
-    case 64: return launch_conv<64>(h, ta, ta2, tb, p, s);
-    default: return launch_conv<32>(h, ta, ta2, tb, p, s);
+    case 256: return launch_conv<256, 1>(h, ta, ta2, tb, p, s);
+    case 128: return launch_conv<128, 1>(h, ta, ta2, tb, p, s);
+    case 64: return launch_conv<64, 1>(h, ta, ta2, tb, p, s);
+    default: return launch_conv<32, 1>(h, ta, ta2, tb, p, s);
   }
 }
 

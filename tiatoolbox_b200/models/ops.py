@@ -61,7 +61,7 @@ class ConvOp:
         d.w, d.w_ld = w.data_ptr(), w.shape[1]
         assert w.shape[0] == N and len(taps) <= _lib.MAX_TAPS
         nseg = 3 if x_lo_off else 1
-        assert w.shape[1] >= len(taps) * nseg * ((cin + 63) // 64) * 64, (w.shape, len(taps), nseg, cin)
+        assert w.shape[1] >= len(taps) * (2 if x_lo_off else 1) * ((cin + 63) // 64) * 64, (w.shape, len(taps), nseg, cin)
         d.M, d.N, d.taps = M, N, len(taps)
         for i, t in enumerate(taps):
             d.tap_off[i] = int(t)

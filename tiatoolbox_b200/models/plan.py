@@ -28,13 +28,13 @@ def ceil_to(x: int, m: int) -> int:
 
 
 def _split_pack(packed64: torch.Tensor, split: bool) -> torch.Tensor:
-    """[Cout, taps, Cpad] float64 -> fp16 [Cout, taps*Cpad] or, split, [Cout, taps*3*Cpad] = per tap [W_hi | W_hi | W_lo]."""
+    """[Cout, taps, Cpad] float64 -> fp16 [Cout, taps*Cpad] or, split, [Cout, taps*2*Cpad] = per tap [W_hi | W_lo]."""
     co, taps, cp = packed64.shape
     hi = packed64.to(torch.float16)
     if not split:
         return hi.reshape(co, taps * cp).contiguous()
     lo = (packed64 - hi.double()).to(torch.float16)
-    return torch.stack([hi, hi, lo], dim=2).reshape(co, taps * 3 * cp).contiguous()
+    return torch.stack([hi, lo], dim=2).reshape(co, taps * 2 * cp).contiguous()
 
 
 def pack_weight(w: torch.Tensor, out_scale: torch.Tensor | None = None, groups: int = 1, split: bool = False, device=None,
