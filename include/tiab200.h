@@ -137,6 +137,12 @@ typedef struct {
   const void* res16;    /* fp16 residual or NULL */
   int ldres, coffres, reslo;
   int relu;
+  /* A-operand transform (pre-activation BN + ReLU fused into this GEMM's operand path, hovernet.py:84-86, 170-172):
+   * a = relu?(x * pre_scale[c] + pre_shift[c]) with x fp32 (x_is_f32) or fp16 hi(+lo at x_lo_off); `split` selects the
+   * 3-term split-fp16 product in this mode (w then holds [W_hi | W_lo] per tap). */
+  const void* pre_scale; /* fp32 [cin] or NULL */
+  const void* pre_shift; /* fp32 [cin] or NULL */
+  int pre_relu, x_is_f32, split;
 } tiab_conv_desc_t;
 
 int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);

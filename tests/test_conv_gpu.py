@@ -158,3 +158,48 @@ def test_split_precision_gemm(ops, m, k, n):
     assert (out32 - ref).abs().max().item() < 2e-5 * scale
     recon = out16[:, :n].float() + out16[:, n:].float()
     assert (recon - ref).abs().max().item() < 2e-5 * scale
+
+
+@pytest.mark.parametrize("src_f32", [True, False])
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("m,k,n", [(1000, 288, 128), (4096 + 50, 64, 256), (300, 512, 32)])
+def test_transform_operand_mode(ops, src_f32, split, m, k, n):
+    """A = relu(x*scale + shift) built inside the GEMM (pre-activation BN+ReLU fused into the operand path)."""
+    import torch
+
+    from tiatoolbox_b200.models.plan import pack_weight
+
+    torch.manual_seed(4)
+    dev = torch.device("cuda")
+    xf = torch.randn(m, k, device=dev)
+    scale = torch.rand(k, device=dev) + 0.5
+    shift = torch.randn(k, device=dev) * 0.3
+    w = torch.randn(n, k, device=dev) / k**0.5
+    bias = torch.randn(n, device=dev) * 0.1
+    ld = k + 64  # pitch larger than cin: stale channels beyond cin must be ignored
+    if src_f32:
+        x = torch.full((m, ld), 7.0, device=dev)
+        x[:, :k] = xf
+        xin = xf
+        kw = dict(x=x, x_ld=ld, x_lo_off=0, x_is_f32=True)
+    else:
+        x = torch.full((m, 2 * ld), 7.0, dtype=torch.float16, device=dev)
+        x[:, :k] = xf.half()
+        x[:, ld:ld + k] = (xf - xf.half().float()).half()
+        xin = x[:, :k].float() + x[:, ld:ld + k].float()
+        kw = dict(x=x, x_ld=2 * ld, x_lo_off=ld)
+    wp = pack_weight(w.reshape(n, k, 1, 1), split=split, device=dev)
+    out32 = torch.zeros(m, n, device=dev)
+    op = ops.ConvOp(x_rows=m, cin=k, w=wp, taps=[0], M=m, N=n, grid=(1, m), window=(0, 1, 0, m), dst_geom=(1, m, 0, 0), out32=out32,
+                    ld32=n, bias=bias, pre_scale=scale, pre_shift=shift, pre_relu=True, split=split, **kw)
+    op()
+    torch.cuda.synchronize()
+    a = torch.relu(xin * scale + shift)
+    if split:
+        ref = (a.double() @ w.double().t()).float() + bias
+        tol = 3e-5
+    else:
+        ref = a.half().float() @ w.half().float().t() + bias
+        tol = 2e-3
+    err = (out32 - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, err

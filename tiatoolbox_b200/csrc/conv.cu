@@ -41,6 +41,7 @@ constexpr int BLOCK_K = 64;  // fp16: 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int CONV_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle ; warps 4-11: epilogue (2 per TMEM lane quadrant)
 constexpr int MAX_STAGES = 8;
+constexpr int CONV_THREADS_T = 512;  // transform mode: warps 4-7 epilogue, warps 8-15 = two groups of 4 operand-transform warps
 
 struct ConvParams {
   int M, N;
@@ -63,6 +64,15 @@ struct ConvParams {
   const __half* res16;
   int ldres, coffres;
   int relu;
+  // A-operand "transform" mode (AMODE == 1): A tiles are produced by 4 warps from a raw tensor instead of TMA:
+  //   a = relu?(x * pre_scale[c] + pre_shift[c]), x fp32 (residual stream) or fp16 hi(+lo); written as hi/lo swizzled tiles.
+  // This is the pre-activation BN+ReLU of hovernet.py:84-86 / :170-172 fused into the consumer GEMM.
+  const void* a_src;
+  long long a_rows;
+  int a_ld, a_lo, a_is_f32, a_cin;
+  const float* pre_scale;
+  const float* pre_shift;
+  int pre_relu;
   int nseg;               // 1: fp16 operands ; 3: split-fp16 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo ~ fp32 operands)
   int lo16, lo16b, reslo; // channel offsets of the residual ("lo") planes of out16 / out16b / res16 (0 = none)
   int num_m_tiles, num_n_tiles;
@@ -158,8 +168,8 @@ struct ConvSmem {
   static constexpr int TMEM_COLS = (2 * BLOCK_N) <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
-template <int BLOCK_N, int NSEG>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+template <int BLOCK_N, int NSEG, int AMODE>
+__global__ void __launch_bounds__(AMODE ? CONV_THREADS_T : CONV_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using S = ConvSmem<BLOCK_N, NSEG>;
@@ -184,12 +194,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
-      mbarrier_init(&full_bar[s], 1);
+      mbarrier_init(&full_bar[s], AMODE ? 5 : 1);  // TMA expect_tx arrive (+ one arrive per transform warp)
       mbarrier_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbarrier_init(&tfull_bar[b], 1);
-      mbarrier_init(&tempty_bar[b], 8);
+      mbarrier_init(&tempty_bar[b], AMODE ? 4 : 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -218,11 +228,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int wbase = t * S::NPLANES * p.kchunks;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbarrier_wait(&empty_bar[s], ph ^ 1u);
-            mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
+            mbarrier_expect_tx(&full_bar[s], AMODE ? S::NPLANES * S::B_BYTES : S::STAGE_BYTES);
             uint8_t* st = smem + s * S::STAGE_BYTES;
-            tma_load_2d(st, &tmA, kc * BLOCK_K, row, &full_bar[s]);
+            if (!AMODE) tma_load_2d(st, &tmA, kc * BLOCK_K, row, &full_bar[s]);
             if (NSEG == 3) {
-              tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, &full_bar[s]);
+              if (!AMODE) tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, &full_bar[s]);
               tma_load_2d(st + 2 * S::A_BYTES, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
               tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB, (wbase + p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
             } else {
@@ -284,10 +294,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (!AMODE || warp < 8)) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;    // the two warps of a quadrant take alternate 32-column chunks
+    const int half = AMODE ? 0 : (warp - 4) >> 2;  // (8-warp epilogue) the two warps of a quadrant take alternate 32-column chunks
     int ab = 0;
     uint32_t aph = 0;
     const int grid_px = p.Hin * p.Win;
@@ -310,7 +320,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += (AMODE ? 32 : 64)) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
@@ -415,6 +425,104 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++ab == 2) {
         ab = 0;
         aph ^= 1u;
+      }
+    }
+  }
+
+  if (AMODE && warp >= 8) {
+    // ===================== A-operand transform warps: raw tensor -> BN/ReLU -> hi/lo swizzled smem tiles =====================
+    const int tw = (threadIdx.x - 256) & 127;   // 0..127 inside the group
+    const int grp = (threadIdx.x - 256) >> 7;   // the two groups take alternate K-iterations so that two stages are in flight
+    int iter = 0;
+    const int rsub = tw >> 4;           // row within an 8-row pass (16 threads cover one 64-channel row chunk)
+    const int c4 = (tw & 15) * 4;       // channel offset inside the 64-channel chunk
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles;
+      const int m0 = m_blk * BLOCK_M;
+      for (int t = 0; t < p.taps; ++t) {
+        const long long row0 = (long long)m0 + p.tap_off[t];
+        for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
+          if ((iter & 1) != grp) {  // the other group's iteration: just keep the stage/phase bookkeeping in step
+            if (++s == S::STAGES) {
+              s = 0;
+              ph ^= 1u;
+            }
+            continue;
+          }
+          const int ch = kc * BLOCK_K + c4;
+          const bool chok = ch < p.a_cin;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.pre_scale && chok) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + ch));
+            sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + ch));
+          }
+          uint8_t* st = smem + s * S::STAGE_BYTES;
+          // phase 1: issue every global load of this stage (16 x 16 B per thread in flight), phase 2: transform + store
+          constexpr int NP = BLOCK_M / 8;
+          float4 xf[NP];
+#pragma unroll
+          for (int pass = 0; pass < NP; ++pass) {
+            const long long srow = row0 + pass * 8 + rsub;
+            xf[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chok && srow >= 0 && srow < p.a_rows) {
+              if (p.a_is_f32) {
+                xf[pass] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.a_src) + srow * p.a_ld + ch);
+              } else {
+                const __half* hp = reinterpret_cast<const __half*>(p.a_src) + srow * p.a_ld + ch;
+                const uint2 q = *reinterpret_cast<const uint2*>(hp);
+                uint2 ql = make_uint2(0u, 0u);
+                if (p.a_lo) ql = *reinterpret_cast<const uint2*>(hp + p.a_lo);
+                xf[pass] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(ql.x), __uint_as_float(ql.y));
+              }
+            }
+          }
+          mbarrier_wait(&empty_bar[s], ph ^ 1u);  // the global loads above are already in flight while we wait for the slot
+#pragma unroll
+          for (int pass = 0; pass < NP; ++pass) {
+            const int r = pass * 8 + rsub;
+            const long long srow = row0 + r;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            if (chok && srow >= 0 && srow < p.a_rows) {
+              if (p.a_is_f32) {
+                v0 = xf[pass].x, v1 = xf[pass].y, v2 = xf[pass].z, v3 = xf[pass].w;
+              } else {
+                const uint32_t q0 = __float_as_uint(xf[pass].x), q1 = __float_as_uint(xf[pass].y);
+                const uint32_t l0 = __float_as_uint(xf[pass].z), l1 = __float_as_uint(xf[pass].w);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q0));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&q1));
+                const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&l0));
+                const float2 g1 = __half22float2(*reinterpret_cast<const __half2*>(&l1));
+                v0 = f0.x + g0.x, v1 = f0.y + g0.y, v2 = f1.x + g1.x, v3 = f1.y + g1.y;
+              }
+              v0 = fmaf(v0, sc.x, sh.x), v1 = fmaf(v1, sc.y, sh.y), v2 = fmaf(v2, sc.z, sh.z), v3 = fmaf(v3, sc.w, sh.w);
+              if (p.pre_relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+            }
+            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+            // SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 128-byte row; 8-row groups are 1024 B apart
+            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c4 >> 3) ^ (r & 7))) << 4) + (c4 & 7) * 2);
+            uint2 w;
+            w.x = *reinterpret_cast<const uint32_t*>(&h01);
+            w.y = *reinterpret_cast<const uint32_t*>(&h23);
+            *reinterpret_cast<uint2*>(st + off) = w;
+            if (NSEG == 3) {
+              const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+              const __half2 l01 = __floats2half2_rn(v0 - b01.x, v1 - b01.y), l23 = __floats2half2_rn(v2 - b23.x, v3 - b23.y);
+              uint2 wl;
+              wl.x = *reinterpret_cast<const uint32_t*>(&l01);
+              wl.y = *reinterpret_cast<const uint32_t*>(&l23);
+              *reinterpret_cast<uint2*>(st + S::A_BYTES + off) = wl;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbarrier_arrive(&full_bar[s]);
+          if (++s == S::STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
       }
     }
   }
@@ -830,20 +938,20 @@ static int make_map_2d(tiab_ctx* h, CUtensorMap* map, const void* base, long lon
   return TIAB_OK;
 }
 
-template <int BN, int NSEG>
+template <int BN, int NSEG, int AMODE>
 static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, ConvParams& p,
                        cudaStream_t s) {
   using S = ConvSmem<BN, NSEG>;
   static bool attr_set = false;
   if (!attr_set) {
-    TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN, NSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN, NSEG, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_tiles = p.N / BN;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = std::min(tiles, h->sm_count);
-  conv_gemm_kernel<BN, NSEG><<<grid, CONV_THREADS, S::TOTAL, s>>>(ta, ta2, tb, p);
+  conv_gemm_kernel<BN, NSEG, AMODE><<<grid, AMODE ? CONV_THREADS_T : CONV_THREADS, S::TOTAL, s>>>(ta, ta2, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     h->err = std::string("conv_gemm launch: ") + cudaGetErrorString(e);
@@ -885,7 +993,8 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
     h->err = "tiab_conv_gemm: invalid grid";
     return TIAB_E_INVALID;
   }
-  const int nseg = d->x_lo_off ? 3 : 1;
+  const int amode = (d->pre_scale || d->x_is_f32) ? 1 : 0;
+  const int nseg = (amode ? d->split : (d->x_lo_off != 0)) ? 3 : 1;
   const int kchunks = (d->cin + BLOCK_K - 1) / BLOCK_K;
   const long long kcols = (long long)d->taps * (nseg == 3 ? 2 : 1) * kchunks * BLOCK_K;  // per tap: [W_hi | W_lo] in split mode
   if (d->w_ld < kcols) {
@@ -895,12 +1004,21 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   const int BN = (d->N % 256 == 0) ? 256 : (d->N % 128 == 0) ? 128 : (d->N % 64 == 0) ? 64 : 32;
   CUtensorMap ta, ta2, tb;
-  int rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+  int rc = make_map_2d(h, &tb, d->w, d->N, (int)kcols, d->w_ld, BN);
   if (rc) return rc;
-  rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, d->cin, d->x_ld, BLOCK_M);
-  if (rc) return rc;
-  rc = make_map_2d(h, &tb, d->w, d->N, (int)kcols, d->w_ld, BN);
-  if (rc) return rc;
+  if (amode) {
+    if ((d->cin & 3) || (d->x_ld & 3) || ((uintptr_t)d->x & 15) || (d->x_lo_off & 3)) {
+      h->err = "tiab_conv_gemm: transform mode needs 16-byte aligned rows and cin % 4 == 0";
+      return TIAB_E_INVALID;
+    }
+    ta = tb;   // unused in transform mode
+    ta2 = tb;
+  } else {
+    rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+    if (rc) return rc;
+    rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+    if (rc) return rc;
+  }
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.M = d->M;
@@ -908,6 +1026,8 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   p.taps = d->taps;
   p.kchunks = kchunks;
   p.nseg = nseg;
+  p.a_src = d->x, p.a_rows = d->x_rows, p.a_ld = (int)d->x_ld, p.a_lo = d->x_lo_off, p.a_is_f32 = d->x_is_f32, p.a_cin = d->cin;
+  p.pre_scale = (const float*)d->pre_scale, p.pre_shift = (const float*)d->pre_shift, p.pre_relu = d->pre_relu;
   for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t];
   p.Hin = d->Hin, p.Win = d->Win;
   p.y0 = d->y0, p.y1 = d->y1, p.x0 = d->x0, p.x1 = d->x1;
@@ -926,20 +1046,20 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
     return TIAB_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (nseg == 3) {
-    switch (BN) {
-      case 256: return launch_conv<256, 3>(h, ta, ta2, tb, p, s);
-      case 128: return launch_conv<128, 3>(h, ta, ta2, tb, p, s);
-      case 64: return launch_conv<64, 3>(h, ta, ta2, tb, p, s);
-      default: return launch_conv<32, 3>(h, ta, ta2, tb, p, s);
-    }
+#define TIAB_CONV_DISPATCH(NS, AM)                                          \
+  switch (BN) {                                                             \
+    case 256: return launch_conv<256, NS, AM>(h, ta, ta2, tb, p, s);        \
+    case 128: return launch_conv<128, NS, AM>(h, ta, ta2, tb, p, s);        \
+    case 64: return launch_conv<64, NS, AM>(h, ta, ta2, tb, p, s);          \
+    default: return launch_conv<32, NS, AM>(h, ta, ta2, tb, p, s);          \
   }
-  switch (BN) {
-    case 256: return launch_conv<256, 1>(h, ta, ta2, tb, p, s);
-    case 128: return launch_conv<128, 1>(h, ta, ta2, tb, p, s);
-    case 64: return launch_conv<64, 1>(h, ta, ta2, tb, p, s);
-    default: return launch_conv<32, 1>(h, ta, ta2, tb, p, s);
+  if (amode) {
+    if (nseg == 3) { TIAB_CONV_DISPATCH(3, 1) }
+    TIAB_CONV_DISPATCH(1, 1)
   }
+  if (nseg == 3) { TIAB_CONV_DISPATCH(3, 0) }
+  TIAB_CONV_DISPATCH(1, 0)
+#undef TIAB_CONV_DISPATCH
 }
 
 int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale, int src_lo, int N, int H, int W, int C,

@@ -57,7 +57,6 @@ class HoVerNetPlan(Plan):
         branches = (["tp"] if num_types is not None else []) + ["np", "hv"]
         # scratch shared by the branches (they run back to back on one stream)
         cb3 = self.act("cb3", (B, G3, G3), 512)
-        act3 = self.act("act3", (B * G3 * G3,), 512)
         t3 = self.act("t3", (B, G3, G3), 128)
         u3out = self.act("u3out", (B, G3, G3), 512)
         lo3 = h * 9                      # conva + 8 dense units
@@ -66,7 +65,6 @@ class HoVerNetPlan(Plan):
         assert G2 == H1 - crop1, (G2, H1, crop1)
         u2in = self.act("u2in", (B, G2, G2), 512)
         cb2 = self.act("cb2", (B, G2, G2), 256)
-        act2 = self.act("act2", (B * G2 * G2,), 256)
         t2 = self.act("t2d", (B, G2, G2), 128)
         u2out = self.act("u2out", (B, G2, G2), 256)
         lo2 = h * 5
@@ -85,19 +83,19 @@ class HoVerNetPlan(Plan):
             # u3
             self.conv(x=u3in, grid=(G3, G3), cin=1024, w=self.weight(sd[f"{p}.u3.conva.weight"]), k=k, centered=True, N=256,
                       window=(h, G3 - h, h, G3 - h), out16=cb3, coff16=0)
-            self._dense(sd, f"{p}.u3.dense", 8, cb3, act3, t3, G3, 256, k, h)
+            self._dense(sd, f"{p}.u3.dense", 8, cb3, t3, G3, 256, k, h)
             s, t = bn_scale_shift(sd, f"{p}.u3.dense.blk_bna.bn")
-            self.bn_relu(cb3, 512, self.const(s), self.const(t), B * G3 * G3, act3)
-            self.gemm(x=act3, rows=B * G3 * G3, cin=512, w=self.weight(sd[f"{p}.u3.convf.weight"]), N=512, out16=u3out)
+            self.gemm(x=cb3, rows=B * G3 * G3, cin=512, w=self.weight(sd[f"{p}.u3.convf.weight"]), N=512, out16=u3out,
+                      pre=(self.const(s), self.const(t), True))
             # u2
             self.add(lambda: ops.upsample_add(u3out, W3, W3, G3, G3, lo3, lo3, d1, H1, H1, crop1 // 2, crop1 // 2, B, 512, None, None,
                                               False, u2in, G2, G2, 0, 0))
             self.conv(x=u2in, grid=(G2, G2), cin=512, w=self.weight(sd[f"{p}.u2.conva.weight"]), k=k, centered=True, N=128,
                       window=(h, G2 - h, h, G2 - h), out16=cb2, coff16=0)
-            self._dense(sd, f"{p}.u2.dense", 4, cb2, act2, t2, G2, 128, k, h)
+            self._dense(sd, f"{p}.u2.dense", 4, cb2, t2, G2, 128, k, h)
             s, t = bn_scale_shift(sd, f"{p}.u2.dense.blk_bna.bn")
-            self.bn_relu(cb2, 256, self.const(s), self.const(t), B * G2 * G2, act2)
-            self.gemm(x=act2, rows=B * G2 * G2, cin=256, w=self.weight(sd[f"{p}.u2.convf.weight"]), N=256, out16=u2out)
+            self.gemm(x=cb2, rows=B * G2 * G2, cin=256, w=self.weight(sd[f"{p}.u2.convf.weight"]), N=256, out16=u2out,
+                      pre=(self.const(s), self.const(t), True))
             # u1
             self.add(lambda: ops.upsample_add(u2out, W2, W2, G2, G2, lo2, lo2, d0, H0, H0, crop0 // 2, crop0 // 2, B, 256, None, None,
                                               False, u1in, G1, G1, pu[0], pu[0]))
@@ -125,7 +123,6 @@ class HoVerNetPlan(Plan):
         B = self.B
         Ho = (H + stride - 1) // stride
         stream = self.buf(f"{name}.stream", (B, Ho, Ho, c3), torch.float32)
-        act = self.act(f"{name}.act", (B, Ho, Ho), c3) if units > 1 else None
         out = self.act(f"{name}.out", (B, Ho, Ho), c3)
         ppad = self.act(f"{name}.pad", (B, Ho + 2, Ho + 2), c1)   # TF-same pad of a stride-1 3x3: (1, 1)
         t2 = self.act(f"{name}.t2", (B, Ho, Ho), c2)
@@ -137,7 +134,7 @@ class HoVerNetPlan(Plan):
             g = self.act(f"{name}.sc_gather", (B * Ho * Ho,), cin)
             self.im2col(x_act.t, False, 1.0, x_act.lo, B, H, H, cin, x_act.ld, 1, stride, 0, Ho, g, cin)
             self.gemm(x=g, rows=B * Ho * Ho, cin=cin, w=wsc, N=c3, out32=stream, ld32=c3)
-        cur_in, cur_c = x_act, cin
+        cur_in, cur_c, cur_pre = x_act, cin, None
         for i in range(units):
             u = f"{name}.units.{i}"
             w1, b1 = self.fold_bn(sd, f"{u}.conv1", f"{u}.conv1/bn")
@@ -147,13 +144,13 @@ class HoVerNetPlan(Plan):
                 w2, b2 = self.fold_bn(sd, f"{u}.conv2", f"{u}.conv2/bn")
                 # conv1 (1x1 + BN + ReLU) straight into the interior of the zero-padded buffer
                 self.conv(x=cur_in, grid=(Hi, Hi), cin=cur_c, w=w1, k=1, centered=False, N=c1, window=(0, Hi, 0, Hi),
-                          dst_geom=(Hi + 2, Hi + 2, 1, 1), bias=b1, relu=True, out16=ppad)
+                          dst_geom=(Hi + 2, Hi + 2, 1, 1), bias=b1, relu=True, out16=ppad, pre=cur_pre)
                 self.conv(x=ppad, grid=(Hi + 2, Hi + 2), cin=c1, w=w2, k=3, centered=False, N=c2, window=(0, Hi, 0, Hi),
                           dst_geom=(Hi, Hi, 0, 0), bias=b2, relu=True, out16=t2)
             else:
                 w2, b2 = self.fold_bn(sd, f"{u}.conv2", f"{u}.conv2/bn", im2col=True)
                 t1 = self.act(f"{name}.t1_full", (B, H, H), c1)
-                self.gemm(x=cur_in, rows=B * H * H, cin=cur_c, w=w1, N=c1, bias=b1, relu=True, out16=t1)
+                self.gemm(x=cur_in, rows=B * H * H, cin=cur_c, w=w1, N=c1, bias=b1, relu=True, out16=t1, pre=cur_pre)
                 pb, _ = tf_same_pad(H, 3, s)
                 i2 = self.act(f"{name}.im2col", (B * Ho * Ho,), 9 * c1)
                 self.im2col(t1.t, False, 1.0, t1.lo, B, H, H, c1, t1.ld, 3, s, pb, Ho, i2, 9 * c1)
@@ -161,13 +158,16 @@ class HoVerNetPlan(Plan):
             last = i == units - 1
             bn_next = f"{name}.blk_bna.bn" if last else f"{name}.units.{i + 1}.preact/bn"
             sc, sh = bn_scale_shift(sd, bn_next)
-            self.gemm(x=t2, rows=B * Ho * Ho, cin=c2, w=self.weight(sd[f"{u}.conv3.weight"]), N=c3, res32=stream, ldres=c3,
-                      out32=None if last else stream, ld32=c3, out16b=out if last else act,
-                      scale2=self.const(sc), shift2=self.const(sh))
-            cur_in, cur_c = act, c3
+            if last:   # closing BN+ReLU of the block: the activated tensor is what the next block / the decoder skip consume
+                self.gemm(x=t2, rows=B * Ho * Ho, cin=c2, w=self.weight(sd[f"{u}.conv3.weight"]), N=c3, res32=stream, ldres=c3,
+                          out16b=out, scale2=self.const(sc), shift2=self.const(sh))
+            else:      # only the fp32 stream is written; the next unit's conv1 applies its pre-activation while loading it
+                self.gemm(x=t2, rows=B * Ho * Ho, cin=c2, w=self.weight(sd[f"{u}.conv3.weight"]), N=c3, res32=stream, ldres=c3,
+                          out32=stream, ld32=c3)
+            cur_in, cur_c, cur_pre = stream, c3, (self.const(sc), self.const(sh), True)
         return out, Ho
 
-    def _dense(self, sd, name, units, cb, act, t, G, c_in, k, h):
+    def _dense(self, sd, name, units, cb, t, G, c_in, k, h):
         """Dense block (hovernet.py:61-149) on one shared grid: unit u reads channels [0, c_in + 32u) of `cb`
         under its own BN+ReLU and appends 32 raw channels; valid windows shrink by k//2 per unit."""
         B = self.B
@@ -175,9 +175,9 @@ class HoVerNetPlan(Plan):
             un = f"{name}.units.{u}"
             c_u = c_in + 32 * u
             s, sft = bn_scale_shift(sd, f"{un}.preact_bna/bn")
-            self.bn_relu(cb, c_u, self.const(s), self.const(sft), B * G * G, act)
             w1, b1 = self.fold_bn(sd, f"{un}.conv1", f"{un}.conv1/bn")
-            self.gemm(x=act, rows=B * G * G, cin=c_u, w=w1, N=128, bias=b1, relu=True, out16=t)
+            # the unit's own BN+ReLU over the raw concat channels is applied while staging the GEMM operand
+            self.gemm(x=cb, rows=B * G * G, cin=c_u, w=w1, N=128, bias=b1, relu=True, out16=t, pre=(self.const(s), self.const(sft), True))
             lo = h * (u + 2)
             w2 = self.weight(sd[f"{un}.conv2.weight"], groups=4)
             self.conv(x=t, grid=(G, G), cin=128, w=w2, k=k, centered=True, N=32, window=(lo, G - lo, lo, G - lo),

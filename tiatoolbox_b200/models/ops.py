@@ -54,14 +54,19 @@ class ConvOp:
                  M: int, N: int, grid: tuple[int, int], window: tuple[int, int, int, int],
                  dst_geom: tuple[int, int, int, int], x_lo_off: int = 0, out16=None, ld16=0, coff16=0, lo16=0, out32=None,
                  ld32=0, coff32=0, out16b=None, ld16b=0, coff16b=0, lo16b=0, scale2=None, shift2=None, bias=None,
-                 res32=None, res16=None, ldres=0, coffres=0, reslo=0, res_geom=(1, 1, 0, 0), relu=False):
+                 res32=None, res16=None, ldres=0, coffres=0, reslo=0, res_geom=(1, 1, 0, 0), relu=False, pre_scale=None,
+                 pre_shift=None, pre_relu=False, x_is_f32=False, split=False):
         d = _lib.ConvDesc()
         d.x, d.x_rows, d.x_ld, d.cin, d.x_lo_off = x.data_ptr(), x_rows, x_ld, cin, x_lo_off
         assert w.dtype == torch.float16 and w.dim() == 2 and w.is_contiguous()
         d.w, d.w_ld = w.data_ptr(), w.shape[1]
         assert w.shape[0] == N and len(taps) <= _lib.MAX_TAPS
-        nseg = 3 if x_lo_off else 1
-        assert w.shape[1] >= len(taps) * (2 if x_lo_off else 1) * ((cin + 63) // 64) * 64, (w.shape, len(taps), nseg, cin)
+        transform = pre_scale is not None or x_is_f32
+        nseg = 3 if (split if transform else x_lo_off) else 1
+        assert w.shape[1] >= len(taps) * (2 if nseg == 3 else 1) * ((cin + 63) // 64) * 64, (w.shape, len(taps), nseg, cin)
+        if transform:
+            assert (pre_scale is None) == (pre_shift is None)
+            assert x.dtype == (torch.float32 if x_is_f32 else torch.float16)
         d.M, d.N, d.taps = M, N, len(taps)
         for i, t in enumerate(taps):
             d.tap_off[i] = int(t)
@@ -75,9 +80,11 @@ class ConvOp:
         d.scale2, d.shift2, d.bias = _ptr(scale2), _ptr(shift2), _ptr(bias)
         d.res32, d.res16, d.ldres, d.coffres, d.reslo = _ptr(res32), _ptr(res16), ldres, coffres, reslo
         d.relu = int(bool(relu))
+        d.pre_scale, d.pre_shift, d.pre_relu = _ptr(pre_scale), _ptr(pre_shift), int(bool(pre_relu))
+        d.x_is_f32, d.split = int(bool(x_is_f32)), int(bool(split))
         self.desc = d
         self.dev = x.device
-        self._keep = (x, w, out16, out32, out16b, scale2, shift2, bias, res32, res16)
+        self._keep = (x, w, out16, out32, out16b, scale2, shift2, bias, res32, res16, pre_scale, pre_shift)
         self.flops = 2.0 * M * N * len(taps) * cin
         self.mma_flops = self.flops * nseg
 

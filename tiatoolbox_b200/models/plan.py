@@ -128,7 +128,21 @@ class Plan:
                 kw[lo] = a.lo
         return kw
 
-    def conv(self, *, x: Act, grid, cin: int, w: torch.Tensor, k: int, centered: bool, N: int, window, dst_geom=None, **kw) -> ops.ConvOp:
+    def _x_kw(self, x, pre) -> dict:
+        """Operand-A description: an Act read by TMA, or (with `pre` = (scale, shift, relu) and/or an fp32 tensor) the
+        transform path that applies the pre-activation BN+ReLU while staging the operand."""
+        if isinstance(x, Act):
+            kw = {"x": x.t, "x_ld": x.ld, "x_lo_off": x.lo}
+        else:  # raw fp32 [.., C] tensor (residual stream)
+            assert x.dtype == torch.float32
+            kw = {"x": x, "x_ld": x.shape[-1], "x_lo_off": 0, "x_is_f32": True}
+        if pre is not None or not isinstance(x, Act):
+            kw["split"] = self.split
+            if pre is not None:
+                kw["pre_scale"], kw["pre_shift"], kw["pre_relu"] = pre
+        return kw
+
+    def conv(self, *, x, grid, cin: int, w: torch.Tensor, k: int, centered: bool, N: int, window, dst_geom=None, pre=None, **kw) -> ops.ConvOp:
         """Shifted-GEMM conv over the (H, W) grid of the NHWC activation `x` (batch = self.B)."""
         H, W = grid
         M = self.B * H * W
@@ -136,18 +150,18 @@ class Plan:
             taps = [(kh - k // 2) * W + (kw_ - k // 2) for kh in range(k) for kw_ in range(k)]
         else:
             taps = [kh * W + kw_ for kh in range(k) for kw_ in range(k)]
-        op = ops.ConvOp(x=x.t, x_rows=M, x_ld=x.ld, x_lo_off=x.lo, cin=cin, w=w, taps=taps, M=M, N=N, grid=(H, W), window=window,
-                        dst_geom=dst_geom or (H, W, 0, 0), **self._out_kw(kw))
+        op = ops.ConvOp(x_rows=M, cin=cin, w=w, taps=taps, M=M, N=N, grid=(H, W), window=window,
+                        dst_geom=dst_geom or (H, W, 0, 0), **self._x_kw(x, pre), **self._out_kw(kw))
         y0, y1, x0, x1 = window
         self.flops += 2.0 * self.B * (y1 - y0) * (x1 - x0) * N * (k * k) * cin
         self.mma_flops += op.mma_flops
         self.ops.append(op)
         return op
 
-    def gemm(self, *, x: Act, rows: int, cin: int, w: torch.Tensor, N: int, **kw) -> ops.ConvOp:
+    def gemm(self, *, x, rows: int, cin: int, w: torch.Tensor, N: int, pre=None, **kw) -> ops.ConvOp:
         """Plain [rows, cin] x [N, cin]^T GEMM (1x1 conv on a dense matrix / im2col output)."""
-        op = ops.ConvOp(x=x.t, x_rows=rows, x_ld=x.ld, x_lo_off=x.lo, cin=cin, w=w, taps=[0], M=rows, N=N, grid=(1, rows),
-                        window=(0, 1, 0, rows), dst_geom=kw.pop("dst_geom", (1, rows, 0, 0)), **self._out_kw(kw))
+        op = ops.ConvOp(x_rows=rows, cin=cin, w=w, taps=[0], M=rows, N=N, grid=(1, rows),
+                        window=(0, 1, 0, rows), dst_geom=kw.pop("dst_geom", (1, rows, 0, 0)), **self._x_kw(x, pre), **self._out_kw(kw))
         self.flops += 2.0 * rows * N * cin
         self.mma_flops += op.mma_flops
         self.ops.append(op)
