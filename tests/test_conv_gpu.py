@@ -162,7 +162,7 @@ def test_split_precision_gemm(ops, m, k, n):
 
 @pytest.mark.parametrize("src_f32", [True, False])
 @pytest.mark.parametrize("split", [True, False])
-@pytest.mark.parametrize("m,k,n", [(1000, 288, 128), (4096 + 50, 64, 256), (300, 512, 32)])
+@pytest.mark.parametrize("m,k,n", [(1000, 288, 128), (4096 + 50, 64, 256), (300, 512, 32), (148 * 128 * 3 + 17, 256, 64), (40000, 1024, 256)])
 def test_transform_operand_mode(ops, src_f32, split, m, k, n):
     """A = relu(x*scale + shift) built inside the GEMM (pre-activation BN+ReLU fused into the operand path)."""
     import torch
@@ -203,3 +203,43 @@ def test_transform_operand_mode(ops, src_f32, split, m, k, n):
         tol = 2e-3
     err = (out32 - ref).abs().max().item() / ref.abs().max().item()
     assert err < tol, err
+
+
+@pytest.mark.parametrize("transform", [False, True])
+@pytest.mark.parametrize("k", [1, 3])
+def test_window_tile_skipping(ops, k, transform):
+    """A y-window that excludes whole 128-row tiles (and image-straddling tiles): outputs inside the window match the
+    reference, everything outside is left untouched."""
+    import torch
+    import torch.nn.functional as F
+
+    if transform and k != 1:
+        pytest.skip("operand-transform mode is used for 1x1 convolutions only")
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    nimg, H, W, cin, cout = 5, 40, 24, 64, 64
+    y0, y1, x0, x1 = 13, 29, 2, 21
+    w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+    wp = _pack_w(w, cin)
+    out32 = torch.full((nimg, H, W, cout), -7.0, device=dev)
+    taps = [(kh - k // 2) * W + (kw - k // 2) for kh in range(k) for kw in range(k)]
+    if transform:
+        xs = torch.randn(nimg, H, W, cin, device=dev)
+        scale, shift = torch.rand(cin, device=dev) + 0.5, torch.randn(cin, device=dev)
+        a = torch.relu(xs * scale + shift).half().float()
+        op = ops.ConvOp(x=xs, x_rows=nimg * H * W, x_ld=cin, cin=cin, w=wp, taps=taps, M=nimg * H * W, N=cout, grid=(H, W),
+                        window=(y0, y1, x0, x1), dst_geom=(H, W, 0, 0), out32=out32, ld32=cout, pre_scale=scale, pre_shift=shift,
+                        pre_relu=True, x_is_f32=True, split=False)
+    else:
+        xh = torch.randn(nimg, H, W, cin, device=dev).half()
+        a = xh.float()
+        op = ops.ConvOp(x=xh, x_rows=nimg * H * W, x_ld=cin, cin=cin, w=wp, taps=taps, M=nimg * H * W, N=cout, grid=(H, W),
+                        window=(y0, y1, x0, x1), dst_geom=(H, W, 0, 0), out32=out32, ld32=cout)
+    op()
+    torch.cuda.synchronize()
+    ref = F.conv2d(a.permute(0, 3, 1, 2), w.half().float(), padding=k // 2).permute(0, 2, 3, 1)
+    inside = torch.zeros(nimg, H, W, dtype=torch.bool, device=dev)
+    inside[:, y0:y1, x0:x1] = True
+    assert (out32[~inside] == -7.0).all()
+    err = (out32[inside] - ref[inside]).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err

@@ -76,6 +76,8 @@ struct ConvParams {
   int nseg;               // 1: fp16 operands ; 3: split-fp16 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo ~ fp32 operands)
   int lo16, lo16b, reslo; // channel offsets of the residual ("lo") planes of out16 / out16b / res16 (0 = none)
   int num_m_tiles, num_n_tiles;
+  int epi_mode;           // specialised epilogue row loop (0 = generic), see tiab_conv_gemm
+  int skip;               // 1: the window does not span all grid rows -> tiles with no valid output row are skipped
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -153,18 +155,152 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
+// explicit shared-state-space accesses (32-bit addresses, immediate offsets; generic LD/ST cost extra address checks)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+// Phase 2 of the operand transform for one stage: 16 row passes of this thread's 4 channels, relu?(x*sc + sh) -> fp16 hi
+// (+ lo) at the SWIZZLE_128B position.  CHECK adds the per-row range test (tiles at the ends of the tensor only); the two
+// source formats and the checked variant are separate instantiations so that the hot path stays short (the three warp
+// roles of this kernel share a 32 KB instruction cache).
+template <int NSEG, bool F32, bool CHECK>
+__device__ __forceinline__ void transform_store(const float4 (&xf)[BLOCK_M / 8], uint32_t dst, uint32_t lo_off, float4 sc, float4 sh,
+                                                bool relu, int rsub, int r_lo, int r_hi) {
+#pragma unroll
+  for (int pass = 0; pass < BLOCK_M / 8; ++pass) {
+    float v0, v1, v2, v3;
+    if (F32) {
+      v0 = xf[pass].x, v1 = xf[pass].y, v2 = xf[pass].z, v3 = xf[pass].w;
+    } else {
+      const float2 f0 = unpack_h2(__float_as_uint(xf[pass].x)), f1 = unpack_h2(__float_as_uint(xf[pass].y));
+      const float2 g0 = unpack_h2(__float_as_uint(xf[pass].z)), g1 = unpack_h2(__float_as_uint(xf[pass].w));
+      v0 = f0.x + g0.x, v1 = f0.y + g0.y, v2 = f1.x + g1.x, v3 = f1.y + g1.y;
+    }
+    v0 = fmaf(v0, sc.x, sh.x), v1 = fmaf(v1, sc.y, sh.y), v2 = fmaf(v2, sc.z, sh.z), v3 = fmaf(v3, sc.w, sh.w);
+    if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+    if (CHECK) {
+      const int r = pass * 8 + rsub;
+      if (r < r_lo || r >= r_hi) v0 = v1 = v2 = v3 = 0.f;
+    }
+    const uint32_t h01 = pack_h2(v0, v1), h23 = pack_h2(v2, v3);
+    sts_u2(dst + pass * 1024, h01, h23);   // row r = pass*8 + rsub: 8-row groups are 1024 B apart
+    if (NSEG == 3) {
+      const float2 b01 = unpack_h2(h01), b23 = unpack_h2(h23);
+      sts_u2(dst + lo_off + pass * 1024, pack_h2(v0 - b01.x, v1 - b01.y), pack_h2(v2 - b23.x, v3 - b23.y));
+    }
+  }
+}
+
+// Coalesced half of the epilogue for one 32-column chunk: lane (rsub, cq) handles rows i*4 + rsub (i = 0..7), columns
+// 4*cq..4*cq+3 of the transposed staging tile.  RES: 0 none / 1 fp32 residual (prefetched in rres, or loaded in place when
+// !PRE) / 2 fp16 hi(+lo) residual / -1 decide at run time; O32 / O16 / O16B select the outputs (GENERIC: all run-time flags).
+// The common combinations are separate instantiations so that the executed path has no per-row feature branches.
+template <bool GENERIC, int RES, bool O32, bool O16, bool O16B, bool LO, bool PRE>
+__device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t stg_s, int rsub, int cq, uint32_t vmask, const int (&drow)[8],
+                                              const int (&rrow)[8], const float4 (&rres)[8], int n, float4 bias4, float4 sc2,
+                                              float4 sh2, float floor_) {
+  const bool res32 = GENERIC ? p.res32 != nullptr : RES == 1;
+  const bool res16 = GENERIC ? (p.res32 == nullptr && p.res16 != nullptr) : RES == 2;
+  const bool o32 = GENERIC ? p.out32 != nullptr : O32;
+  const bool o16 = GENERIC ? p.out16 != nullptr : O16;
+  const bool o16b = GENERIC ? p.out16b != nullptr : O16B;
+  const bool lo_a = GENERIC ? p.lo16 != 0 : LO, lo_b = GENERIC ? p.lo16b != 0 : LO;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (!(vmask >> i & 1u)) continue;
+    const int rl7 = (i & 1) * 4 + rsub;   // (i*4 + rsub) & 7
+    float4 x = lds_f4(stg_s + i * 512 + rsub * 128 + ((cq ^ rl7) << 4));
+    x.x += bias4.x, x.y += bias4.y, x.z += bias4.z, x.w += bias4.w;
+    if (res32) {
+      const float4 rr = PRE ? rres[i] : *reinterpret_cast<const float4*>(p.res32 + (long long)rrow[i] * p.ldres + p.coffres + n);
+      x.x += rr.x, x.y += rr.y, x.z += rr.z, x.w += rr.w;
+    } else if (res16) {
+      const __half* rp = p.res16 + (long long)rrow[i] * p.ldres + p.coffres + n;
+      const uint2 q = *reinterpret_cast<const uint2*>(rp);
+      const float2 f0 = unpack_h2(q.x), f1 = unpack_h2(q.y);
+      x.x += f0.x, x.y += f0.y, x.z += f1.x, x.w += f1.y;
+      if (p.reslo) {
+        const uint2 ql = *reinterpret_cast<const uint2*>(rp + p.reslo);
+        const float2 g0 = unpack_h2(ql.x), g1 = unpack_h2(ql.y);
+        x.x += g0.x, x.y += g0.y, x.z += g1.x, x.w += g1.y;
+      }
+    }
+    x.x = fmaxf(x.x, floor_), x.y = fmaxf(x.y, floor_), x.z = fmaxf(x.z, floor_), x.w = fmaxf(x.w, floor_);   // ReLU or no-op (-inf)
+    if (o32) *reinterpret_cast<float4*>(p.out32 + (long long)drow[i] * p.ld32 + p.coff32 + n) = x;
+    if (o16) {
+      __half* op = p.out16 + (long long)drow[i] * p.ld16 + p.coff16 + n;
+      const uint32_t h01 = pack_h2(x.x, x.y), h23 = pack_h2(x.z, x.w);
+      *reinterpret_cast<uint2*>(op) = make_uint2(h01, h23);
+      if (lo_a) {
+        const float2 b01 = unpack_h2(h01), b23 = unpack_h2(h23);
+        *reinterpret_cast<uint2*>(op + p.lo16) = make_uint2(pack_h2(x.x - b01.x, x.y - b01.y), pack_h2(x.z - b23.x, x.w - b23.y));
+      }
+    }
+    if (o16b) {
+      __half* op = p.out16b + (long long)drow[i] * p.ld16b + p.coff16b + n;
+      const float a0 = fmaxf(fmaf(x.x, sc2.x, sh2.x), 0.f), a1 = fmaxf(fmaf(x.y, sc2.y, sh2.y), 0.f);
+      const float a2 = fmaxf(fmaf(x.z, sc2.z, sh2.z), 0.f), a3 = fmaxf(fmaf(x.w, sc2.w, sh2.w), 0.f);
+      const uint32_t h01 = pack_h2(a0, a1), h23 = pack_h2(a2, a3);
+      *reinterpret_cast<uint2*>(op) = make_uint2(h01, h23);
+      if (lo_b) {
+        const float2 b01 = unpack_h2(h01), b23 = unpack_h2(h23);
+        *reinterpret_cast<uint2*>(op + p.lo16b) = make_uint2(pack_h2(a0 - b01.x, a1 - b01.y), pack_h2(a2 - b23.x, a3 - b23.y));
+      }
+    }
+  }
+}
+
+// True when at least one of the tile's 128 grid rows lies inside the valid y-window (every warp role evaluates this for
+// the same tile sequence, so skipped tiles never touch a barrier).
+__device__ __forceinline__ bool tile_active(const ConvParams& p, int m_blk) {
+  if (!p.skip) return true;
+  const int gp = p.Hin * p.Win;
+  const int r0 = m_blk * BLOCK_M;
+  const int r1 = min(r0 + BLOCK_M, p.M) - 1;
+  const int i0 = r0 / gp, i1 = r1 / gp;
+  const int ya = (r0 - i0 * gp) / p.Win, yb = (r1 - i1 * gp) / p.Win;
+  if (i0 == i1) return !(yb < p.y0 || ya >= p.y1);
+  if (i1 == i0 + 1) return !(ya >= p.y1 && yb < p.y0);
+  return true;
+}
+
 // One pipeline stage holds everything ONE K-chunk of one tap needs:
 //   NSEG == 1 : [A 16 KB][B]                      -> 4 UMMAs  (A*W)
 //   NSEG == 3 : [A_hi 16 KB][A_lo 16 KB][W_hi][W_lo] -> 12 UMMAs (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo), every operand loaded once
-template <int BLOCK_N, int NSEG>
+//   AMODE == 1: the A area is always 32 KB: TMA drops the RAW tile there (fp32 [128 x 64] or fp16 hi + lo planes), the
+//               transform warps pull it into registers and overwrite it in place with the swizzled fp16 hi (+ lo) tiles.
+template <int BLOCK_N, int NSEG, int AMODE>
 struct ConvSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int NPLANES = NSEG == 3 ? 2 : 1;
-  static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (200 * 1024 / STAGE_BYTES);
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr, + slack for 1024 B alignment
+  static constexpr int A_AREA = (NSEG == 3 || AMODE) ? 2 * A_BYTES : A_BYTES;
+  static constexpr int STAGE_BYTES = A_AREA + NPLANES * B_BYTES;
+  static constexpr int STG_BYTES = (AMODE ? 4 : 8) * 4096;   // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 384 - STG_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (BUDGET / STAGE_BYTES);
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 384 + 1024;  // barriers + tmem ptr, + slack for 1024 B alignment
   static constexpr int TMEM_COLS = (2 * BLOCK_N) <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
 };
 
@@ -172,7 +308,7 @@ template <int BLOCK_N, int NSEG, int AMODE>
 __global__ void __launch_bounds__(AMODE ? CONV_THREADS_T : CONV_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-  using S = ConvSmem<BLOCK_N, NSEG>;
+  using S = ConvSmem<BLOCK_N, NSEG, AMODE>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -180,7 +316,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // (AMODE) "raw A tile landed", one set per transform group: the groups take alternate K-iterations, so with an odd
+  // stage count a stage alternates between them -- on a shared barrier a group one ring ahead of the other would see the
+  // previous phase's parity and run on a tile that has not arrived.  Per-group barriers are only ever waited on in order.
+  uint64_t* raw_bar = tempty_bar + 2;             // [2][MAX_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(raw_bar + 2 * MAX_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,6 +336,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < S::STAGES; ++s) {
       mbarrier_init(&full_bar[s], AMODE ? 5 : 1);  // TMA expect_tx arrive (+ one arrive per transform warp)
       mbarrier_init(&empty_bar[s], 1);
+      mbarrier_init(&raw_bar[s], 1);
+      mbarrier_init(&raw_bar[MAX_STAGES + s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbarrier_init(&tfull_bar[b], 1);
@@ -216,28 +358,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+    int s = 0;
+    uint32_t ph = 0;
+    int iter = 0;   // K-iterations issued so far (parity = transform group that will take the stage)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
+      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      if (!tile_active(p, m_blk)) continue;
+      if (lane == 0) {
         for (int t = 0; t < p.taps; ++t) {
           const int row = m0 + p.tap_off[t];
           // weights of tap t: NSEG == 3 -> [W_hi | W_lo], each kchunks*64 columns
           const int wbase = t * S::NPLANES * p.kchunks;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
             mbarrier_wait(&empty_bar[s], ph ^ 1u);
-            mbarrier_expect_tx(&full_bar[s], AMODE ? S::NPLANES * S::B_BYTES : S::STAGE_BYTES);
             uint8_t* st = smem + s * S::STAGE_BYTES;
-            if (!AMODE) tma_load_2d(st, &tmA, kc * BLOCK_K, row, &full_bar[s]);
-            if (NSEG == 3) {
-              if (!AMODE) tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, &full_bar[s]);
-              tma_load_2d(st + 2 * S::A_BYTES, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
-              tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmB, (wbase + p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
+            if (AMODE) {
+              uint64_t* rb = &raw_bar[(iter & 1) * MAX_STAGES + s];
+              // raw tile -> A area (rows / channels outside the tensor are zero filled), signalled on its own barrier
+              const bool two = !p.a_is_f32 && p.a_lo;
+              mbarrier_expect_tx(rb, (p.a_is_f32 || two) ? 2 * S::A_BYTES : S::A_BYTES);
+              tma_load_2d(st, &tmA, kc * BLOCK_K, row, rb);
+              if (two) tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, rb);
+              mbarrier_expect_tx(&full_bar[s], S::NPLANES * S::B_BYTES);
             } else {
-              tma_load_2d(st + S::A_BYTES, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
+              mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
+              tma_load_2d(st, &tmA, kc * BLOCK_K, row, &full_bar[s]);
+              if (NSEG == 3) tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, &full_bar[s]);
             }
+            tma_load_2d(st + S::A_AREA, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
+            if (NSEG == 3) tma_load_2d(st + S::A_AREA + S::B_BYTES, &tmB, (wbase + p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
             if (++s == S::STAGES) {
               s = 0;
               ph ^= 1u;
@@ -245,6 +395,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -256,6 +407,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int ab = 0;
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (!tile_active(p, tile / p.num_n_tiles)) continue;
         mbarrier_wait(&tempty_bar[ab], aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BLOCK_N);
@@ -265,7 +417,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t base = cvta_smem(smem + s * S::STAGE_BYTES);
           if (NSEG == 3) {
             const uint64_t ahi = make_smem_desc(base), alo = make_smem_desc(base + S::A_BYTES);
-            const uint64_t bhi = make_smem_desc(base + 2 * S::A_BYTES), blo = make_smem_desc(base + 2 * S::A_BYTES + S::B_BYTES);
+            const uint64_t bhi = make_smem_desc(base + S::A_AREA), blo = make_smem_desc(base + S::A_AREA + S::B_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)  // +2 in (addr >> 4) units = 32 bytes = 16 fp16 along K
               tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
@@ -276,7 +428,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
               tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), blo + (uint64_t)(kk * 2), idesc, 1u);
           } else {
-            const uint64_t adesc = make_smem_desc(base), bdesc = make_smem_desc(base + S::A_BYTES);
+            const uint64_t adesc = make_smem_desc(base), bdesc = make_smem_desc(base + S::A_AREA);
 #pragma unroll
             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
               tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
@@ -295,133 +447,106 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4 && (!AMODE || warp < 8)) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
+    // tcgen05.ld hands every lane one tile ROW; written like that, each global access of a warp touches 32 different
+    // cache lines and the L1 tag stage (one line per cycle) becomes the bound of the memory-bound 1x1 convolutions.  Each warp
+    // therefore transposes its 32x32 fp32 chunk through a private 4 KB swizzled staging tile so that 8 lanes cover 128
+    // contiguous bytes of one output row (4 lines per request instead of 32).
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = AMODE ? 0 : (warp - 4) >> 2;  // (8-warp epilogue) the two warps of a quadrant take alternate 32-column chunks
+    const uint32_t stg_s = cvta_smem(smem + S::STG_OFFSET + (warp - 4) * 4096);
+    const float floor_ = p.relu ? 0.f : -__int_as_float(0x7f800000);   // max(x, -inf) == x
+    const int rsub = lane >> 3;          // coalesced phase: row i*4 + rsub of the chunk, ...
+    const int cq = lane & 7;             // ... 16-byte column group cq (columns 4*cq .. 4*cq+3)
     int ab = 0;
     uint32_t aph = 0;
     const int grid_px = p.Hin * p.Win;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
+      if (!tile_active(p, m_blk)) continue;
       const int n0 = n_blk * BLOCK_N;
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
-      bool valid = row < p.M;
-      long long drow = 0, rrow = 0;
+      // geometry of the row this lane owns in TMEM, then redistributed to the lanes that will store it
+      int drow_l = 0, rrow_l = 0, valid_l = 0;
       {
+        const int row = m_blk * BLOCK_M + quad * 32 + lane;
         const int img = row / grid_px;
         const int rem = row - img * grid_px;
         const int y = rem / p.Win;
         const int x = rem - y * p.Win;
-        valid = valid && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
-        drow = ((long long)img * p.Hd + (y + p.dy)) * p.Wd + (x + p.dx);
-        rrow = ((long long)img * p.Hr + (y + p.ry)) * p.Wr + (x + p.rx);
+        valid_l = row < p.M && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
+        drow_l = (img * p.Hd + (y + p.dy)) * p.Wd + (x + p.dx);
+        rrow_l = (img * p.Hr + (y + p.ry)) * p.Wr + (x + p.rx);
+      }
+      int drow[8], rrow[8];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int src = i * 4 + rsub;
+        drow[i] = __shfl_sync(0xffffffffu, drow_l, src);
+        rrow[i] = __shfl_sync(0xffffffffu, rrow_l, src);
+        if (__shfl_sync(0xffffffffu, valid_l, src)) vmask |= 1u << i;
+      }
+      // fp32 residual: keep the NEXT chunk's loads in flight while the current one is combined and stored, and issue the
+      // first chunk before waiting for the MMAs
+      constexpr int CSTEP = AMODE ? 32 : 64;
+      const float* rbase = p.res32 ? p.res32 + p.coffres + n0 + 4 * cq : nullptr;
+      float4 rcur[8], rnext[8];
+      if (!AMODE && rbase) {   // (the 512-thread transform variant has no registers to spare: it loads in place)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (vmask >> i & 1u) rcur[i] = *reinterpret_cast<const float4*>(rbase + (long long)rrow[i] * p.ldres + half * 32);
       }
       mbarrier_wait(&tfull_bar[ab], aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BLOCK_N);
+      bool released = false;
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < BLOCK_N; c0 += (AMODE ? 32 : 64)) {
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += CSTEP) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
-          const int n = n0 + c0;
+        if (!AMODE && rbase && c0 + CSTEP < BLOCK_N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-            }
-          }
-          if (p.res32) {
-            const float* rp = p.res32 + rrow * p.ldres + p.coffres + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = *reinterpret_cast<const float4*>(rp + j);
-              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-            }
-          } else if (p.res16) {
-            const __half* rp = p.res16 + rrow * p.ldres + p.coffres + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(h2[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
-              }
-              if (p.reslo) {
-                uint4 ql = *reinterpret_cast<const uint4*>(rp + p.reslo + j);
-                const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 f = __half22float2(l2[e]);
-                  v[j + 2 * e] += f.x;
-                  v[j + 2 * e + 1] += f.y;
-                }
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.out32) {
-            float* op = p.out32 + drow * p.ld32 + p.coff32 + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (p.out16) {
-            __half* op = p.out16 + drow * p.ld16 + p.coff16 + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              __half2* h2 = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(op + j) = q;
-              if (p.lo16) {
-                uint4 ql;
-                __half2* l2 = reinterpret_cast<__half2*>(&ql);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 hf = __half22float2(h2[e]);
-                  l2[e] = __floats2half2_rn(v[j + 2 * e] - hf.x, v[j + 2 * e + 1] - hf.y);
-                }
-                *reinterpret_cast<uint4*>(op + p.lo16 + j) = ql;
-              }
-            }
-          }
-          if (p.out16b) {
-            __half* op = p.out16b + drow * p.ld16b + p.coff16b + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q, ql;
-              __half2* h2 = reinterpret_cast<__half2*>(&q);
-              __half2* l2 = reinterpret_cast<__half2*>(&ql);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = n + j + 2 * e;
-                float a0 = fmaxf(fmaf(v[j + 2 * e], __ldg(p.scale2 + c), __ldg(p.shift2 + c)), 0.f);
-                float a1 = fmaxf(fmaf(v[j + 2 * e + 1], __ldg(p.scale2 + c + 1), __ldg(p.shift2 + c + 1)), 0.f);
-                h2[e] = __floats2half2_rn(a0, a1);
-                float2 hf = __half22float2(h2[e]);
-                l2[e] = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-              }
-              *reinterpret_cast<uint4*>(op + j) = q;
-              if (p.lo16b) *reinterpret_cast<uint4*>(op + p.lo16b + j) = ql;
-            }
-          }
+          for (int i = 0; i < 8; ++i)
+            if (vmask >> i & 1u) rnext[i] = *reinterpret_cast<const float4*>(rbase + (long long)rrow[i] * p.ldres + c0 + CSTEP);
         }
+        tmem_ld_wait();
+        if (c0 + CSTEP >= BLOCK_N) {   // last chunk of this warp is in registers: hand the accumulator back to the MMA warp now
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbarrier_arrive(&tempty_bar[ab]);
+          released = true;
+        }
+        // transpose through the staging tile: 16-byte group g of row `lane` lives at lane*128 + ((g ^ (lane & 7)) << 4)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) sts_u4(stg_s + lane * 128 + ((g ^ (lane & 7)) << 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+        __syncwarp();
+        const int n = n0 + c0 + 4 * cq;   // first of this lane's 4 output channels
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc2 = bias4, sh2 = bias4;
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        if (p.out16b) {
+          sc2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + n));
+          sh2 = __ldg(reinterpret_cast<const float4*>(p.shift2 + n));
+        }
+        constexpr bool PRE = !AMODE;
+        switch (p.epi_mode) {
+          case 1: epilogue_rows<false, 0, false, true, false, true, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+          case 2: epilogue_rows<false, 0, false, true, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+          case 3: epilogue_rows<false, 0, true, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+          case 4: epilogue_rows<false, 1, true, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+          case 5: epilogue_rows<false, 1, false, false, true, true, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+          default: epilogue_rows<true, -1, false, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+        }
+        if (!AMODE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+        }
+        __syncwarp();   // the staging tile is rewritten by the next chunk
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbarrier_arrive(&tempty_bar[ab]);
+      if (!released) {   // (warps without a chunk: BLOCK_N == 32, second half)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbarrier_arrive(&tempty_bar[ab]);
+      }
       if (++ab == 2) {
         ab = 0;
         aph ^= 1u;
@@ -436,10 +561,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int iter = 0;
     const int rsub = tw >> 4;           // row within an 8-row pass (16 threads cover one 64-channel row chunk)
     const int c4 = (tw & 15) * 4;       // channel offset inside the 64-channel chunk
+    const uint32_t smem_s = cvta_smem(smem);
+    uint32_t rawph = 0;                 // bit s: parity of this group's next wait on its raw barrier of stage s
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_tiles;
+      if (!tile_active(p, m_blk)) continue;
       const int m0 = m_blk * BLOCK_M;
       for (int t = 0; t < p.taps; ++t) {
         const long long row0 = (long long)m0 + p.tap_off[t];
@@ -458,62 +586,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + ch));
             sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + ch));
           }
-          uint8_t* st = smem + s * S::STAGE_BYTES;
-          // phase 1: issue every global load of this stage (16 x 16 B per thread in flight), phase 2: transform + store
+          const uint32_t st = smem_s + (uint32_t)(s * S::STAGE_BYTES);
+          // phase 1: pull this thread's share of the raw tile (TMA-staged) into registers; phase 2 (after the whole group
+          // has read): transform and overwrite the same bytes with the swizzled hi / lo operand tiles
           constexpr int NP = BLOCK_M / 8;
           float4 xf[NP];
+          mbarrier_wait(&raw_bar[grp * MAX_STAGES + s], (rawph >> s) & 1u);
+          rawph ^= 1u << s;
+          if (p.a_is_f32) {
 #pragma unroll
-          for (int pass = 0; pass < NP; ++pass) {
-            const long long srow = row0 + pass * 8 + rsub;
-            xf[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (chok && srow >= 0 && srow < p.a_rows) {
-              if (p.a_is_f32) {
-                xf[pass] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.a_src) + srow * p.a_ld + ch);
-              } else {
-                const __half* hp = reinterpret_cast<const __half*>(p.a_src) + srow * p.a_ld + ch;
-                const uint2 q = *reinterpret_cast<const uint2*>(hp);
-                uint2 ql = make_uint2(0u, 0u);
-                if (p.a_lo) ql = *reinterpret_cast<const uint2*>(hp + p.a_lo);
-                xf[pass] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(ql.x), __uint_as_float(ql.y));
-              }
+            for (int pass = 0; pass < NP; ++pass) xf[pass] = lds_f4(st + rsub * (BLOCK_K * 4) + c4 * 4 + pass * (8 * BLOCK_K * 4));
+          } else {
+#pragma unroll
+            for (int pass = 0; pass < NP; ++pass) {
+              const uint2 q = lds_u2(st + rsub * (BLOCK_K * 2) + c4 * 2 + pass * (8 * BLOCK_K * 2));
+              uint2 ql = make_uint2(0u, 0u);
+              if (p.a_lo) ql = lds_u2(st + S::A_BYTES + rsub * (BLOCK_K * 2) + c4 * 2 + pass * (8 * BLOCK_K * 2));
+              xf[pass] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(ql.x), __uint_as_float(ql.y));
             }
           }
-          mbarrier_wait(&empty_bar[s], ph ^ 1u);  // the global loads above are already in flight while we wait for the slot
-#pragma unroll
-          for (int pass = 0; pass < NP; ++pass) {
-            const int r = pass * 8 + rsub;
-            const long long srow = row0 + r;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            if (chok && srow >= 0 && srow < p.a_rows) {
-              if (p.a_is_f32) {
-                v0 = xf[pass].x, v1 = xf[pass].y, v2 = xf[pass].z, v3 = xf[pass].w;
-              } else {
-                const uint32_t q0 = __float_as_uint(xf[pass].x), q1 = __float_as_uint(xf[pass].y);
-                const uint32_t l0 = __float_as_uint(xf[pass].z), l1 = __float_as_uint(xf[pass].w);
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q0));
-                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&q1));
-                const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&l0));
-                const float2 g1 = __half22float2(*reinterpret_cast<const __half2*>(&l1));
-                v0 = f0.x + g0.x, v1 = f0.y + g0.y, v2 = f1.x + g1.x, v3 = f1.y + g1.y;
-              }
-              v0 = fmaf(v0, sc.x, sh.x), v1 = fmaf(v1, sc.y, sh.y), v2 = fmaf(v2, sc.z, sh.z), v3 = fmaf(v3, sc.w, sh.w);
-              if (p.pre_relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
-            }
-            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-            // SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 128-byte row; 8-row groups are 1024 B apart
-            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c4 >> 3) ^ (r & 7))) << 4) + (c4 & 7) * 2);
-            uint2 w;
-            w.x = *reinterpret_cast<const uint32_t*>(&h01);
-            w.y = *reinterpret_cast<const uint32_t*>(&h23);
-            *reinterpret_cast<uint2*>(st + off) = w;
-            if (NSEG == 3) {
-              const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-              const __half2 l01 = __floats2half2_rn(v0 - b01.x, v1 - b01.y), l23 = __floats2half2_rn(v2 - b23.x, v3 - b23.y);
-              uint2 wl;
-              wl.x = *reinterpret_cast<const uint32_t*>(&l01);
-              wl.y = *reinterpret_cast<const uint32_t*>(&l23);
-              *reinterpret_cast<uint2*>(st + S::A_BYTES + off) = wl;
-            }
+          asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+          // rows [r_lo, r_hi) of this tile exist in the source tensor (all of them except at its two ends)
+          const long long lo64 = -row0, hi64 = p.a_rows - row0;
+          const int r_lo = lo64 > 0 ? (int)(lo64 < BLOCK_M ? lo64 : BLOCK_M) : 0;
+          const int r_hi = !chok ? 0 : (hi64 >= BLOCK_M ? BLOCK_M : (hi64 > 0 ? (int)hi64 : 0));
+          // SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 128-byte row
+          const uint32_t dst = st + (uint32_t)(rsub * 128 + (((c4 >> 3) ^ rsub) << 4) + (c4 & 7) * 2);
+          const bool full = r_lo == 0 && r_hi == BLOCK_M;
+          if (p.a_is_f32) {
+            if (full) transform_store<NSEG, true, false>(xf, dst, S::A_BYTES, sc, sh, p.pre_relu != 0, rsub, r_lo, r_hi);
+            else transform_store<NSEG, true, true>(xf, dst, S::A_BYTES, sc, sh, p.pre_relu != 0, rsub, r_lo, r_hi);
+          } else {
+            if (full) transform_store<NSEG, false, false>(xf, dst, S::A_BYTES, sc, sh, p.pre_relu != 0, rsub, r_lo, r_hi);
+            else transform_store<NSEG, false, true>(xf, dst, S::A_BYTES, sc, sh, p.pre_relu != 0, rsub, r_lo, r_hi);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
@@ -607,34 +712,53 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ sr
   }
 }
 
-// 3-channel uint8 stem (7x7 etc.): one thread per 8 consecutive K elements of an output pixel -> one 16-byte store per plane
+// 3-channel uint8 stem (7x7 etc.): one thread per 8 consecutive K elements of an output pixel -> one 16-byte store per plane.
+// The k -> (kh, kw, c) decomposition comes from a shared-memory table (no runtime divisions in the inner loop):
+// entry = byte offset (kh*W + kw)*3 + c | kh << 24 | kw << 28, or 0xFFFFFFFF for the zero padding of K.
 __global__ void __launch_bounds__(256) im2col_u8c3_kernel(const uint8_t* __restrict__ src, float u8_scale, int Nimg, int H, int W, int KH,
                                                           int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, __half* __restrict__ out,
                                                           int ldout, int Kpad, int out_lo) {
+  extern __shared__ uint32_t ktab[];
+  const int K = KH * KW * 3;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    uint32_t e = 0xFFFFFFFFu;
+    if (k < K) {
+      const int c = k % 3, t = k / 3, kw = t % KW, kh = t / KW;
+      e = (uint32_t)((kh * W + kw) * 3 + c) | ((uint32_t)kh << 24) | ((uint32_t)kw << 28);
+    }
+    ktab[k] = e;
+  }
+  __syncthreads();
   const int k8n = Kpad >> 3;
   const long long total = (long long)Nimg * Ho * Wo * k8n;
-  const int K = KH * KW * 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k0 = (int)(i % k8n) * 8;
+    const int g = (int)(i % k8n);
     const long long m = i / k8n;
     const int xo = (int)(m % Wo);
-    const int yo = (int)((m / Wo) % Ho);
-    const int img = (int)(m / ((long long)Wo * Ho));
+    const long long my = m / Wo;
+    const int yo = (int)(my % Ho);
+    const int img = (int)(my / Ho);
     const int ybase = yo * stride - pad_t, xbase = xo * stride - pad_l;
-    const uint8_t* sp = src + (long long)img * H * W * 3;
+    const uint8_t* sp = src + ((long long)img * H * W + (long long)ybase * W + xbase) * 3;
+    const bool interior = ybase >= 0 && xbase >= 0 && ybase + KH <= H && xbase + KW <= W;
+    const uint4 e0 = *reinterpret_cast<const uint4*>(ktab + g * 8), e1 = *reinterpret_cast<const uint4*>(ktab + g * 8 + 4);
+    const uint32_t ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = k0 + e;
       float val = 0.f;
-      if (k < K) {
-        const int c = k % 3, t = k / 3, kw = t % KW, kh = t / KW;
-        const int y = ybase + kh, x = xbase + kw;
-        if (y >= 0 && y < H && x >= 0 && x < W) val = (float)sp[((long long)y * W + x) * 3 + c] * u8_scale;
+      const uint32_t t = ee[e];
+      if (t != 0xFFFFFFFFu) {
+        bool ok = interior;
+        if (!interior) {
+          const int y = ybase + (int)((t >> 24) & 15u), x = xbase + (int)(t >> 28);
+          ok = y >= 0 && y < H && x >= 0 && x < W;
+        }
+        if (ok) val = (float)sp[t & 0xFFFFFFu] * u8_scale;
       }
       v[e] = val;
     }
-    store8(out + m * ldout + k0, out_lo, v);
+    store8(out + m * ldout + g * 8, out_lo, v);
   }
 }
 
@@ -915,22 +1039,25 @@ static PFN_encodeTiled get_encode_fn(tiab_ctx* h) {
   return fn;
 }
 
-// 2-D fp16 matrix [rows, cols] with row pitch ld (elements); box = {64 cols, box_rows}; 128-byte swizzle.
+// 2-D matrix [rows, cols] with row pitch ld (elements); box = {64 cols, box_rows}.
+// raw == 0: fp16 operand tile, 128-byte swizzle (what the UMMA descriptors expect).
+// raw == 1 / 2: un-swizzled fp16 / fp32 tile for the operand-transform warps (dense [box_rows][64] in shared memory).
 static int make_map_2d(tiab_ctx* h, CUtensorMap* map, const void* base, long long rows, int cols, long long ld,
-                       int box_rows) {
+                       int box_rows, int raw = 0) {
   PFN_encodeTiled enc = get_encode_fn(h);
   if (!enc) return TIAB_E_CUDA;
-  if (((uintptr_t)base & 15) || ((ld * 2) & 15)) {
+  const int esz = raw == 2 ? 4 : 2;
+  if (((uintptr_t)base & 15) || ((ld * esz) & 15)) {
     h->err = "conv: operand base/pitch must be 16-byte aligned";
     return TIAB_E_INVALID;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, raw == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, raw ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
     return TIAB_E_CUDA;
@@ -941,7 +1068,7 @@ static int make_map_2d(tiab_ctx* h, CUtensorMap* map, const void* base, long lon
 template <int BN, int NSEG, int AMODE>
 static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, ConvParams& p,
                        cudaStream_t s) {
-  using S = ConvSmem<BN, NSEG>;
+  using S = ConvSmem<BN, NSEG, AMODE>;
   static bool attr_set = false;
   if (!attr_set) {
     TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN, NSEG, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -1007,12 +1134,18 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   int rc = make_map_2d(h, &tb, d->w, d->N, (int)kcols, d->w_ld, BN);
   if (rc) return rc;
   if (amode) {
-    if ((d->cin & 3) || (d->x_ld & 3) || ((uintptr_t)d->x & 15) || (d->x_lo_off & 3)) {
-      h->err = "tiab_conv_gemm: transform mode needs 16-byte aligned rows and cin % 4 == 0";
+    if ((d->cin & 3) || (d->x_lo_off & 7)) {
+      h->err = "tiab_conv_gemm: transform mode needs cin % 4 == 0 and a 16-byte aligned lo plane";
       return TIAB_E_INVALID;
     }
-    ta = tb;   // unused in transform mode
-    ta2 = tb;
+    // raw tiles for the transform warps; the map's inner extent is the logical cin, so the K padding reads as zeros
+    rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M, d->x_is_f32 ? 2 : 1);
+    if (rc) return rc;
+    ta2 = ta;
+    if (!d->x_is_f32 && d->x_lo_off) {
+      rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, d->cin, d->x_ld, BLOCK_M, 1);
+      if (rc) return rc;
+    }
   } else {
     rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M);
     if (rc) return rc;
@@ -1030,6 +1163,15 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   p.pre_scale = (const float*)d->pre_scale, p.pre_shift = (const float*)d->pre_shift, p.pre_relu = d->pre_relu;
   for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t];
   p.Hin = d->Hin, p.Win = d->Win;
+  p.skip = (d->y0 > 0 || d->y1 < d->Hin) ? 1 : 0;
+  {
+    const bool r32 = d->res32 != nullptr, r16 = d->res16 != nullptr, o32 = d->out32 != nullptr, o16 = d->out16 != nullptr,
+               o16b = d->out16b != nullptr;
+    p.epi_mode = 0;
+    if (!r32 && !r16 && !o32 && o16 && !o16b) p.epi_mode = d->lo16 ? 1 : 2;
+    else if (!r16 && o32 && !o16 && !o16b) p.epi_mode = r32 ? 4 : 3;
+    else if (r32 && !o32 && !o16 && o16b && d->lo16b) p.epi_mode = 5;
+  }
   p.y0 = d->y0, p.y1 = d->y1, p.x0 = d->x0, p.x1 = d->x1;
   p.Hd = d->Hd, p.Wd = d->Wd, p.dy = d->dy, p.dx = d->dx;
   p.Hr = d->Hr, p.Wr = d->Wr, p.ry = d->ry, p.rx = d->rx;
@@ -1076,9 +1218,10 @@ int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale,
     AUX_LAUNCH_CHECK(h, "im2col_vec8");
     return TIAB_OK;
   }
-  if (src_is_u8 && C == 3 && ldsrc == 3 && (Kpad % 8) == 0 && (ldout % 8) == 0 && (out_lo % 8) == 0 && ((uintptr_t)out_f16 & 15) == 0) {
+  if (src_is_u8 && C == 3 && ldsrc == 3 && (Kpad % 8) == 0 && (ldout % 8) == 0 && (out_lo % 8) == 0 && ((uintptr_t)out_f16 & 15) == 0 &&
+      KH <= 15 && KW <= 15 && (long long)(KH * (long long)W + KW) * 3 < (1 << 24)) {
     long long t3 = (long long)N * Ho * Wo * (Kpad >> 3);
-    im2col_u8c3_kernel<<<aux_grid(h, t3, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, u8_scale, N, H, W, KH, KW, stride, pad_t,
+    im2col_u8c3_kernel<<<aux_grid(h, t3, 256), 256, Kpad * sizeof(uint32_t), (cudaStream_t)stream>>>((const uint8_t*)src, u8_scale, N, H, W, KH, KW, stride, pad_t,
                                                                              pad_l, Ho, Wo, (__half*)out_f16, ldout, Kpad, out_lo);
     AUX_LAUNCH_CHECK(h, "im2col_u8c3");
     return TIAB_OK;

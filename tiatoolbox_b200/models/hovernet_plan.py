@@ -31,11 +31,9 @@ class HoVerNetPlan(Plan):
         # ---------------- conv0: [pad] 7x7 s1 + BN + ReLU via im2col (Cin = 3) ----------------
         pad0 = tf_same_pad(S, 7, 1)[0] if mode == "fast" else 0
         S0 = S if mode == "fast" else S - 6
-        w0, b0 = self.fold_bn(sd, "conv0./", "conv0.bn", im2col=True)
-        i0 = self.act("im2col0", (B * S0 * S0,), 192)
         x0 = self.act("x0", (B, S0, S0), 64)
-        self.im2col(self.inp, True, 1.0 / 255.0, 0, B, S, S, 3, 3, 7, 1, pad0, S0, i0, 192)
-        self.gemm(x=i0, rows=B * S0 * S0, cin=192, w=w0, N=64, bias=b0, relu=True, out16=x0)
+        self.stem_u8(sd, "conv0./", "conv0.bn", inp=self.inp, u8_scale=1.0 / 255.0, hw=(S, S), k=7, stride=1, pad=pad0,
+                     out_hw=(S0, S0), N=64, out16=x0, name="im2col0")
 
         # ---------------- encoder: 4 pre-activation bottleneck residual blocks ----------------
         feats = []
@@ -85,8 +83,8 @@ class HoVerNetPlan(Plan):
                       window=(h, G3 - h, h, G3 - h), out16=cb3, coff16=0)
             self._dense(sd, f"{p}.u3.dense", 8, cb3, t3, G3, 256, k, h)
             s, t = bn_scale_shift(sd, f"{p}.u3.dense.blk_bna.bn")
-            self.gemm(x=cb3, rows=B * G3 * G3, cin=512, w=self.weight(sd[f"{p}.u3.convf.weight"]), N=512, out16=u3out,
-                      pre=(self.const(s), self.const(t), True))
+            self.conv(x=cb3, grid=(G3, G3), cin=512, w=self.weight(sd[f"{p}.u3.convf.weight"]), k=1, centered=False, N=512,
+                      window=(lo3, G3 - lo3, lo3, G3 - lo3), out16=u3out, pre=(self.const(s), self.const(t), True))
             # u2
             self.add(lambda: ops.upsample_add(u3out, W3, W3, G3, G3, lo3, lo3, d1, H1, H1, crop1 // 2, crop1 // 2, B, 512, None, None,
                                               False, u2in, G2, G2, 0, 0))
@@ -94,8 +92,8 @@ class HoVerNetPlan(Plan):
                       window=(h, G2 - h, h, G2 - h), out16=cb2, coff16=0)
             self._dense(sd, f"{p}.u2.dense", 4, cb2, t2, G2, 128, k, h)
             s, t = bn_scale_shift(sd, f"{p}.u2.dense.blk_bna.bn")
-            self.gemm(x=cb2, rows=B * G2 * G2, cin=256, w=self.weight(sd[f"{p}.u2.convf.weight"]), N=256, out16=u2out,
-                      pre=(self.const(s), self.const(t), True))
+            self.conv(x=cb2, grid=(G2, G2), cin=256, w=self.weight(sd[f"{p}.u2.convf.weight"]), k=1, centered=False, N=256,
+                      window=(lo2, G2 - lo2, lo2, G2 - lo2), out16=u2out, pre=(self.const(s), self.const(t), True))
             # u1
             self.add(lambda: ops.upsample_add(u2out, W2, W2, G2, G2, lo2, lo2, d0, H0, H0, crop0 // 2, crop0 // 2, B, 256, None, None,
                                               False, u1in, G1, G1, pu[0], pu[0]))
@@ -177,8 +175,10 @@ class HoVerNetPlan(Plan):
             s, sft = bn_scale_shift(sd, f"{un}.preact_bna/bn")
             w1, b1 = self.fold_bn(sd, f"{un}.conv1", f"{un}.conv1/bn")
             # the unit's own BN+ReLU over the raw concat channels is applied while staging the GEMM operand
-            self.gemm(x=cb, rows=B * G * G, cin=c_u, w=w1, N=128, bias=b1, relu=True, out16=t, pre=(self.const(s), self.const(sft), True))
             lo = h * (u + 2)
+            # only the rows / columns the unit's kxk convolution will read are produced (whole tiles outside are skipped)
+            self.conv(x=cb, grid=(G, G), cin=c_u, w=w1, k=1, centered=False, N=128, window=(lo - h, G - lo + h, lo - h, G - lo + h),
+                      bias=b1, relu=True, out16=t, pre=(self.const(s), self.const(sft), True))
             w2 = self.weight(sd[f"{un}.conv2.weight"], groups=4)
             self.conv(x=t, grid=(G, G), cin=128, w=w2, k=k, centered=True, N=32, window=(lo, G - lo, lo, G - lo),
                       out16=cb, coff16=c_u)

@@ -158,9 +158,9 @@ class Plan:
         self.ops.append(op)
         return op
 
-    def gemm(self, *, x, rows: int, cin: int, w: torch.Tensor, N: int, pre=None, **kw) -> ops.ConvOp:
+    def gemm(self, *, x, rows: int, cin: int, w: torch.Tensor, N: int, pre=None, taps=(0,), **kw) -> ops.ConvOp:
         """Plain [rows, cin] x [N, cin]^T GEMM (1x1 conv on a dense matrix / im2col output)."""
-        op = ops.ConvOp(x_rows=rows, cin=cin, w=w, taps=[0], M=rows, N=N, grid=(1, rows),
+        op = ops.ConvOp(x_rows=rows, cin=cin, w=w, taps=list(taps), M=rows, N=N, grid=(1, rows),
                         window=(0, 1, 0, rows), dst_geom=kw.pop("dst_geom", (1, rows, 0, 0)), **self._x_kw(x, pre), **self._out_kw(kw))
         self.flops += 2.0 * rows * N * cin
         self.mma_flops += op.mma_flops
@@ -170,6 +170,26 @@ class Plan:
     def im2col(self, src, src_is_u8, u8_scale, src_lo, n, h, w, c, ldsrc, k, stride, pad, ho, out: Act, kpad):
         self.add(lambda: ops.im2col(src, src_is_u8, u8_scale, src_lo, n, h, w, c, ldsrc, k, k, stride, pad, pad, ho, ho, out.t, out.ld,
                                     kpad, out.lo))
+
+    def stem_u8(self, sd, conv_name: str, bn_name: str, *, inp: torch.Tensor, u8_scale: float, hw, k: int, stride: int, pad: int,
+                out_hw, N: int, out16: Act, name: str = "stem.im2col") -> None:
+        """First convolution straight from the uint8 NHWC batch: im2col (K = k*k*3 padded to 64) + GEMM + BN + ReLU.
+
+        The input scale (1/255) is folded into the weights, so the gathered operand holds the raw byte values, which
+        fp16 represents exactly: it needs no lo plane, and split precision only has to cover the weights --
+        A*W_hi + A*W_lo, run as two zero-offset "taps" over the same rows (2 instead of 3 MMA segments, half the
+        im2col bytes)."""
+        H, W = hw
+        Ho, Wo = out_hw
+        scale, shift = bn_scale_shift(sd, bn_name)
+        w = self.weight(sd[conv_name + ".weight"], scale.double() * float(u8_scale), im2col=True)
+        kpad = ceil_to(k * k * 3, 64)
+        rows = self.B * Ho * Wo
+        gathered = Act(self.buf(name, (rows, kpad)), kpad, kpad, 0)
+        self.add(lambda: ops.im2col(inp, True, 1.0, 0, self.B, H, W, 3, 3, k, k, stride, pad, pad, Ho, Wo, gathered.t, kpad, kpad, 0))
+        self.gemm(x=gathered, rows=rows, cin=kpad, w=w, N=N, bias=self.const(shift), relu=True, out16=out16,
+                  taps=(0, 0) if self.split else (0,))
+        self.flops -= 2.0 * rows * N * (kpad - k * k * 3)   # count the real K, not the padding
 
     def bn_relu(self, src: Act, c: int, scale, shift, rows: int, dst: Act, relu=True):
         self.add(lambda: ops.bn_relu(src.t, False, src.ld, 0, src.lo, scale, shift, relu, rows, c, dst.t, dst.ld, 0, dst.lo))

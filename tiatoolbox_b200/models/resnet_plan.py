@@ -27,11 +27,9 @@ class ResNetTrunkMixin:
         exp = 4 if bottleneck else 1
         # ---- stem: 7x7/2 pad 3 + BN + ReLU (im2col, K = 147 -> 192), then 3x3/2 max pool ----
         H0, W0 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-        w0, b0 = self.fold_bn(sd, prefix + stem_names[0], prefix + stem_names[1], im2col=True)
-        i0 = self.act("stem.im2col", (B * H0 * W0,), 192)
         x0 = self.act("stem.x0", (B, H0, W0), 64)
-        self.add(lambda: ops.im2col(self.inp, True, u8_scale, 0, B, H, W, 3, 3, 7, 7, 2, 3, 3, H0, W0, i0.t, i0.ld, 192, i0.lo))
-        self.gemm(x=i0, rows=B * H0 * W0, cin=192, w=w0, N=64, bias=b0, relu=True, out16=x0)
+        self.stem_u8(sd, prefix + stem_names[0], prefix + stem_names[1], inp=self.inp, u8_scale=u8_scale, hw=(H, W), k=7, stride=2, pad=3,
+                     out_hw=(H0, W0), N=64, out16=x0)
         H1, W1 = (H0 + 2 - 3) // 2 + 1, (W0 + 2 - 3) // 2 + 1
         feats = [(x0, H0, W0)]
         inplanes = 64
