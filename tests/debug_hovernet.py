@@ -43,7 +43,9 @@ def val(name, c):
     return v[..., :c]
 
 
-cmp("x0", val("x0", 64), cap["x0"])
+_cat = plan.bufs["d0.cat"]          # [t2 | x0] per plane; conv0's output is the second 64-channel slice
+_C = _cat.shape[-1] // (2 if plan.split else 1)
+cmp("x0", _cat[..., 64:128].float() + (_cat[..., _C + 64:_C + 128].float() if plan.split else 0), cap["x0"])
 for n in ("d0", "d1", "d2", "d3"):
     cmp(n, val(f"{n}.out", 10**6), cap[n])
 cmp("dbot", val("dbot", 1024), cap["dbot"])

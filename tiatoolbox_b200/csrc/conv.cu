@@ -301,7 +301,12 @@ struct ConvSmem {
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 384 + 1024;  // barriers + tmem ptr, + slack for 1024 B alignment
-  static constexpr int TMEM_COLS = (2 * BLOCK_N) <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  // Narrow split-precision tiles (N <= 64) are bound by the shared-memory reads of the A operand (4 KB per UMMA whatever N
+  // is), so W_hi and W_lo -- adjacent in the stage -- are fed as ONE 2N-row B tile: A_hi x [W_hi; W_lo] lands in 2N
+  // accumulator columns, A_lo x W_hi adds to the first N, and the epilogue sums the two halves (2 UMMAs per K step, not 3).
+  static constexpr bool CONCAT = NSEG == 3 && BLOCK_N <= 64;
+  static constexpr int ACC_COLS = CONCAT ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
 };
 
 template <int BLOCK_N, int NSEG, int AMODE>
@@ -402,6 +407,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BLOCK_N) >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);  // N = 2*BLOCK_N
       int s = 0;
       uint32_t ph = 0;
       int ab = 0;
@@ -410,7 +416,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!tile_active(p, tile / p.num_n_tiles)) continue;
         mbarrier_wait(&tempty_bar[ab], aph ^ 1u);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BLOCK_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ab * S::ACC_COLS);
         for (int k = 0; k < kiters; ++k) {
           mbarrier_wait(&full_bar[s], ph);
           tcgen05_fence_after();
@@ -418,15 +424,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (NSEG == 3) {
             const uint64_t ahi = make_smem_desc(base), alo = make_smem_desc(base + S::A_BYTES);
             const uint64_t bhi = make_smem_desc(base + S::A_AREA), blo = make_smem_desc(base + S::A_AREA + S::B_BYTES);
+            if (S::CONCAT) {
 #pragma unroll
-            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)  // +2 in (addr >> 4) units = 32 bytes = 16 fp16 along K
-              tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {  // +2 in (addr >> 4) units = 32 bytes = 16 fp16 along K
+                tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc2, (k > 0 || kk > 0) ? 1u : 0u);
+                tcgen05_mma_f16(tmem_d, alo + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, 1u);
+              }
+            } else {
 #pragma unroll
-            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-              tcgen05_mma_f16(tmem_d, alo + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, 1u);
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, (k > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-              tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), blo + (uint64_t)(kk * 2), idesc, 1u);
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                tcgen05_mma_f16(tmem_d, alo + (uint64_t)(kk * 2), bhi + (uint64_t)(kk * 2), idesc, 1u);
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                tcgen05_mma_f16(tmem_d, ahi + (uint64_t)(kk * 2), blo + (uint64_t)(kk * 2), idesc, 1u);
+            }
           } else {
             const uint64_t adesc = make_smem_desc(base), bdesc = make_smem_desc(base + S::A_AREA);
 #pragma unroll
@@ -498,7 +512,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbarrier_wait(&tfull_bar[ab], aph);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * S::ACC_COLS);
       bool released = false;
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += CSTEP) {
@@ -509,7 +523,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 8; ++i)
             if (vmask >> i & 1u) rnext[i] = *reinterpret_cast<const float4*>(rbase + (long long)rrow[i] * p.ldres + c0 + CSTEP);
         }
-        tmem_ld_wait();
+        if (S::CONCAT) {   // second accumulator half (A_hi x W_lo)
+          uint32_t r2[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(BLOCK_N + c0), r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         if (c0 + CSTEP >= BLOCK_N) {   // last chunk of this warp is in registers: hand the accumulator back to the MMA warp now
           tcgen05_fence_before();
           __syncwarp();

@@ -31,15 +31,20 @@ class HoVerNetPlan(Plan):
         # ---------------- conv0: [pad] 7x7 s1 + BN + ReLU via im2col (Cin = 3) ----------------
         pad0 = tf_same_pad(S, 7, 1)[0] if mode == "fast" else 0
         S0 = S if mode == "fast" else S - 6
-        x0 = self.act("x0", (B, S0, S0), 64)
+        # d0's unit-0 conv3 and its 1x1 shortcut are ONE GEMM over the channel concatenation [t2 | x0] (see _res_block), so x0 is
+        # produced straight into its slice of that buffer
+        name0, cin0, (_, c2_0, _), _, stride0 = RES_CFG[0]
+        assert stride0 == 1 and cin0 == 64
+        cat0 = self.act(f"{name0}.cat", (B, S0, S0), c2_0 + cin0)
+        x0 = cat0.slice(c2_0, cin0)
         self.stem_u8(sd, "conv0./", "conv0.bn", inp=self.inp, u8_scale=1.0 / 255.0, hw=(S, S), k=7, stride=1, pad=pad0,
                      out_hw=(S0, S0), N=64, out16=x0, name="im2col0")
 
         # ---------------- encoder: 4 pre-activation bottleneck residual blocks ----------------
         feats = []
         x_act, H = x0, S0
-        for name, cin, (c1, c2, c3), units, stride in RES_CFG:
-            x_act, H = self._res_block(sd, name, x_act, H, cin, c1, c2, c3, units, stride)
+        for bi, (name, cin, (c1, c2, c3), units, stride) in enumerate(RES_CFG):
+            x_act, H = self._res_block(sd, name, x_act, H, cin, c1, c2, c3, units, stride, cat=cat0 if bi == 0 else None)
             feats.append((x_act, H))
         (d0, H0), (d1, H1), (d2, H2), (d3, H3) = feats
         dbot = self.act("dbot", (B, H3, H3), 1024)
@@ -117,21 +122,23 @@ class HoVerNetPlan(Plan):
                                             self.hv_out, self.tp_out))
 
     # ------------------------------------------------------------------------------------------
-    def _res_block(self, sd, name, x_act, H, cin, c1, c2, c3, units, stride):
+    def _res_block(self, sd, name, x_act, H, cin, c1, c2, c3, units, stride, cat=None):
+        """Pre-activation bottleneck block (hovernet.py:152-251).  The residual stream is fp32; unit 0's conv3 and the block's
+        1x1 shortcut are a single GEMM over the channel concatenation [t2 | shortcut input] with K-concatenated weights
+        [W3 | Wsc], which writes the stream once instead of write + read-modify-write."""
         B = self.B
         Ho = (H + stride - 1) // stride
         stream = self.buf(f"{name}.stream", (B, Ho, Ho, c3), torch.float32)
         out = self.act(f"{name}.out", (B, Ho, Ho), c3)
         ppad = self.act(f"{name}.pad", (B, Ho + 2, Ho + 2), c1)   # TF-same pad of a stride-1 3x3: (1, 1)
-        t2 = self.act(f"{name}.t2", (B, Ho, Ho), c2)
-        # ---- shortcut of unit 0 -> fp32 residual stream ----
-        wsc = self.weight(sd[f"{name}.shortcut.weight"])
-        if stride == 1:
-            self.gemm(x=x_act, rows=B * H * H, cin=cin, w=wsc, N=c3, out32=stream, ld32=c3)
-        else:
-            g = self.act(f"{name}.sc_gather", (B * Ho * Ho,), cin)
-            self.im2col(x_act.t, False, 1.0, x_act.lo, B, H, H, cin, x_act.ld, 1, stride, 0, Ho, g, cin)
-            self.gemm(x=g, rows=B * Ho * Ho, cin=cin, w=wsc, N=c3, out32=stream, ld32=c3)
+        if cat is None:
+            cat = self.act(f"{name}.cat", (B, Ho, Ho), c2 + cin)
+        t2, sc_in = cat.slice(0, c2), cat.slice(c2, cin)
+        if stride == 1:   # the caller produced x_act straight into the shortcut slice
+            assert x_act.t.data_ptr() == sc_in.t.data_ptr() and x_act.ld == sc_in.ld
+        else:             # strided 1x1 shortcut: gather the pixels it sees
+            self.im2col(x_act.t, False, 1.0, x_act.lo, B, H, H, cin, x_act.ld, 1, stride, 0, Ho, sc_in, cin)
+        w3sc = self.weight(torch.cat([sd[f"{name}.units.0.conv3.weight"], sd[f"{name}.shortcut.weight"]], dim=1))
         cur_in, cur_c, cur_pre = x_act, cin, None
         for i in range(units):
             u = f"{name}.units.{i}"
@@ -156,12 +163,14 @@ class HoVerNetPlan(Plan):
             last = i == units - 1
             bn_next = f"{name}.blk_bna.bn" if last else f"{name}.units.{i + 1}.preact/bn"
             sc, sh = bn_scale_shift(sd, bn_next)
+            if i == 0:   # conv3 + shortcut in one GEMM, no residual operand
+                x3, k3, w3, res = cat, c2 + cin, w3sc, {}
+            else:
+                x3, k3, w3, res = t2, c2, self.weight(sd[f"{u}.conv3.weight"]), {"res32": stream, "ldres": c3}
             if last:   # closing BN+ReLU of the block: the activated tensor is what the next block / the decoder skip consume
-                self.gemm(x=t2, rows=B * Ho * Ho, cin=c2, w=self.weight(sd[f"{u}.conv3.weight"]), N=c3, res32=stream, ldres=c3,
-                          out16b=out, scale2=self.const(sc), shift2=self.const(sh))
+                self.gemm(x=x3, rows=B * Ho * Ho, cin=k3, w=w3, N=c3, out16b=out, scale2=self.const(sc), shift2=self.const(sh), **res)
             else:      # only the fp32 stream is written; the next unit's conv1 applies its pre-activation while loading it
-                self.gemm(x=t2, rows=B * Ho * Ho, cin=c2, w=self.weight(sd[f"{u}.conv3.weight"]), N=c3, res32=stream, ldres=c3,
-                          out32=stream, ld32=c3)
+                self.gemm(x=x3, rows=B * Ho * Ho, cin=k3, w=w3, N=c3, out32=stream, ld32=c3, **res)
             cur_in, cur_c, cur_pre = stream, c3, (self.const(sc), self.const(sh), True)
         return out, Ho
 

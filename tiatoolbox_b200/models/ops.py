@@ -39,6 +39,11 @@ class Act:
     def hi(self) -> torch.Tensor:
         return self.t[..., : self.C]
 
+    def slice(self, c0: int, C: int) -> "Act":
+        """Channels [c0, c0 + C) of every plane as an Act of its own (same pitch and lo offset, shifted base pointer)."""
+        assert c0 % 8 == 0 and c0 + C <= self.C
+        return Act(self.t[..., c0:], C, self.ld, self.lo)
+
     def value(self) -> torch.Tensor:
         """fp32 value (hi + lo) — for tests/debugging."""
         v = self.t[..., : self.C].float()
