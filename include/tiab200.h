@@ -143,6 +143,11 @@ typedef struct {
   const void* pre_scale; /* fp32 [cin] or NULL */
   const void* pre_shift; /* fp32 [cin] or NULL */
   int pre_relu, x_is_f32, split;
+  /* Grouped launch (several networks branches of identical shape in one grid, e.g. HoVer-Net's np / hv / tp decoders):
+   * the M output rows are `groups` consecutive blocks of group_rows rows; group g uses weight rows [g*N, (g+1)*N) of w,
+   * bias / scale2 / shift2 + g*N and pre_scale / pre_shift + g*cin.  x_grouped == 0: every group reads the same input rows
+   * [0, group_rows) of x (a shared input); != 0: x holds groups*group_rows rows.  groups <= 1: plain launch. */
+  int groups, group_rows, x_grouped;
 } tiab_conv_desc_t;
 
 int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);

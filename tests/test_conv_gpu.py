@@ -243,3 +243,47 @@ def test_window_tile_skipping(ops, k, transform):
     assert (out32[~inside] == -7.0).all()
     err = (out32[inside] - ref[inside]).abs().max().item()
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("mode", ["shared_input_3x3", "grouped_input_3x3", "grouped_transform_1x1"])
+def test_grouped_launch(ops, mode):
+    """Three same-shape convolutions with different weights in one grid (HoVer-Net's decoder branches): group rows are not
+    a multiple of the 128-row tile, so every group ends in a partial tile."""
+    import torch
+    import torch.nn.functional as F
+
+    torch.manual_seed(6)
+    dev = torch.device("cuda")
+    R, nimg, H, W, cin, cout = 3, 2, 19, 21, 64, 64          # group_rows = 2*19*21 = 798
+    k = 1 if mode == "grouped_transform_1x1" else 3
+    shared = mode == "shared_input_3x3"
+    w = torch.randn(R, cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+    bias = torch.randn(R * cout, device=dev) * 0.1
+    wp = torch.cat([_pack_w(w[r], cin) for r in range(R)], dim=0).contiguous()
+    taps = [(kh - k // 2) * W + (kw - k // 2) for kh in range(k) for kw in range(k)]
+    y0, y1, x0, x1 = k // 2, H - k // 2, k // 2, W - k // 2
+    M = R * nimg * H * W
+    out32 = torch.full((R * nimg, H, W, cout), -7.0, device=dev)
+    if mode == "grouped_transform_1x1":
+        xs = torch.randn(R * nimg, H, W, cin, device=dev)
+        scale, shift = torch.rand(R * cin, device=dev) + 0.5, torch.randn(R * cin, device=dev)
+        a = torch.relu(xs.view(R, nimg, H, W, cin) * scale.view(R, 1, 1, 1, cin) + shift.view(R, 1, 1, 1, cin)).half().float()
+        op = ops.ConvOp(x=xs, x_rows=M, x_ld=cin, cin=cin, w=wp, taps=taps, M=M, N=cout, grid=(H, W), window=(y0, y1, x0, x1),
+                        dst_geom=(H, W, 0, 0), out32=out32, ld32=cout, bias=bias, pre_scale=scale, pre_shift=shift, pre_relu=True,
+                        x_is_f32=True, split=False, groups=R, group_rows=nimg * H * W)
+    else:
+        nin = nimg if shared else R * nimg
+        xh = torch.randn(nin, H, W, cin, device=dev).half()
+        a = (xh.float().unsqueeze(0).expand(R, -1, -1, -1, -1) if shared else xh.float().view(R, nimg, H, W, cin))
+        op = ops.ConvOp(x=xh, x_rows=nin * H * W, x_ld=cin, cin=cin, w=wp, taps=taps, M=M, N=cout, grid=(H, W),
+                        window=(y0, y1, x0, x1), dst_geom=(H, W, 0, 0), out32=out32, ld32=cout, bias=bias, groups=R,
+                        group_rows=nimg * H * W, x_grouped=not shared)
+    op()
+    torch.cuda.synchronize()
+    got = out32.view(R, nimg, H, W, cout)
+    for r in range(R):
+        ref = F.conv2d(a[r].permute(0, 3, 1, 2), w[r].half().float(), bias[r * cout:(r + 1) * cout], padding=k // 2).permute(0, 2, 3, 1)
+        err = (got[r][:, y0:y1, x0:x1] - ref[:, y0:y1, x0:x1]).abs().max().item()
+        assert err < 2e-3 * max(1.0, ref.abs().max().item()), (r, err)
+    if k == 3:
+        assert (got[:, :, 0] == -7.0).all() and (got[:, :, :, 0] == -7.0).all()

@@ -50,6 +50,7 @@ class ConvDesc(C.Structure):
         ("res32", C.c_void_p), ("res16", C.c_void_p), ("ldres", C.c_int), ("coffres", C.c_int), ("reslo", C.c_int),
         ("relu", C.c_int),
         ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p), ("pre_relu", C.c_int), ("x_is_f32", C.c_int), ("split", C.c_int),
+        ("groups", C.c_int), ("group_rows", C.c_int), ("x_grouped", C.c_int),
     ]
 
 

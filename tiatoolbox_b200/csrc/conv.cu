@@ -76,6 +76,11 @@ struct ConvParams {
   int nseg;               // 1: fp16 operands ; 3: split-fp16 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo ~ fp32 operands)
   int lo16, lo16b, reslo; // channel offsets of the residual ("lo") planes of out16 / out16b / res16 (0 = none)
   int num_m_tiles, num_n_tiles;
+  // Grouped launch (HoVer-Net's three decoder branches in one grid): the M rows are `groups` consecutive blocks of
+  // group_rows rows; group g uses weight rows [g*N, (g+1)*N), bias/scale2/shift2 + g*N and pre_scale/pre_shift + g*cin.
+  // Tiles never straddle groups (each group has its own ceil(group_rows/128) row tiles).  a_grouped == 0: all groups read
+  // the same A rows [0, group_rows) (a shared input tensor).
+  int groups, group_rows, a_grouped, m_tiles_pg;
   int epi_mode;           // specialised epilogue row loop (0 = generic), see tiab_conv_gemm
   int skip;               // 1: the window does not span all grid rows -> tiles with no valid output row are skipped
 };
@@ -271,11 +276,19 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t stg_
 
 // True when at least one of the tile's 128 grid rows lies inside the valid y-window (every warp role evaluates this for
 // the same tile sequence, so skipped tiles never touch a barrier).
+// Row tile m_blk -> its group g, first global output row m0 and the end (exclusive) of the group's rows.
+__device__ __forceinline__ void tile_rows(const ConvParams& p, int m_blk, int& g, int& m0, int& mend) {
+  g = m_blk / p.m_tiles_pg;
+  m0 = g * p.group_rows + (m_blk - g * p.m_tiles_pg) * BLOCK_M;
+  mend = (g + 1) * p.group_rows;
+}
+
 __device__ __forceinline__ bool tile_active(const ConvParams& p, int m_blk) {
   if (!p.skip) return true;
   const int gp = p.Hin * p.Win;
-  const int r0 = m_blk * BLOCK_M;
-  const int r1 = min(r0 + BLOCK_M, p.M) - 1;
+  int g, r0, mend;
+  tile_rows(p, m_blk, g, r0, mend);
+  const int r1 = min(r0 + BLOCK_M, mend) - 1;
   const int i0 = r0 / gp, i1 = r1 / gp;
   const int ya = (r0 - i0 * gp) / p.Win, yb = (r1 - i1 * gp) / p.Win;
   if (i0 == i1) return !(yb < p.y0 || ya >= p.y1);
@@ -368,8 +381,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int iter = 0;   // K-iterations issued so far (parity = transform group that will take the stage)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
-      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
       if (!tile_active(p, m_blk)) continue;
+      int g, m0, mend;
+      tile_rows(p, m_blk, g, m0, mend);
+      if (!p.a_grouped) m0 -= g * p.group_rows;        // shared input: every group reads rows [0, group_rows)
+      const int n0 = g * p.N + n_blk * BLOCK_N;        // weight rows of this group
       if (lane == 0) {
         for (int t = 0; t < p.taps; ++t) {
           const int row = m0 + p.tap_off[t];
@@ -479,15 +495,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_blk = tile % p.num_n_tiles, m_blk = tile / p.num_n_tiles;
       if (!tile_active(p, m_blk)) continue;
       const int n0 = n_blk * BLOCK_N;
+      int g, m0, mend;
+      tile_rows(p, m_blk, g, m0, mend);
+      const int gn = g * p.N;   // offset of this group's per-channel vectors
       // geometry of the row this lane owns in TMEM, then redistributed to the lanes that will store it
       int drow_l = 0, rrow_l = 0, valid_l = 0;
       {
-        const int row = m_blk * BLOCK_M + quad * 32 + lane;
+        const int row = m0 + quad * 32 + lane;
         const int img = row / grid_px;
         const int rem = row - img * grid_px;
         const int y = rem / p.Win;
         const int x = rem - y * p.Win;
-        valid_l = row < p.M && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
+        valid_l = row < mend && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
         drow_l = (img * p.Hd + (y + p.dy)) * p.Wd + (x + p.dx);
         rrow_l = (img * p.Hr + (y + p.ry)) * p.Wr + (x + p.rx);
       }
@@ -544,10 +563,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         const int n = n0 + c0 + 4 * cq;   // first of this lane's 4 output channels
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc2 = bias4, sh2 = bias4;
-        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + n));
         if (p.out16b) {
-          sc2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + n));
-          sh2 = __ldg(reinterpret_cast<const float4*>(p.shift2 + n));
+          sc2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + gn + n));
+          sh2 = __ldg(reinterpret_cast<const float4*>(p.shift2 + gn + n));
         }
         constexpr bool PRE = !AMODE;
         switch (p.epi_mode) {
@@ -590,7 +609,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_tiles;
       if (!tile_active(p, m_blk)) continue;
-      const int m0 = m_blk * BLOCK_M;
+      int g, m0, mend;
+      tile_rows(p, m_blk, g, m0, mend);
+      if (!p.a_grouped) m0 -= g * p.group_rows;
+      const int gc = g * p.a_cin;   // this group's pre-activation vectors
       for (int t = 0; t < p.taps; ++t) {
         const long long row0 = (long long)m0 + p.tap_off[t];
         for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
@@ -605,8 +627,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool chok = ch < p.a_cin;
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.pre_scale && chok) {
-            sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + ch));
-            sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + ch));
+            sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + gc + ch));
+            sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + gc + ch));
           }
           const uint32_t st = smem_s + (uint32_t)(s * S::STAGE_BYTES);
           // phase 1: pull this thread's share of the raw tile (TMA-staged) into registers; phase 2 (after the whole group
@@ -1096,7 +1118,8 @@ static int launch_conv(tiab_ctx* h, const CUtensorMap& ta, const CUtensorMap& ta
     TIAB_CUDA_OK(h, cudaFuncSetAttribute(conv_gemm_kernel<BN, NSEG, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.m_tiles_pg = (p.group_rows + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_tiles = p.groups * p.m_tiles_pg;
   p.num_n_tiles = p.N / BN;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = std::min(tiles, h->sm_count);
@@ -1153,7 +1176,12 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   const int BN = (d->N % 256 == 0) ? 256 : (d->N % 128 == 0) ? 128 : (d->N % 64 == 0) ? 64 : 32;
   CUtensorMap ta, ta2, tb;
-  int rc = make_map_2d(h, &tb, d->w, d->N, (int)kcols, d->w_ld, BN);
+  const int groups = d->groups > 1 ? d->groups : 1;
+  if (groups > 1 && (d->group_rows <= 0 || (long long)d->group_rows * groups != d->M || (d->cin & 3))) {
+    h->err = "tiab_conv_gemm: grouped launch needs M == groups * group_rows and cin % 4 == 0";
+    return TIAB_E_INVALID;
+  }
+  int rc = make_map_2d(h, &tb, d->w, (long long)groups * d->N, (int)kcols, d->w_ld, BN);
   if (rc) return rc;
   if (amode) {
     if ((d->cin & 3) || (d->x_lo_off & 7)) {
@@ -1177,6 +1205,7 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.M = d->M;
+  p.groups = groups, p.group_rows = groups > 1 ? d->group_rows : d->M, p.a_grouped = groups > 1 ? (d->x_grouped != 0) : 1;
   p.N = d->N;
   p.taps = d->taps;
   p.kchunks = kchunks;

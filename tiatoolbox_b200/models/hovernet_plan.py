@@ -58,61 +58,72 @@ class HoVerNetPlan(Plan):
         crop0, crop1 = (184, 72) if mode == "original" else (92, 36)
         h = k // 2
         branches = (["tp"] if num_types is not None else []) + ["np", "hv"]
-        # scratch shared by the branches (they run back to back on one stream)
-        cb3 = self.act("cb3", (B, G3, G3), 512)
-        t3 = self.act("t3", (B, G3, G3), 128)
-        u3out = self.act("u3out", (B, G3, G3), 512)
+        # The branches have identical shapes, so every decoder layer is ONE grouped launch over R*B images (group r = branch
+        # r with its own weight rows): three times the tiles per launch, a third of the launches.
+        R = len(branches)
+        BR = B * R
+        pre = [f"decoder.{b}" for b in branches]
+        cb3 = self.act("cb3", (BR, G3, G3), 512)
+        t3 = self.act("t3", (BR, G3, G3), 128)
+        u3out = self.act("u3out", (BR, G3, G3), 512)
         lo3 = h * 9                      # conva + 8 dense units
         W3 = G3 - 2 * lo3                # valid width of u3's output
         G2 = 2 * W3
         assert G2 == H1 - crop1, (G2, H1, crop1)
-        u2in = self.act("u2in", (B, G2, G2), 512)
-        cb2 = self.act("cb2", (B, G2, G2), 256)
-        t2 = self.act("t2d", (B, G2, G2), 128)
-        u2out = self.act("u2out", (B, G2, G2), 256)
+        u2in = self.act("u2in", (BR, G2, G2), 512)
+        cb2 = self.act("cb2", (BR, G2, G2), 256)
+        t2 = self.act("t2d", (BR, G2, G2), 128)
+        u2out = self.act("u2out", (BR, G2, G2), 256)
         lo2 = h * 5
         W2 = G2 - 2 * lo2
         So = 2 * W2
         assert So == H0 - crop0, (So, H0, crop0)
         pu = tf_same_pad(So, k, 1)
         G1 = So + pu[0] + pu[1]
-        u1in = self.act("u1in_padded", (B, G1, G1), 256)
-        u1 = self.act("u1", (B, So, So), 64)
+        u1in = self.act("u1in_padded", (BR, G1, G1), 256)
+        u1 = self.act("u1", (BR, So, So), 64)
         self.So = So
+
+        def bn_cat(names):
+            st = [bn_scale_shift(sd, n) for n in names]
+            return self.const(torch.cat([a for a, _ in st])), self.const(torch.cat([b_ for _, b_ in st]))
+
+        # u3: conva reads the shared u3in, each branch writes its own block of cb3
+        self.conv(x=u3in, grid=(G3, G3), cin=1024, w=self.weight_groups([sd[f"{p}.u3.conva.weight"] for p in pre]), k=k, centered=True,
+                  N=256, window=(h, G3 - h, h, G3 - h), out16=cb3, coff16=0, nimg=BR, groups=R, x_grouped=False)
+        self._dense(sd, [f"{p}.u3.dense" for p in pre], 8, cb3, t3, G3, 256, k, h)
+        sc, sh = bn_cat([f"{p}.u3.dense.blk_bna.bn" for p in pre])
+        self.conv(x=cb3, grid=(G3, G3), cin=512, w=self.weight_groups([sd[f"{p}.u3.convf.weight"] for p in pre]), k=1, centered=False,
+                  N=512, window=(lo3, G3 - lo3, lo3, G3 - lo3), out16=u3out, pre=(sc, sh, True), nimg=BR, groups=R)
+        # u2
+        for r in range(R):
+            self.add(lambda r=r: ops.upsample_add(u3out.images(r * B, B), W3, W3, G3, G3, lo3, lo3, d1, H1, H1, crop1 // 2, crop1 // 2, B,
+                                                  512, None, None, False, u2in.images(r * B, B), G2, G2, 0, 0))
+        self.conv(x=u2in, grid=(G2, G2), cin=512, w=self.weight_groups([sd[f"{p}.u2.conva.weight"] for p in pre]), k=k, centered=True,
+                  N=128, window=(h, G2 - h, h, G2 - h), out16=cb2, coff16=0, nimg=BR, groups=R)
+        self._dense(sd, [f"{p}.u2.dense" for p in pre], 4, cb2, t2, G2, 128, k, h)
+        sc, sh = bn_cat([f"{p}.u2.dense.blk_bna.bn" for p in pre])
+        self.conv(x=cb2, grid=(G2, G2), cin=256, w=self.weight_groups([sd[f"{p}.u2.convf.weight"] for p in pre]), k=1, centered=False,
+                  N=256, window=(lo2, G2 - lo2, lo2, G2 - lo2), out16=u2out, pre=(sc, sh, True), nimg=BR, groups=R)
+        # u1
+        for r in range(R):
+            self.add(lambda r=r: ops.upsample_add(u2out.images(r * B, B), W2, W2, G2, G2, lo2, lo2, d0, H0, H0, crop0 // 2, crop0 // 2, B,
+                                                  256, None, None, False, u1in.images(r * B, B), G1, G1, pu[0], pu[0]))
+        self.conv(x=u1in, grid=(G1, G1), cin=256, w=self.weight_groups([sd[f"{p}.u1.conva.weight"] for p in pre]), k=k, centered=False,
+                  N=64, window=(0, So, 0, So), dst_geom=(So, So, 0, 0), out16=u1, nimg=BR, groups=R)
+        # u0: BN + ReLU + 1x1 (+bias) -> fp32 logits (per branch: the output widths differ)
         logits = {}
-        for b in branches:
-            p = f"decoder.{b}"
+        for r, b in enumerate(branches):
+            p = pre[r]
             out_ch = num_types if b == "tp" else 2
-            # u3
-            self.conv(x=u3in, grid=(G3, G3), cin=1024, w=self.weight(sd[f"{p}.u3.conva.weight"]), k=k, centered=True, N=256,
-                      window=(h, G3 - h, h, G3 - h), out16=cb3, coff16=0)
-            self._dense(sd, f"{p}.u3.dense", 8, cb3, t3, G3, 256, k, h)
-            s, t = bn_scale_shift(sd, f"{p}.u3.dense.blk_bna.bn")
-            self.conv(x=cb3, grid=(G3, G3), cin=512, w=self.weight(sd[f"{p}.u3.convf.weight"]), k=1, centered=False, N=512,
-                      window=(lo3, G3 - lo3, lo3, G3 - lo3), out16=u3out, pre=(self.const(s), self.const(t), True))
-            # u2
-            self.add(lambda: ops.upsample_add(u3out, W3, W3, G3, G3, lo3, lo3, d1, H1, H1, crop1 // 2, crop1 // 2, B, 512, None, None,
-                                              False, u2in, G2, G2, 0, 0))
-            self.conv(x=u2in, grid=(G2, G2), cin=512, w=self.weight(sd[f"{p}.u2.conva.weight"]), k=k, centered=True, N=128,
-                      window=(h, G2 - h, h, G2 - h), out16=cb2, coff16=0)
-            self._dense(sd, f"{p}.u2.dense", 4, cb2, t2, G2, 128, k, h)
-            s, t = bn_scale_shift(sd, f"{p}.u2.dense.blk_bna.bn")
-            self.conv(x=cb2, grid=(G2, G2), cin=256, w=self.weight(sd[f"{p}.u2.convf.weight"]), k=1, centered=False, N=256,
-                      window=(lo2, G2 - lo2, lo2, G2 - lo2), out16=u2out, pre=(self.const(s), self.const(t), True))
-            # u1
-            self.add(lambda: ops.upsample_add(u2out, W2, W2, G2, G2, lo2, lo2, d0, H0, H0, crop0 // 2, crop0 // 2, B, 256, None, None,
-                                              False, u1in, G1, G1, pu[0], pu[0]))
-            self.conv(x=u1in, grid=(G1, G1), cin=256, w=self.weight(sd[f"{p}.u1.conva.weight"]), k=k, centered=False, N=64,
-                      window=(0, So, 0, So), dst_geom=(So, So, 0, 0), out16=u1)
-            # u0: BN + ReLU + 1x1 (+bias) -> fp32 logits
-            s, t = bn_scale_shift(sd, f"{p}.u0.bn")
-            sc, sh = self.const(s), self.const(t)
+            s_, t_ = bn_scale_shift(sd, f"{p}.u0.bn")
+            sc, sh = self.const(s_), self.const(t_)
             wt = self.const(sd[f"{p}.u0.conv.weight"].reshape(out_ch, 64))
             bb = self.const(sd[f"{p}.u0.conv.bias"])
             lg = self.buf(f"logits_{b}", (B, So, So, out_ch), torch.float32)
             logits[b] = lg
-            self.add(lambda sc=sc, sh=sh, wt=wt, bb=bb, lg=lg, out_ch=out_ch: ops.pointwise_head(
-                u1, B * So * So, 64, sc, sh, True, wt, bb, out_ch, lg, out_ch, 0))
+            self.add(lambda sc=sc, sh=sh, wt=wt, bb=bb, lg=lg, out_ch=out_ch, r=r: ops.pointwise_head(
+                u1.images(r * B, B), B * So * So, 64, sc, sh, True, wt, bb, out_ch, lg, out_ch, 0))
             self.flops += 2.0 * B * So * So * 64 * out_ch
         self.logits = logits
         self.np_out = self.buf("np_out", (B, So, So, 1), torch.float32)
@@ -174,23 +185,27 @@ class HoVerNetPlan(Plan):
             cur_in, cur_c, cur_pre = stream, c3, (self.const(sc), self.const(sh), True)
         return out, Ho
 
-    def _dense(self, sd, name, units, cb, t, G, c_in, k, h):
-        """Dense block (hovernet.py:61-149) on one shared grid: unit u reads channels [0, c_in + 32u) of `cb`
-        under its own BN+ReLU and appends 32 raw channels; valid windows shrink by k//2 per unit."""
-        B = self.B
+    def _dense(self, sd, names, units, cb, t, G, c_in, k, h):
+        """Dense blocks (hovernet.py:61-149) of all branches (`names`: one parameter prefix per branch) on one shared grid:
+        unit u reads channels [0, c_in + 32u) of `cb` under its own BN+ReLU and appends 32 raw channels; valid windows
+        shrink by k//2 per unit.  One grouped launch per layer (group = branch)."""
+        R = len(names)
+        BR = self.B * R
         for u in range(units):
-            un = f"{name}.units.{u}"
+            uns = [f"{n}.units.{u}" for n in names]
             c_u = c_in + 32 * u
-            s, sft = bn_scale_shift(sd, f"{un}.preact_bna/bn")
-            w1, b1 = self.fold_bn(sd, f"{un}.conv1", f"{un}.conv1/bn")
-            # the unit's own BN+ReLU over the raw concat channels is applied while staging the GEMM operand
+            st = [bn_scale_shift(sd, f"{un}.preact_bna/bn") for un in uns]
+            sc = self.const(torch.cat([a for a, _ in st]))
+            sh = self.const(torch.cat([b for _, b in st]))
+            w1, b1 = self.fold_bn_groups(sd, [f"{un}.conv1" for un in uns], [f"{un}.conv1/bn" for un in uns])
             lo = h * (u + 2)
-            # only the rows / columns the unit's kxk convolution will read are produced (whole tiles outside are skipped)
+            # the unit's own BN+ReLU over the raw concat channels is applied while staging the GEMM operand; only the rows /
+            # columns the unit's kxk convolution will read are produced (whole tiles outside are skipped)
             self.conv(x=cb, grid=(G, G), cin=c_u, w=w1, k=1, centered=False, N=128, window=(lo - h, G - lo + h, lo - h, G - lo + h),
-                      bias=b1, relu=True, out16=t, pre=(self.const(s), self.const(sft), True))
-            w2 = self.weight(sd[f"{un}.conv2.weight"], groups=4)
+                      bias=b1, relu=True, out16=t, pre=(sc, sh, True), nimg=BR, groups=R)
+            w2 = self.weight_groups([sd[f"{un}.conv2.weight"] for un in uns], groups=4)
             self.conv(x=t, grid=(G, G), cin=128, w=w2, k=k, centered=True, N=32, window=(lo, G - lo, lo, G - lo),
-                      out16=cb, coff16=c_u)
+                      out16=cb, coff16=c_u, nimg=BR, groups=R)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x_u8: torch.Tensor):

@@ -39,6 +39,10 @@ class Act:
     def hi(self) -> torch.Tensor:
         return self.t[..., : self.C]
 
+    def images(self, i0: int, n: int) -> "Act":
+        """Images [i0, i0 + n) of the leading (batch) dimension."""
+        return Act(self.t[i0:i0 + n], self.C, self.ld, self.lo)
+
     def slice(self, c0: int, C: int) -> "Act":
         """Channels [c0, c0 + C) of every plane as an Act of its own (same pitch and lo offset, shifted base pointer)."""
         assert c0 % 8 == 0 and c0 + C <= self.C
@@ -60,12 +64,16 @@ class ConvOp:
                  dst_geom: tuple[int, int, int, int], x_lo_off: int = 0, out16=None, ld16=0, coff16=0, lo16=0, out32=None,
                  ld32=0, coff32=0, out16b=None, ld16b=0, coff16b=0, lo16b=0, scale2=None, shift2=None, bias=None,
                  res32=None, res16=None, ldres=0, coffres=0, reslo=0, res_geom=(1, 1, 0, 0), relu=False, pre_scale=None,
-                 pre_shift=None, pre_relu=False, x_is_f32=False, split=False):
+                 pre_shift=None, pre_relu=False, x_is_f32=False, split=False, groups: int = 1, group_rows: int = 0,
+                 x_grouped: bool = True):
         d = _lib.ConvDesc()
         d.x, d.x_rows, d.x_ld, d.cin, d.x_lo_off = x.data_ptr(), x_rows, x_ld, cin, x_lo_off
         assert w.dtype == torch.float16 and w.dim() == 2 and w.is_contiguous()
         d.w, d.w_ld = w.data_ptr(), w.shape[1]
-        assert w.shape[0] == N and len(taps) <= _lib.MAX_TAPS
+        assert w.shape[0] == max(groups, 1) * N and len(taps) <= _lib.MAX_TAPS
+        if groups > 1:
+            assert group_rows * groups == M, (groups, group_rows, M)
+            d.groups, d.group_rows, d.x_grouped = groups, group_rows, int(bool(x_grouped))
         transform = pre_scale is not None or x_is_f32
         nseg = 3 if (split if transform else x_lo_off) else 1
         assert w.shape[1] >= len(taps) * (2 if nseg == 3 else 1) * ((cin + 63) // 64) * 64, (w.shape, len(taps), nseg, cin)

@@ -142,21 +142,34 @@ class Plan:
                 kw["pre_scale"], kw["pre_shift"], kw["pre_relu"] = pre
         return kw
 
-    def conv(self, *, x, grid, cin: int, w: torch.Tensor, k: int, centered: bool, N: int, window, dst_geom=None, pre=None, **kw) -> ops.ConvOp:
-        """Shifted-GEMM conv over the (H, W) grid of the NHWC activation `x` (batch = self.B)."""
+    def conv(self, *, x, grid, cin: int, w: torch.Tensor, k: int, centered: bool, N: int, window, dst_geom=None, pre=None, nimg=None,
+             groups: int = 1, x_grouped: bool = True, **kw) -> ops.ConvOp:
+        """Shifted-GEMM conv over the (H, W) grid of the NHWC activation `x` (nimg images, default the plan's batch).
+        groups > 1: the images are `groups` equal blocks, block g convolved with weight rows [g*N, (g+1)*N) of `w`
+        (x_grouped=False: every block reads the same nimg/groups input images)."""
         H, W = grid
-        M = self.B * H * W
+        nimg = nimg or self.B
+        M = nimg * H * W
         if centered:
             taps = [(kh - k // 2) * W + (kw_ - k // 2) for kh in range(k) for kw_ in range(k)]
         else:
             taps = [kh * W + kw_ for kh in range(k) for kw_ in range(k)]
-        op = ops.ConvOp(x_rows=M, cin=cin, w=w, taps=taps, M=M, N=N, grid=(H, W), window=window,
-                        dst_geom=dst_geom or (H, W, 0, 0), **self._x_kw(x, pre), **self._out_kw(kw))
+        gkw = {"groups": groups, "group_rows": M // groups, "x_grouped": x_grouped} if groups > 1 else {}
+        op = ops.ConvOp(x_rows=M if x_grouped else M // groups, cin=cin, w=w, taps=taps, M=M, N=N, grid=(H, W), window=window,
+                        dst_geom=dst_geom or (H, W, 0, 0), **gkw, **self._x_kw(x, pre), **self._out_kw(kw))
         y0, y1, x0, x1 = window
-        self.flops += 2.0 * self.B * (y1 - y0) * (x1 - x0) * N * (k * k) * cin
+        self.flops += 2.0 * nimg * (y1 - y0) * (x1 - x0) * N * (k * k) * cin
         self.mma_flops += op.mma_flops
         self.ops.append(op)
         return op
+
+    def weight_groups(self, ws, **kw) -> torch.Tensor:
+        """Packed weights of several same-shape convolutions stacked along the output-channel axis (grouped launches)."""
+        return torch.cat([self.weight(w, **kw) for w in ws], dim=0).contiguous()
+
+    def fold_bn_groups(self, sd, conv_names, bn_names):
+        packed, biases = zip(*(self.fold_bn(sd, c, b) for c, b in zip(conv_names, bn_names)))
+        return torch.cat(packed, dim=0).contiguous(), self.const(torch.cat([b.cpu() for b in biases]))
 
     def gemm(self, *, x, rows: int, cin: int, w: torch.Tensor, N: int, pre=None, taps=(0,), **kw) -> ops.ConvOp:
         """Plain [rows, cin] x [N, cin]^T GEMM (1x1 conv on a dense matrix / im2col output)."""
