@@ -408,15 +408,51 @@ __global__ void pp_morph(const uint8_t* __restrict__ src, int H, int W, long lon
 }
 
 // heap slice offsets of the foreground components: one thread per image (components are few)
-__global__ void pp_heap_offsets(const int* __restrict__ roots, const int* __restrict__ ncomp, const int* __restrict__ size, int P, int N,
-                                int* __restrict__ heap_off) {
-  PP_GRID_LOOP(n, N) {
+// Exclusive prefix sum of one int per thread over a PP_THREADS block; *total = block sum.  `sh` holds >= 33 ints.
+__device__ __forceinline__ int block_excl_scan(int v, int* sh, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  __syncthreads();   // sh may still be read by the previous call
+  if (lane == 31) sh[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    sh[lane] = w;   // inclusive warp totals
+  }
+  __syncthreads();
+  *total = sh[(blockDim.x >> 5) - 1];
+  return inc - v + (warp ? sh[warp - 1] : 0);
+}
+
+// heap arena offset of every component = exclusive prefix sum of the component sizes in rank order; one block per image
+__global__ void __launch_bounds__(PP_THREADS) pp_heap_offsets(const int* __restrict__ roots, const int* __restrict__ ncomp,
+                                                              const int* __restrict__ size, int P, int N, int* __restrict__ heap_off) {
+  __shared__ int sh[33];
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
     const long long base = (long long)n * P;
-    int off = 0;
-    for (int c = 0; c < ncomp[n]; ++c) {
-      const int r = roots[base + c];
-      heap_off[base + r] = off;
-      off += size[base + r];
+    const int nc = ncomp[n];
+    int run = 0;
+    for (int c0 = 0; c0 < nc; c0 += blockDim.x) {
+      const int c = c0 + threadIdx.x;
+      int r = -1, v = 0;
+      if (c < nc) {
+        r = roots[base + c];
+        v = size[base + r];
+      }
+      int tot;
+      const int ex = block_excl_scan(v, sh, &tot);
+      if (r >= 0) heap_off[base + r] = run + ex;
+      run += tot;
     }
   }
 }
@@ -530,16 +566,23 @@ __global__ void pp_inst_accum(const int* __restrict__ inst, const float* __restr
     }
   }
 }
-// compact rows in ascending id order: one thread per image
-__global__ void pp_inst_finalize(int N, int maxI, int has_type, const int* __restrict__ iarea, const int* __restrict__ ibox,
-                                 const unsigned long long* __restrict__ isx, const unsigned long long* __restrict__ isy,
-                                 const int* __restrict__ itype, int* __restrict__ count, int* __restrict__ ids, int* __restrict__ box,
-                                 double* __restrict__ centroid, int* __restrict__ type, double* __restrict__ prob) {
-  PP_GRID_LOOP(n, N) {
-    int k = 0;
-    for (int id = 1; id <= maxI; ++id) {
+// compact rows in ascending id order: one block per image, block-wide scan of the "instance exists" flags
+__global__ void __launch_bounds__(PP_THREADS) pp_inst_finalize(int N, int maxI, int has_type, const int* __restrict__ iarea,
+                                                               const int* __restrict__ ibox, const unsigned long long* __restrict__ isx,
+                                                               const unsigned long long* __restrict__ isy, const int* __restrict__ itype,
+                                                               int* __restrict__ count, int* __restrict__ ids, int* __restrict__ box,
+                                                               double* __restrict__ centroid, int* __restrict__ type,
+                                                               double* __restrict__ prob) {
+  __shared__ int sh[33];
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    int run = 0;
+    for (int i0 = 0; i0 < maxI; i0 += blockDim.x) {
+      const int id = i0 + threadIdx.x + 1;
       const long long s = (long long)n * maxI + (id - 1);
-      const int a = iarea[s];
+      const int a = id <= maxI ? iarea[s] : 0;
+      int tot;
+      const int k = run + block_excl_scan(a > 0 ? 1 : 0, sh, &tot);
+      run += tot;
       if (a <= 0) continue;
       const long long o = (long long)n * maxI + k;
       ids[o] = id;
@@ -568,9 +611,8 @@ __global__ void pp_inst_finalize(int N, int maxI, int has_type, const int* __res
         type[o] = -1;
         prob[o] = 0.0;
       }
-      ++k;
     }
-    count[n] = k;
+    if (threadIdx.x == 0) count[n] = run;
   }
 }
 
@@ -734,7 +776,7 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
   PP_LAUNCH(h, pp_keep_large, g, PP_THREADS, lab2, size2, w.cid, P, T, 9, (uint8_t*)nullptr, w.marker);
   // 7. watershed (hovernet.py:616)
   TIAB_CUDA_OK(h, cudaMemsetAsync(inst_map, 0, (size_t)T * 4, s));
-  PP_LAUNCH(h, pp_heap_offsets, gN, PP_THREADS, w.roots, w.ncomp, w.size, P, N, w.heap_off);
+  PP_LAUNCH(h, pp_heap_offsets, N, PP_THREADS, w.roots, w.ncomp, w.size, P, N, w.heap_off);
   {
     // one thread per possible component rank (ranks >= ncomp[n] and removed small components exit immediately)
     const int mc = P;
@@ -747,7 +789,7 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
     const int gi = (int)std::min<long long>((TI + PP_THREADS - 1) / PP_THREADS, (long long)h->sm_count * 32);
     PP_LAUNCH(h, pp_inst_init, gi, PP_THREADS, TI, w.iarea, w.ibox, w.isx, w.isy, w.itype);
     PP_LAUNCH(h, pp_inst_accum, g, PP_THREADS, inst_map, tp_map, H, W, T, max_inst, w.iarea, w.ibox, w.isx, w.isy, w.itype);
-    PP_LAUNCH(h, pp_inst_finalize, gN, PP_THREADS, N, max_inst, tp_map ? 1 : 0, w.iarea, w.ibox, w.isx, w.isy, w.itype, inst_count, inst_id,
+    PP_LAUNCH(h, pp_inst_finalize, N, PP_THREADS, N, max_inst, tp_map ? 1 : 0, w.iarea, w.ibox, w.isx, w.isy, w.itype, inst_count, inst_id,
               inst_box, inst_centroid, inst_type, inst_prob);
   }
   return TIAB_OK;
