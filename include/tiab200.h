@@ -148,6 +148,12 @@ typedef struct {
    * bias / scale2 / shift2 + g*N and pre_scale / pre_shift + g*cin.  x_grouped == 0: every group reads the same input rows
    * [0, group_rows) of x (a shared input); != 0: x holds groups*group_rows rows.  groups <= 1: plain launch. */
   int groups, group_rows, x_grouped;
+  /* Strided convolutions without im2col.  The producer of the input stores it space-to-depth (s2d_c > 0 on ITS descriptor:
+   * out16 pixel (y+dy, x+dx) goes to cell ((y+dy)/2, (x+dx)/2) of the Hd x Wd destination grid, channel block
+   * ((y+dy)%2*2 + (x+dx)%2) * s2d_c); a stride-2 KxK convolution is then a stride-1 shifted GEMM over the cell grid whose tap
+   * (kh, kw) has row offset (kh/2)*Wd + kw/2 and reads the channel block tap_coff[t] = ((kh%2)*2 + kw%2) * C of each row. */
+  int tap_coff[TIAB_MAX_TAPS];
+  int s2d_c;
 } tiab_conv_desc_t;
 
 int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);

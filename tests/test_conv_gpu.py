@@ -287,3 +287,39 @@ def test_grouped_launch(ops, mode):
         assert err < 2e-3 * max(1.0, ref.abs().max().item()), (r, err)
     if k == 3:
         assert (got[:, :, 0] == -7.0).all() and (got[:, :, :, 0] == -7.0).all()
+
+
+@pytest.mark.parametrize("hw", [12, 11])
+def test_stride2_conv_via_space_to_depth(ops, hw):
+    """1x1 producer storing space-to-depth + 3x3 stride-2 consumer with per-tap channel offsets == TF-'same' stride-2 conv."""
+    import torch
+    import torch.nn.functional as F
+
+    torch.manual_seed(7)
+    dev = torch.device("cuda")
+    nimg, H, cin, c1, cout = 2, hw, 64, 64, 64
+    Ho = (H + 1) // 2
+    pad_total = max((Ho - 1) * 2 + 3 - H, 0)
+    pb, pe = pad_total // 2, pad_total - pad_total // 2
+    Hs = Ho + 1
+    x = torch.randn(nimg, H, H, cin, device=dev).half()
+    w1 = torch.randn(c1, cin, 1, 1, device=dev) / cin**0.5
+    w2 = torch.randn(cout, c1, 3, 3, device=dev) / (9 * c1) ** 0.5
+    t1s = torch.zeros(nimg, Hs, Hs, 4 * c1, dtype=torch.float16, device=dev)
+    M1 = nimg * H * H
+    op1 = ops.ConvOp(x=x, x_rows=M1, x_ld=cin, cin=cin, w=_pack_w(w1, cin), taps=[0], M=M1, N=c1, grid=(H, H), window=(0, H, 0, H),
+                     dst_geom=(Hs, Hs, pb, pb), out16=t1s, ld16=4 * c1, s2d_c=c1, relu=True)
+    op1()
+    taps = [(kh // 2) * Hs + (kw // 2) for kh in range(3) for kw in range(3)]
+    coff = [((kh % 2) * 2 + (kw % 2)) * c1 for kh in range(3) for kw in range(3)]
+    M2 = nimg * Hs * Hs
+    out32 = torch.full((nimg, Ho, Ho, cout), -3.0, device=dev)
+    op2 = ops.ConvOp(x=t1s, x_rows=M2, x_ld=4 * c1, cin=c1, w=_pack_w(w2, c1), taps=taps, tap_coff=coff, M=M2, N=cout, grid=(Hs, Hs),
+                     window=(0, Ho, 0, Ho), dst_geom=(Ho, Ho, 0, 0), out32=out32, ld32=cout)
+    op2()
+    torch.cuda.synchronize()
+    t1 = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w1.half().float())).half().float()
+    ref = F.conv2d(F.pad(t1, (pb, pe, pb, pe)), w2.half().float(), stride=2).permute(0, 2, 3, 1)
+    assert ref.shape == out32.shape
+    err = (out32 - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err

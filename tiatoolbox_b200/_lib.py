@@ -51,6 +51,7 @@ class ConvDesc(C.Structure):
         ("relu", C.c_int),
         ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p), ("pre_relu", C.c_int), ("x_is_f32", C.c_int), ("split", C.c_int),
         ("groups", C.c_int), ("group_rows", C.c_int), ("x_grouped", C.c_int),
+        ("tap_coff", C.c_int * MAX_TAPS), ("s2d_c", C.c_int),
     ]
 
 

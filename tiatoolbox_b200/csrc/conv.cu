@@ -47,6 +47,8 @@ struct ConvParams {
   int M, N;
   int taps, kchunks;
   int tap_off[TIAB_MAX_TAPS];
+  int tap_coff[TIAB_MAX_TAPS];   // channel offset of each tap's operand inside the x rows (space-to-depth inputs), else 0
+  int s2d_c;                     // > 0: out16 is stored space-to-depth (see tiab_conv_desc_t.s2d_c)
   int Hin, Win;           // virtual grid (rows per image = Hin*Win)
   int y0, y1, x0, x1;     // valid output window on the grid
   int Hd, Wd, dy, dx;     // destination row = (img*Hd + y + dy)*Wd + x + dx
@@ -252,7 +254,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t stg_
     x.x = fmaxf(x.x, floor_), x.y = fmaxf(x.y, floor_), x.z = fmaxf(x.z, floor_), x.w = fmaxf(x.w, floor_);   // ReLU or no-op (-inf)
     if (o32) *reinterpret_cast<float4*>(p.out32 + (long long)drow[i] * p.ld32 + p.coff32 + n) = x;
     if (o16) {
-      __half* op = p.out16 + (long long)drow[i] * p.ld16 + p.coff16 + n;
+      __half* op = p.out16 + (long long)(drow[i] & 0x0FFFFFFF) * p.ld16 + p.coff16 + (drow[i] >> 28) * p.s2d_c + n;
       const uint32_t h01 = pack_h2(x.x, x.y), h23 = pack_h2(x.z, x.w);
       *reinterpret_cast<uint2*>(op) = make_uint2(h01, h23);
       if (lo_a) {
@@ -389,6 +391,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) {
         for (int t = 0; t < p.taps; ++t) {
           const int row = m0 + p.tap_off[t];
+          const int cbase = p.tap_coff[t];
           // weights of tap t: NSEG == 3 -> [W_hi | W_lo], each kchunks*64 columns
           const int wbase = t * S::NPLANES * p.kchunks;
           for (int kc = 0; kc < p.kchunks; ++kc, ++iter) {
@@ -399,13 +402,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               // raw tile -> A area (rows / channels outside the tensor are zero filled), signalled on its own barrier
               const bool two = !p.a_is_f32 && p.a_lo;
               mbarrier_expect_tx(rb, (p.a_is_f32 || two) ? 2 * S::A_BYTES : S::A_BYTES);
-              tma_load_2d(st, &tmA, kc * BLOCK_K, row, rb);
-              if (two) tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, rb);
+              tma_load_2d(st, &tmA, cbase + kc * BLOCK_K, row, rb);
+              if (two) tma_load_2d(st + S::A_BYTES, &tmA2, cbase + kc * BLOCK_K, row, rb);
               mbarrier_expect_tx(&full_bar[s], S::NPLANES * S::B_BYTES);
             } else {
               mbarrier_expect_tx(&full_bar[s], S::STAGE_BYTES);
-              tma_load_2d(st, &tmA, kc * BLOCK_K, row, &full_bar[s]);
-              if (NSEG == 3) tma_load_2d(st + S::A_BYTES, &tmA2, kc * BLOCK_K, row, &full_bar[s]);
+              tma_load_2d(st, &tmA, cbase + kc * BLOCK_K, row, &full_bar[s]);
+              if (NSEG == 3) tma_load_2d(st + S::A_BYTES, &tmA2, cbase + kc * BLOCK_K, row, &full_bar[s]);
             }
             tma_load_2d(st + S::A_AREA, &tmB, (wbase + kc) * BLOCK_K, n0, &full_bar[s]);
             if (NSEG == 3) tma_load_2d(st + S::A_AREA + S::B_BYTES, &tmB, (wbase + p.kchunks + kc) * BLOCK_K, n0, &full_bar[s]);
@@ -507,7 +510,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int y = rem / p.Win;
         const int x = rem - y * p.Win;
         valid_l = row < mend && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
-        drow_l = (img * p.Hd + (y + p.dy)) * p.Wd + (x + p.dx);
+        if (p.s2d_c) {   // space-to-depth store: cell (yy/2, xx/2), phase (yy%2, xx%2) carried in the top bits of the row index
+          const int yy = y + p.dy, xx = x + p.dx;
+          drow_l = ((img * p.Hd + (yy >> 1)) * p.Wd + (xx >> 1)) | ((((yy & 1) << 1) | (xx & 1)) << 28);
+        } else {
+          drow_l = (img * p.Hd + (y + p.dy)) * p.Wd + (x + p.dx);
+        }
         rrow_l = (img * p.Hr + (y + p.ry)) * p.Wr + (x + p.rx);
       }
       int drow[8], rrow[8];
@@ -1176,6 +1184,18 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   TIAB_CUDA_OK(h, cudaSetDevice(h->device));
   const int BN = (d->N % 256 == 0) ? 256 : (d->N % 128 == 0) ? 128 : (d->N % 64 == 0) ? 64 : 32;
   CUtensorMap ta, ta2, tb;
+  int xcols = d->cin;   // extent of the operand map along the channels (taps may address different channel blocks of a row)
+  for (int t = 0; t < d->taps; ++t) {
+    if (d->tap_coff[t] < 0 || (d->tap_coff[t] & 7) || (d->tap_coff[t] && (d->cin % BLOCK_K))) {
+      h->err = "tiab_conv_gemm: tap_coff must be >= 0, a multiple of 8, and needs cin % 64 == 0";
+      return TIAB_E_INVALID;
+    }
+    xcols = std::max(xcols, d->tap_coff[t] + d->cin);
+  }
+  if (d->s2d_c && (!d->out16 || d->out32 || d->out16b || (d->s2d_c & 3))) {
+    h->err = "tiab_conv_gemm: space-to-depth store is for out16 only";
+    return TIAB_E_INVALID;
+  }
   const int groups = d->groups > 1 ? d->groups : 1;
   if (groups > 1 && (d->group_rows <= 0 || (long long)d->group_rows * groups != d->M || (d->cin & 3))) {
     h->err = "tiab_conv_gemm: grouped launch needs M == groups * group_rows and cin % 4 == 0";
@@ -1189,17 +1209,17 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
       return TIAB_E_INVALID;
     }
     // raw tiles for the transform warps; the map's inner extent is the logical cin, so the K padding reads as zeros
-    rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M, d->x_is_f32 ? 2 : 1);
+    rc = make_map_2d(h, &ta, d->x, d->x_rows, xcols, d->x_ld, BLOCK_M, d->x_is_f32 ? 2 : 1);
     if (rc) return rc;
     ta2 = ta;
     if (!d->x_is_f32 && d->x_lo_off) {
-      rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, d->cin, d->x_ld, BLOCK_M, 1);
+      rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, xcols, d->x_ld, BLOCK_M, 1);
       if (rc) return rc;
     }
   } else {
-    rc = make_map_2d(h, &ta, d->x, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+    rc = make_map_2d(h, &ta, d->x, d->x_rows, xcols, d->x_ld, BLOCK_M);
     if (rc) return rc;
-    rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, d->cin, d->x_ld, BLOCK_M);
+    rc = make_map_2d(h, &ta2, (const __half*)d->x + d->x_lo_off, d->x_rows, xcols, d->x_ld, BLOCK_M);
     if (rc) return rc;
   }
   ConvParams p;
@@ -1212,7 +1232,8 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   p.nseg = nseg;
   p.a_src = d->x, p.a_rows = d->x_rows, p.a_ld = (int)d->x_ld, p.a_lo = d->x_lo_off, p.a_is_f32 = d->x_is_f32, p.a_cin = d->cin;
   p.pre_scale = (const float*)d->pre_scale, p.pre_shift = (const float*)d->pre_shift, p.pre_relu = d->pre_relu;
-  for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t];
+  for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t], p.tap_coff[t] = d->tap_coff[t];
+  p.s2d_c = d->s2d_c;
   p.Hin = d->Hin, p.Win = d->Win;
   p.skip = (d->y0 > 0 || d->y1 < d->Hin) ? 1 : 0;
   {

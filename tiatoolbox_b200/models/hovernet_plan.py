@@ -164,13 +164,15 @@ class HoVerNetPlan(Plan):
                 self.conv(x=ppad, grid=(Hi + 2, Hi + 2), cin=c1, w=w2, k=3, centered=False, N=c2, window=(0, Hi, 0, Hi),
                           dst_geom=(Hi, Hi, 0, 0), bias=b2, relu=True, out16=t2)
             else:
-                w2, b2 = self.fold_bn(sd, f"{u}.conv2", f"{u}.conv2/bn", im2col=True)
-                t1 = self.act(f"{name}.t1_full", (B, H, H), c1)
-                self.gemm(x=cur_in, rows=B * H * H, cin=cur_c, w=w1, N=c1, bias=b1, relu=True, out16=t1, pre=cur_pre)
+                # strided unit: conv1 stores its output space-to-depth (TF-same padding offset included), so the stride-2 3x3 is a
+                # stride-1 shifted GEMM over the cell grid -- no im2col
+                w2, b2 = self.fold_bn(sd, f"{u}.conv2", f"{u}.conv2/bn")
                 pb, _ = tf_same_pad(H, 3, s)
-                i2 = self.act(f"{name}.im2col", (B * Ho * Ho,), 9 * c1)
-                self.im2col(t1.t, False, 1.0, t1.lo, B, H, H, c1, t1.ld, 3, s, pb, Ho, i2, 9 * c1)
-                self.gemm(x=i2, rows=B * Ho * Ho, cin=9 * c1, w=w2, N=c2, bias=b2, relu=True, out16=t2)
+                Hs = Ho + 1
+                t1s = self.act(f"{name}.t1_s2d", (B, Hs, Hs), 4 * c1)
+                self.conv(x=cur_in, grid=(H, H), cin=cur_c, w=w1, k=1, centered=False, N=c1, window=(0, H, 0, H),
+                          dst_geom=(Hs, Hs, pb, pb), bias=b1, relu=True, out16=t1s, s2d_c=c1, pre=cur_pre)
+                self.conv_s2d(x=t1s, grid=(Hs, Hs), cin=c1, w=w2, k=3, N=c2, out_hw=(Ho, Ho), bias=b2, relu=True, out16=t2)
             last = i == units - 1
             bn_next = f"{name}.blk_bna.bn" if last else f"{name}.units.{i + 1}.preact/bn"
             sc, sh = bn_scale_shift(sd, bn_next)

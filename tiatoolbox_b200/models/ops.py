@@ -65,7 +65,7 @@ class ConvOp:
                  ld32=0, coff32=0, out16b=None, ld16b=0, coff16b=0, lo16b=0, scale2=None, shift2=None, bias=None,
                  res32=None, res16=None, ldres=0, coffres=0, reslo=0, res_geom=(1, 1, 0, 0), relu=False, pre_scale=None,
                  pre_shift=None, pre_relu=False, x_is_f32=False, split=False, groups: int = 1, group_rows: int = 0,
-                 x_grouped: bool = True):
+                 x_grouped: bool = True, tap_coff: list[int] | None = None, s2d_c: int = 0):
         d = _lib.ConvDesc()
         d.x, d.x_rows, d.x_ld, d.cin, d.x_lo_off = x.data_ptr(), x_rows, x_ld, cin, x_lo_off
         assert w.dtype == torch.float16 and w.dim() == 2 and w.is_contiguous()
@@ -83,6 +83,8 @@ class ConvOp:
         d.M, d.N, d.taps = M, N, len(taps)
         for i, t in enumerate(taps):
             d.tap_off[i] = int(t)
+            d.tap_coff[i] = int(tap_coff[i]) if tap_coff else 0
+        d.s2d_c = int(s2d_c)
         d.Hin, d.Win = grid
         d.y0, d.y1, d.x0, d.x1 = window
         d.Hd, d.Wd, d.dy, d.dx = dst_geom

@@ -163,6 +163,23 @@ class Plan:
         self.ops.append(op)
         return op
 
+    def conv_s2d(self, *, x: Act, grid, cin: int, w: torch.Tensor, k: int, N: int, out_hw, **kw) -> ops.ConvOp:
+        """Stride-2 kxk convolution without im2col: `x` is the space-to-depth form of the (padded) input (cells grid = (Hs, Ws),
+        4*cin channels per plane, written by the producing conv with `s2d_c=cin`), so input pixel (2*yo + kh, 2*xo + kw) is
+        cell (yo + kh//2, xo + kw//2), channel block (kh%2)*2 + kw%2 -- a stride-1 shifted GEMM whose taps carry a channel offset."""
+        Hs, Ws = grid
+        Ho, Wo = out_hw
+        assert x.C == 4 * cin and Hs >= Ho + (k - 1) // 2 and Ws >= Wo + (k - 1) // 2
+        taps = [(kh // 2) * Ws + (kw_ // 2) for kh in range(k) for kw_ in range(k)]
+        coff = [((kh % 2) * 2 + (kw_ % 2)) * cin for kh in range(k) for kw_ in range(k)]
+        M = self.B * Hs * Ws
+        op = ops.ConvOp(x=x.t, x_rows=M, x_ld=x.ld, x_lo_off=x.lo, cin=cin, w=w, taps=taps, tap_coff=coff, M=M, N=N, grid=(Hs, Ws),
+                        window=(0, Ho, 0, Wo), dst_geom=(Ho, Wo, 0, 0), **self._out_kw(kw))
+        self.flops += 2.0 * self.B * Ho * Wo * N * (k * k) * cin
+        self.mma_flops += op.mma_flops
+        self.ops.append(op)
+        return op
+
     def weight_groups(self, ws, **kw) -> torch.Tensor:
         """Packed weights of several same-shape convolutions stacked along the output-channel axis (grouped launches)."""
         return torch.cat([self.weight(w, **kw) for w in ws], dim=0).contiguous()
