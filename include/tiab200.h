@@ -154,6 +154,17 @@ typedef struct {
    * (kh, kw) has row offset (kh/2)*Wd + kw/2 and reads the channel block tap_coff[t] = ((kh%2)*2 + kw%2) * C of each row. */
   int tap_coff[TIAB_MAX_TAPS];
   int s2d_c;
+  /* Fused pointwise head on a N == 64 convolution (HoVer-Net's u0: BN, ReLU, 1x1 conv + bias, hovernet.py:487-497):
+   *   head_out[g][row, j] = head_b[g][j] + sum_c relu(D[row, c] * head_scale[g][c] + head_shift[g][c]) * head_w[g][j][c],  j < head_nout[g] <= 8
+   * with row counted inside group g's destination grid; the 64-channel tensor itself is never stored.  head_w: fp32 [groups][8][64],
+   * head_b: [groups][8], head_scale / head_shift: [groups][64]. */
+  const void* head_w;
+  const void* head_b;
+  const void* head_scale;
+  const void* head_shift;
+  void* head_out[4];
+  int head_nout[4];
+  int head_ld[4];
 } tiab_conv_desc_t;
 
 int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);

@@ -56,6 +56,5 @@ cmp("hv.u3out", val("u3out", 512), cap["hv.u3out"], (9, 46))
 cmp("hv.u2in", val("u2in", 512), cap["hv.u2in"])
 cmp("hv.u2out", val("u2out", 256), cap["hv.u2out"], (5, 82))
 cmp("hv.u1in", val("u1in_padded", 256), cap["hv.u1in"], (1, 164))
-cmp("hv.u1", val("u1", 64), cap["hv.u1"])
 for b in ("tp", "np", "hv"):
     cmp(f"logits {b}", plan.logits[b], ref[b])

@@ -323,3 +323,38 @@ def test_stride2_conv_via_space_to_depth(ops, hw):
     assert ref.shape == out32.shape
     err = (out32 - ref).abs().max().item()
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_fused_pointwise_head(ops):
+    """3x3 conv (N = 64, two groups) with BN + ReLU + 1x1 conv + bias fused into the epilogue; only the fp32 logits are stored."""
+    import torch
+    import torch.nn.functional as F
+
+    torch.manual_seed(8)
+    dev = torch.device("cuda")
+    R, nimg, H, W, cin = 2, 2, 20, 22, 64
+    nouts = [2, 6]
+    xh = torch.randn(R * nimg, H, W, cin, device=dev).half()
+    w = torch.randn(R, 64, cin, 3, 3, device=dev) / (9 * cin) ** 0.5
+    wp = torch.cat([_pack_w(w[r], cin) for r in range(R)], dim=0).contiguous()
+    hw = torch.zeros(R, 8, 64, device=dev)
+    hb = torch.zeros(R, 8, device=dev)
+    for r, oc in enumerate(nouts):
+        hw[r, :oc] = torch.randn(oc, 64, device=dev) / 8.0
+        hb[r, :oc] = torch.randn(oc, device=dev)
+    hs, ht = torch.rand(R, 64, device=dev) + 0.5, torch.randn(R, 64, device=dev) * 0.2
+    Ho, Wo = H - 2, W - 2
+    outs = [torch.full((nimg, Ho, Wo, oc), -5.0, device=dev) for oc in nouts]
+    taps = [kh * W + kw for kh in range(3) for kw in range(3)]
+    M = R * nimg * H * W
+    op = ops.ConvOp(x=xh, x_rows=M, x_ld=cin, cin=cin, w=wp, taps=taps, M=M, N=64, grid=(H, W), window=(0, Ho, 0, Wo),
+                    dst_geom=(Ho, Wo, 0, 0), groups=R, group_rows=nimg * H * W, head=(hw, hb, hs.contiguous(), ht.contiguous(), outs))
+    op()
+    torch.cuda.synchronize()
+    for r, oc in enumerate(nouts):
+        xr = xh[r * nimg:(r + 1) * nimg].float().permute(0, 3, 1, 2)
+        feat = F.conv2d(xr, w[r].half().float())                                   # valid 3x3
+        act = torch.relu(feat * hs[r].view(1, 64, 1, 1) + ht[r].view(1, 64, 1, 1))
+        ref = (F.conv2d(act, hw[r, :oc].view(oc, 64, 1, 1)) + hb[r, :oc].view(1, oc, 1, 1)).permute(0, 2, 3, 1)
+        err = (outs[r] - ref).abs().max().item()
+        assert err < 2e-3 * max(1.0, ref.abs().max().item()), (r, err)

@@ -52,6 +52,8 @@ class ConvDesc(C.Structure):
         ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p), ("pre_relu", C.c_int), ("x_is_f32", C.c_int), ("split", C.c_int),
         ("groups", C.c_int), ("group_rows", C.c_int), ("x_grouped", C.c_int),
         ("tap_coff", C.c_int * MAX_TAPS), ("s2d_c", C.c_int),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_scale", C.c_void_p), ("head_shift", C.c_void_p),
+        ("head_out", C.c_void_p * 4), ("head_nout", C.c_int * 4), ("head_ld", C.c_int * 4),
     ]
 
 

@@ -83,6 +83,14 @@ struct ConvParams {
   // Tiles never straddle groups (each group has its own ceil(group_rows/128) row tiles).  a_grouped == 0: all groups read
   // the same A rows [0, group_rows) (a shared input tensor).
   int groups, group_rows, a_grouped, m_tiles_pg;
+  // Fused pointwise head (HoVer-Net u0, hovernet.py:487-497): out[j] = b[j] + sum_c relu(acc[c]*scale[c] + shift[c]) * w[j][c] over the
+  // 64 output channels of a BLOCK_N == 64 tile, j < nout <= 8, written as fp32 [rows, head_ld] per group; nothing else is stored.
+  const float* head_w;      // [groups][8][64]
+  const float* head_b;      // [groups][8]
+  const float* head_scale;  // [groups][64]
+  const float* head_shift;  // [groups][64]
+  float* head_out[4];
+  int head_nout[4], head_ld[4];
   int epi_mode;           // specialised epilogue row loop (0 = generic), see tiab_conv_gemm
   int skip;               // 1: the window does not span all grid rows -> tiles with no valid output row are skipped
 };
@@ -565,6 +573,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbarrier_arrive(&tempty_bar[ab]);
           released = true;
         }
+        if (BLOCK_N == 64 && !AMODE && p.head_w != nullptr) {
+          // ---- fused head: this warp holds channels [c0, c0+32) of its 32 rows; the quadrant's other warp holds the rest ----
+          const int nout = p.head_nout[g];
+          const float* hw = p.head_w + g * 8 * 64 + c0;
+          const float* hs = p.head_scale + g * 64 + c0;
+          const float* ht = p.head_shift + g * 64 + c0;
+          float part[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) part[j] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(hs + c)), t4 = __ldg(reinterpret_cast<const float4*>(ht + c));
+            const float a0 = fmaxf(fmaf(__uint_as_float(r[c]), s4.x, t4.x), 0.f), a1 = fmaxf(fmaf(__uint_as_float(r[c + 1]), s4.y, t4.y), 0.f);
+            const float a2 = fmaxf(fmaf(__uint_as_float(r[c + 2]), s4.z, t4.z), 0.f), a3 = fmaxf(fmaf(__uint_as_float(r[c + 3]), s4.w, t4.w), 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nout) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(hw + j * 64 + c));
+                part[j] = fmaf(a0, w4.x, fmaf(a1, w4.y, fmaf(a2, w4.z, fmaf(a3, w4.w, part[j]))));
+              }
+            }
+          }
+          // combine the two column halves through the upper warp's staging tile (32 bytes per row)
+          const uint32_t xch = cvta_smem(smem + S::STG_OFFSET + (4 + quad) * 4096) + lane * 32;
+          if (half == 1) {
+            sts_u4(xch, __float_as_uint(part[0]), __float_as_uint(part[1]), __float_as_uint(part[2]), __float_as_uint(part[3]));
+            sts_u4(xch + 16, __float_as_uint(part[4]), __float_as_uint(part[5]), __float_as_uint(part[6]), __float_as_uint(part[7]));
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+          if (half == 0) {
+            const float4 q0 = lds_f4(xch), q1 = lds_f4(xch + 16);
+            const float other[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            if (valid_l) {
+              const long long lrow = (long long)drow_l - (long long)g * (p.group_rows / grid_px) * p.Hd * p.Wd;   // row inside this group's output
+              float* op = p.head_out[g] + lrow * p.head_ld[g];
+              const float* hb = p.head_b + g * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nout) op[j] = part[j] + other[j] + __ldg(hb + j);
+            }
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");   // the exchange slots are rewritten by the next tile
+          continue;
+        }
         // transpose through the staging tile: 16-byte group g of row `lane` lives at lane*128 + ((g ^ (lane & 7)) << 4)
 #pragma unroll
         for (int g = 0; g < 8; ++g) sts_u4(stg_s + lane * 128 + ((g ^ (lane & 7)) << 4), r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
@@ -633,7 +685,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const int ch = kc * BLOCK_K + c4;
           const bool chok = ch < p.a_cin;
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          // channels beyond cin (K padding; TMA zero-fills them) get scale = shift = 0 -> operand 0, without a divergent path
+          float4 sc = chok ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.pre_scale && chok) {
             sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + gc + ch));
             sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + gc + ch));
@@ -661,7 +714,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // rows [r_lo, r_hi) of this tile exist in the source tensor (all of them except at its two ends)
           const long long lo64 = -row0, hi64 = p.a_rows - row0;
           const int r_lo = lo64 > 0 ? (int)(lo64 < BLOCK_M ? lo64 : BLOCK_M) : 0;
-          const int r_hi = !chok ? 0 : (hi64 >= BLOCK_M ? BLOCK_M : (hi64 > 0 ? (int)hi64 : 0));
+          const int r_hi = hi64 >= BLOCK_M ? BLOCK_M : (hi64 > 0 ? (int)hi64 : 0);
           // SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 128-byte row
           const uint32_t dst = st + (uint32_t)(rsub * 128 + (((c4 >> 3) ^ rsub) << 4) + (c4 & 7) * 2);
           const bool full = r_lo == 0 && r_hi == BLOCK_M;
@@ -1234,6 +1287,22 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   p.pre_scale = (const float*)d->pre_scale, p.pre_shift = (const float*)d->pre_shift, p.pre_relu = d->pre_relu;
   for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t], p.tap_coff[t] = d->tap_coff[t];
   p.s2d_c = d->s2d_c;
+  if (d->head_w) {
+    if (d->N != 64 || amode || groups > 4 || d->out16 || d->out32 || d->out16b || d->res32 || d->res16 || !d->head_b || !d->head_scale ||
+        !d->head_shift) {
+      h->err = "tiab_conv_gemm: the fused head needs N == 64, a TMA operand, <= 4 groups and no other output";
+      return TIAB_E_INVALID;
+    }
+    p.head_w = (const float*)d->head_w, p.head_b = (const float*)d->head_b;
+    p.head_scale = (const float*)d->head_scale, p.head_shift = (const float*)d->head_shift;
+    for (int g = 0; g < groups; ++g) {
+      if (!d->head_out[g] || d->head_nout[g] < 1 || d->head_nout[g] > 8 || d->head_ld[g] < d->head_nout[g]) {
+        h->err = "tiab_conv_gemm: fused head: 1 <= nout <= 8 and an output per group";
+        return TIAB_E_INVALID;
+      }
+      p.head_out[g] = (float*)d->head_out[g], p.head_nout[g] = d->head_nout[g], p.head_ld[g] = d->head_ld[g];
+    }
+  }
   p.Hin = d->Hin, p.Win = d->Win;
   p.skip = (d->y0 > 0 || d->y1 < d->Hin) ? 1 : 0;
   {

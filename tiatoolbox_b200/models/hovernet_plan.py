@@ -81,7 +81,6 @@ class HoVerNetPlan(Plan):
         pu = tf_same_pad(So, k, 1)
         G1 = So + pu[0] + pu[1]
         u1in = self.act("u1in_padded", (BR, G1, G1), 256)
-        u1 = self.act("u1", (BR, So, So), 64)
         self.So = So
 
         def bn_cat(names):
@@ -109,22 +108,33 @@ class HoVerNetPlan(Plan):
         for r in range(R):
             self.add(lambda r=r: ops.upsample_add(u2out.images(r * B, B), W2, W2, G2, G2, lo2, lo2, d0, H0, H0, crop0 // 2, crop0 // 2, B,
                                                   256, None, None, False, u1in.images(r * B, B), G1, G1, pu[0], pu[0]))
-        self.conv(x=u1in, grid=(G1, G1), cin=256, w=self.weight_groups([sd[f"{p}.u1.conva.weight"] for p in pre]), k=k, centered=False,
-                  N=64, window=(0, So, 0, So), dst_geom=(So, So, 0, 0), out16=u1, nimg=BR, groups=R)
-        # u0: BN + ReLU + 1x1 (+bias) -> fp32 logits (per branch: the output widths differ)
-        logits = {}
-        for r, b in enumerate(branches):
-            p = pre[r]
-            out_ch = num_types if b == "tp" else 2
-            s_, t_ = bn_scale_shift(sd, f"{p}.u0.bn")
-            sc, sh = self.const(s_), self.const(t_)
-            wt = self.const(sd[f"{p}.u0.conv.weight"].reshape(out_ch, 64))
-            bb = self.const(sd[f"{p}.u0.conv.bias"])
-            lg = self.buf(f"logits_{b}", (B, So, So, out_ch), torch.float32)
-            logits[b] = lg
-            self.add(lambda sc=sc, sh=sh, wt=wt, bb=bb, lg=lg, out_ch=out_ch, r=r: ops.pointwise_head(
-                u1.images(r * B, B), B * So * So, 64, sc, sh, True, wt, bb, out_ch, lg, out_ch, 0))
-            self.flops += 2.0 * B * So * So * 64 * out_ch
+        # u1 conv with u0 (BN + ReLU + 1x1 conv + bias -> fp32 logits) fused into its epilogue: the 64-channel tensor is never stored
+        out_chs = [num_types if b == "tp" else 2 for b in branches]
+        logits = {b: self.buf(f"logits_{b}", (B, So, So, oc), torch.float32) for b, oc in zip(branches, out_chs)}
+        w_u1 = self.weight_groups([sd[f"{p}.u1.conva.weight"] for p in pre])
+        if max(out_chs) <= 8:
+            hw = torch.zeros(R, 8, 64)
+            hb = torch.zeros(R, 8)
+            for r, (p, oc) in enumerate(zip(pre, out_chs)):
+                hw[r, :oc] = sd[f"{p}.u0.conv.weight"].reshape(oc, 64).float()
+                hb[r, :oc] = sd[f"{p}.u0.conv.bias"].float()
+            hs, ht = bn_cat([f"{p}.u0.bn" for p in pre])
+            self.conv(x=u1in, grid=(G1, G1), cin=256, w=w_u1, k=k, centered=False, N=64, window=(0, So, 0, So), dst_geom=(So, So, 0, 0),
+                      nimg=BR, groups=R, head=(self.const(hw), self.const(hb), hs, ht, [logits[b] for b in branches]))
+            for oc in out_chs:
+                self.flops += 2.0 * B * So * So * 64 * oc
+        else:   # more than 8 nucleus types: separate head kernels
+            u1 = self.act("u1", (BR, So, So), 64)
+            self.conv(x=u1in, grid=(G1, G1), cin=256, w=w_u1, k=k, centered=False, N=64, window=(0, So, 0, So), dst_geom=(So, So, 0, 0),
+                      out16=u1, nimg=BR, groups=R)
+            for r, (b, p, oc) in enumerate(zip(branches, pre, out_chs)):
+                s_, t_ = bn_scale_shift(sd, f"{p}.u0.bn")
+                sc, sh = self.const(s_), self.const(t_)
+                wt = self.const(sd[f"{p}.u0.conv.weight"].reshape(oc, 64))
+                bb = self.const(sd[f"{p}.u0.conv.bias"])
+                self.add(lambda sc=sc, sh=sh, wt=wt, bb=bb, lg=logits[b], oc=oc, r=r: ops.pointwise_head(
+                    u1.images(r * B, B), B * So * So, 64, sc, sh, True, wt, bb, oc, lg, oc, 0))
+                self.flops += 2.0 * B * So * So * 64 * oc
         self.logits = logits
         self.np_out = self.buf("np_out", (B, So, So, 1), torch.float32)
         self.hv_out = self.buf("hv_out", (B, So, So, 2), torch.float32)

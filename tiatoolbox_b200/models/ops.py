@@ -65,7 +65,9 @@ class ConvOp:
                  ld32=0, coff32=0, out16b=None, ld16b=0, coff16b=0, lo16b=0, scale2=None, shift2=None, bias=None,
                  res32=None, res16=None, ldres=0, coffres=0, reslo=0, res_geom=(1, 1, 0, 0), relu=False, pre_scale=None,
                  pre_shift=None, pre_relu=False, x_is_f32=False, split=False, groups: int = 1, group_rows: int = 0,
-                 x_grouped: bool = True, tap_coff: list[int] | None = None, s2d_c: int = 0):
+                 x_grouped: bool = True, tap_coff: list[int] | None = None, s2d_c: int = 0, head=None):
+        """`head` = (w [G,8,64] fp32, b [G,8], scale [G,64], shift [G,64], outs: list of fp32 [rows_g, nout_g] tensors): fused
+        BN + ReLU + 1x1 conv (+bias) on the 64 output channels, one output tensor per group."""
         d = _lib.ConvDesc()
         d.x, d.x_rows, d.x_ld, d.cin, d.x_lo_off = x.data_ptr(), x_rows, x_ld, cin, x_lo_off
         assert w.dtype == torch.float16 and w.dim() == 2 and w.is_contiguous()
@@ -85,6 +87,14 @@ class ConvOp:
             d.tap_off[i] = int(t)
             d.tap_coff[i] = int(tap_coff[i]) if tap_coff else 0
         d.s2d_c = int(s2d_c)
+        if head is not None:
+            hw, hb, hs, ht, outs = head
+            assert N == 64 and hw.dtype == torch.float32 and hw.shape == (max(groups, 1), 8, 64) and len(outs) == max(groups, 1)
+            d.head_w, d.head_b, d.head_scale, d.head_shift = hw.data_ptr(), hb.data_ptr(), hs.data_ptr(), ht.data_ptr()
+            for i, o in enumerate(outs):
+                assert o.dtype == torch.float32 and o.is_contiguous() and o.shape[-1] <= 8
+                d.head_out[i], d.head_nout[i], d.head_ld[i] = o.data_ptr(), o.shape[-1], o.shape[-1]
+            self._head_keep = (hw, hb, hs, ht, outs)
         d.Hin, d.Win = grid
         d.y0, d.y1, d.x0, d.x1 = window
         d.Hd, d.Wd, d.dy, d.dx = dst_geom
