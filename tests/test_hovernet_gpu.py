@@ -120,3 +120,34 @@ def test_single_pass_fp16_mode_shallow_layers(built_lib):
     d0 = plan.bufs["d0.out"].float().cpu().numpy()
     assert rel_l2(x0, cap["x0"].permute(0, 2, 3, 1).cpu().numpy()) <= 2e-3
     assert rel_l2(d0, cap["d0"].permute(0, 2, 3, 1).cpu().numpy()) <= 5e-3
+
+
+def test_original_mode_270_matches_fp32_reference(built_lib):
+    """mode="original" (270x270 input, 5x5 decoder convolutions, 80x80 output): plan vs the fp32 restatement on the same device.
+    BN statistics are calibrated on the fly (no committed fixture for this mode); weights are the seeded ones."""
+    import torch
+
+    from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_spec
+    from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.cuda() for k, v in seeded_state_dict(hovernet_spec(3, 6, "original"), seed=0).items()}
+    x = torch.from_numpy(he_tiles(2, 270, 270, seed=2)).cuda()
+    xf = x.permute(0, 3, 1, 2).float()
+    sd.update(calibrate(sd, lambda s, inp: hovernet_forward_reference(s, inp, "original", 6), xf))
+    plan = HoVerNetPlan({k: v.cpu() for k, v in sd.items()}, batch=2, device="cuda:0", mode="original", num_types=6, precision="fp16x3")
+    plan.forward(x)
+    torch.cuda.synchronize()
+    # float64 reference: cuDNN's fp32 algorithms for 5x5 NCHW convolutions (FFT / Winograd tiling) are themselves only good to ~2e-3
+    with torch.inference_mode():
+        ref = hovernet_forward_reference({k: v.double() for k, v in sd.items()}, xf.double(), "original", 6)
+    for b in ("tp", "np", "hv"):
+        got = plan.logits[b].cpu().numpy()
+        r = ref[b].permute(0, 2, 3, 1).float().cpu().numpy()
+        assert got.shape == r.shape and got.shape[1] == 80
+        e = rel_l2(got, r)
+        print(f"original {b}: rel_l2 {e:.2e}")
+        assert np.isfinite(got).all() and e <= 1e-3, (b, e)

@@ -155,6 +155,9 @@ class HoVerNetPlan(Plan):
         if cat is None:
             cat = self.act(f"{name}.cat", (B, Ho, Ho), c2 + cin)
         t2, sc_in = cat.slice(0, c2), cat.slice(c2, cin)
+        # TMA promotes its L2 fetches to 256 bytes: a 64-channel slice (128 B) of the wider concat row would drag its neighbour along on
+        # every read (ncu: +0.27 GB per conv3 in d0), so the units that do not need the concatenation get a buffer of their own
+        t2_rest = self.act(f"{name}.t2", (B, Ho, Ho), c2) if (c2 * 2 < 256 and units > 1) else t2
         if stride == 1:   # the caller produced x_act straight into the shortcut slice
             assert x_act.t.data_ptr() == sc_in.t.data_ptr() and x_act.ld == sc_in.ld
         else:             # strided 1x1 shortcut: gather the pixels it sees
@@ -172,7 +175,7 @@ class HoVerNetPlan(Plan):
                 self.conv(x=cur_in, grid=(Hi, Hi), cin=cur_c, w=w1, k=1, centered=False, N=c1, window=(0, Hi, 0, Hi),
                           dst_geom=(Hi + 2, Hi + 2, 1, 1), bias=b1, relu=True, out16=ppad, pre=cur_pre)
                 self.conv(x=ppad, grid=(Hi + 2, Hi + 2), cin=c1, w=w2, k=3, centered=False, N=c2, window=(0, Hi, 0, Hi),
-                          dst_geom=(Hi, Hi, 0, 0), bias=b2, relu=True, out16=t2)
+                          dst_geom=(Hi, Hi, 0, 0), bias=b2, relu=True, out16=t2 if i == 0 else t2_rest)
             else:
                 # strided unit: conv1 stores its output space-to-depth (TF-same padding offset included), so the stride-2 3x3 is a
                 # stride-1 shifted GEMM over the cell grid -- no im2col
@@ -189,7 +192,7 @@ class HoVerNetPlan(Plan):
             if i == 0:   # conv3 + shortcut in one GEMM, no residual operand
                 x3, k3, w3, res = cat, c2 + cin, w3sc, {}
             else:
-                x3, k3, w3, res = t2, c2, self.weight(sd[f"{u}.conv3.weight"]), {"res32": stream, "ldres": c3}
+                x3, k3, w3, res = t2_rest, c2, self.weight(sd[f"{u}.conv3.weight"]), {"res32": stream, "ldres": c3}
             if last:   # closing BN+ReLU of the block: the activated tensor is what the next block / the decoder skip consume
                 self.gemm(x=x3, rows=B * Ho * Ho, cin=k3, w=w3, N=c3, out16b=out, scale2=self.const(sc), shift2=self.const(sh), **res)
             else:      # only the fp32 stream is written; the next unit's conv1 applies its pre-activation while loading it

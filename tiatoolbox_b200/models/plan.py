@@ -205,18 +205,22 @@ class Plan:
                 out_hw, N: int, out16: Act, name: str = "stem.im2col") -> None:
         """First convolution straight from the uint8 NHWC batch: im2col (K = k*k*3 padded to 64) + GEMM + BN + ReLU.
 
-        The input scale (1/255) is folded into the weights, so the gathered operand holds the raw byte values, which
-        fp16 represents exactly: it needs no lo plane, and split precision only has to cover the weights --
-        A*W_hi + A*W_lo, run as two zero-offset "taps" over the same rows (2 instead of 3 MMA segments, half the
-        im2col bytes)."""
+        The input scale (1/255) is split into a power of two, applied to the bytes (byte * 2^-8 is exact in fp16, so the
+        gathered operand needs no lo plane), and a factor in [0.7, 1.4] folded into the weights (folding all of 1/255 there
+        would push W_lo = W - fp16(W) below fp16's subnormal range and cost ~8 bits).  Split precision then only has to cover
+        the weights -- A*W_hi + A*W_lo, run as two zero-offset "taps" over the same rows (2 instead of 3 MMA segments, half
+        the im2col bytes)."""
+        import math
+
         H, W = hw
         Ho, Wo = out_hw
         scale, shift = bn_scale_shift(sd, bn_name)
-        w = self.weight(sd[conv_name + ".weight"], scale.double() * float(u8_scale), im2col=True)
+        p2 = 2.0 ** round(math.log2(float(u8_scale)))
+        w = self.weight(sd[conv_name + ".weight"], scale.double() * (float(u8_scale) / p2), im2col=True)
         kpad = ceil_to(k * k * 3, 64)
         rows = self.B * Ho * Wo
         gathered = Act(self.buf(name, (rows, kpad)), kpad, kpad, 0)
-        self.add(lambda: ops.im2col(inp, True, 1.0, 0, self.B, H, W, 3, 3, k, k, stride, pad, pad, Ho, Wo, gathered.t, kpad, kpad, 0))
+        self.add(lambda: ops.im2col(inp, True, p2, 0, self.B, H, W, 3, 3, k, k, stride, pad, pad, Ho, Wo, gathered.t, kpad, kpad, 0))
         self.gemm(x=gathered, rows=rows, cin=kpad, w=w, N=N, bias=self.const(shift), relu=True, out16=out16,
                   taps=(0, 0) if self.split else (0,))
         self.flops -= 2.0 * rows * N * (kpad - k * k * 3)   # count the real K, not the padding
