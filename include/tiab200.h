@@ -165,6 +165,10 @@ typedef struct {
   void* head_out[4];
   int head_nout[4];
   int head_ld[4];
+  /* fp32 [groups*N] or NULL: the accumulator of output channel co is multiplied by out_scale[co] before the bias.  Lets the
+   * packed weights be stored pre-scaled by a power of two per output channel, so that W_lo = W - fp16(W) stays inside fp16's
+   * normal range whatever the magnitude of the checkpoint's weights. */
+  const void* out_scale;
 } tiab_conv_desc_t;
 
 int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream);

@@ -54,6 +54,7 @@ class ConvDesc(C.Structure):
         ("tap_coff", C.c_int * MAX_TAPS), ("s2d_c", C.c_int),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_scale", C.c_void_p), ("head_shift", C.c_void_p),
         ("head_out", C.c_void_p * 4), ("head_nout", C.c_int * 4), ("head_ld", C.c_int * 4),
+        ("out_scale", C.c_void_p),
     ]
 
 

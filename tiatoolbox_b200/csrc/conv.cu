@@ -62,6 +62,7 @@ struct ConvParams {
   const float* scale2;
   const float* shift2;
   const float* bias;
+  const float* oscale;    // per-output-channel factor applied to the accumulator before the bias (weights are stored pre-scaled), or null
   const float* res32;
   const __half* res16;
   int ldres, coffres;
@@ -231,7 +232,7 @@ __device__ __forceinline__ void transform_store(const float4 (&xf)[BLOCK_M / 8],
 // The common combinations are separate instantiations so that the executed path has no per-row feature branches.
 template <bool GENERIC, int RES, bool O32, bool O16, bool O16B, bool LO, bool PRE>
 __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t stg_s, int rsub, int cq, uint32_t vmask, const int (&drow)[8],
-                                              const int (&rrow)[8], const float4 (&rres)[8], int n, float4 bias4, float4 sc2,
+                                              const int (&rrow)[8], const float4 (&rres)[8], int n, float4 os4, float4 bias4, float4 sc2,
                                               float4 sh2, float floor_) {
   const bool res32 = GENERIC ? p.res32 != nullptr : RES == 1;
   const bool res16 = GENERIC ? (p.res32 == nullptr && p.res16 != nullptr) : RES == 2;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void epilogue_rows(const ConvParams& p, uint32_t stg_
     if (!(vmask >> i & 1u)) continue;
     const int rl7 = (i & 1) * 4 + rsub;   // (i*4 + rsub) & 7
     float4 x = lds_f4(stg_s + i * 512 + rsub * 128 + ((cq ^ rl7) << 4));
-    x.x += bias4.x, x.y += bias4.y, x.z += bias4.z, x.w += bias4.w;
+    x.x = fmaf(x.x, os4.x, bias4.x), x.y = fmaf(x.y, os4.y, bias4.y), x.z = fmaf(x.z, os4.z, bias4.z), x.w = fmaf(x.w, os4.w, bias4.w);
     if (res32) {
       const float4 rr = PRE ? rres[i] : *reinterpret_cast<const float4*>(p.res32 + (long long)rrow[i] * p.ldres + p.coffres + n);
       x.x += rr.x, x.y += rr.y, x.z += rr.z, x.w += rr.w;
@@ -584,7 +585,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 8; ++j) part[j] = 0.f;
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(hs + c)), t4 = __ldg(reinterpret_cast<const float4*>(ht + c));
+            float4 s4 = __ldg(reinterpret_cast<const float4*>(hs + c));
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(ht + c));
+            if (p.oscale) {   // fold the weight pre-scaling into the head's BN scale
+              const float4 o4 = __ldg(reinterpret_cast<const float4*>(p.oscale + gn + c0 + c));
+              s4.x *= o4.x, s4.y *= o4.y, s4.z *= o4.z, s4.w *= o4.w;
+            }
             const float a0 = fmaxf(fmaf(__uint_as_float(r[c]), s4.x, t4.x), 0.f), a1 = fmaxf(fmaf(__uint_as_float(r[c + 1]), s4.y, t4.y), 0.f);
             const float a2 = fmaxf(fmaf(__uint_as_float(r[c + 2]), s4.z, t4.z), 0.f), a3 = fmaxf(fmaf(__uint_as_float(r[c + 3]), s4.w, t4.w), 0.f);
 #pragma unroll
@@ -624,18 +630,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n = n0 + c0 + 4 * cq;   // first of this lane's 4 output channels
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc2 = bias4, sh2 = bias4;
         if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn + n));
+        float4 os4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.oscale) os4 = __ldg(reinterpret_cast<const float4*>(p.oscale + gn + n));
         if (p.out16b) {
           sc2 = __ldg(reinterpret_cast<const float4*>(p.scale2 + gn + n));
           sh2 = __ldg(reinterpret_cast<const float4*>(p.shift2 + gn + n));
         }
         constexpr bool PRE = !AMODE;
         switch (p.epi_mode) {
-          case 1: epilogue_rows<false, 0, false, true, false, true, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
-          case 2: epilogue_rows<false, 0, false, true, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
-          case 3: epilogue_rows<false, 0, true, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
-          case 4: epilogue_rows<false, 1, true, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
-          case 5: epilogue_rows<false, 1, false, false, true, true, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
-          default: epilogue_rows<true, -1, false, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, bias4, sc2, sh2, floor_); break;
+          case 1: epilogue_rows<false, 0, false, true, false, true, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, os4, bias4, sc2, sh2, floor_); break;
+          case 2: epilogue_rows<false, 0, false, true, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, os4, bias4, sc2, sh2, floor_); break;
+          case 3: epilogue_rows<false, 0, true, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, os4, bias4, sc2, sh2, floor_); break;
+          case 4: epilogue_rows<false, 1, true, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, os4, bias4, sc2, sh2, floor_); break;
+          case 5: epilogue_rows<false, 1, false, false, true, true, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, os4, bias4, sc2, sh2, floor_); break;
+          default: epilogue_rows<true, -1, false, false, false, false, PRE>(p, stg_s, rsub, cq, vmask, drow, rrow, rcur, n, os4, bias4, sc2, sh2, floor_); break;
         }
         if (!AMODE) {
 #pragma unroll
@@ -1287,6 +1295,7 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
   p.pre_scale = (const float*)d->pre_scale, p.pre_shift = (const float*)d->pre_shift, p.pre_relu = d->pre_relu;
   for (int t = 0; t < d->taps; ++t) p.tap_off[t] = d->tap_off[t], p.tap_coff[t] = d->tap_coff[t];
   p.s2d_c = d->s2d_c;
+  p.oscale = (const float*)d->out_scale;
   if (d->head_w) {
     if (d->N != 64 || amode || groups > 4 || d->out16 || d->out32 || d->out16b || d->res32 || d->res16 || !d->head_b || !d->head_scale ||
         !d->head_shift) {

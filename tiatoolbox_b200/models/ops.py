@@ -87,6 +87,11 @@ class ConvOp:
             d.tap_off[i] = int(t)
             d.tap_coff[i] = int(tap_coff[i]) if tap_coff else 0
         d.s2d_c = int(s2d_c)
+        oscale = getattr(w, "oscale", None)   # per-output-channel power-of-two pre-scaling of the packed weights (plan.pack_weight)
+        if oscale is not None:
+            assert oscale.dtype == torch.float32 and oscale.numel() == w.shape[0] and oscale.device == w.device
+            d.out_scale = oscale.data_ptr()
+        self._oscale_keep = oscale
         if head is not None:
             hw, hb, hs, ht, outs = head
             assert N == 64 and hw.dtype == torch.float32 and hw.shape == (max(groups, 1), 8, 64) and len(outs) == max(groups, 1)

@@ -64,7 +64,13 @@ def pack_weight(w: torch.Tensor, out_scale: torch.Tensor | None = None, groups: 
         cp = ceil_to(cin, 64)
         packed = torch.zeros(co, kh * kw, cp, dtype=torch.float64)
         packed[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, cin)
-    return _split_pack(packed, split).to(device)
+    # per-output-channel power-of-two pre-scaling (undone exactly by the epilogue's out_scale): keeps W_lo = W - fp16(W) inside
+    # fp16's normal range for small-magnitude weights, which would otherwise leave the split product with ~14 instead of ~22 bits
+    rowmax = packed.abs().amax(dim=(1, 2)).clamp_min(1e-30)
+    pre = torch.exp2(torch.floor(torch.log2(64.0 / rowmax))).clamp(2.0 ** -16, 2.0 ** 24)
+    out = _split_pack(packed * pre.view(-1, 1, 1), split).to(device)
+    out.oscale = (1.0 / pre).to(torch.float32).to(device)
+    return out
 
 
 class Plan:
@@ -182,11 +188,16 @@ class Plan:
 
     def weight_groups(self, ws, **kw) -> torch.Tensor:
         """Packed weights of several same-shape convolutions stacked along the output-channel axis (grouped launches)."""
-        return torch.cat([self.weight(w, **kw) for w in ws], dim=0).contiguous()
+        parts = [self.weight(w, **kw) for w in ws]
+        out = torch.cat(parts, dim=0).contiguous()
+        out.oscale = torch.cat([p.oscale for p in parts]).contiguous()
+        return out
 
     def fold_bn_groups(self, sd, conv_names, bn_names):
         packed, biases = zip(*(self.fold_bn(sd, c, b) for c, b in zip(conv_names, bn_names)))
-        return torch.cat(packed, dim=0).contiguous(), self.const(torch.cat([b.cpu() for b in biases]))
+        out = torch.cat(packed, dim=0).contiguous()
+        out.oscale = torch.cat([p.oscale for p in packed]).contiguous()
+        return out, self.const(torch.cat([b.cpu() for b in biases]))
 
     def gemm(self, *, x, rows: int, cin: int, w: torch.Tensor, N: int, pre=None, taps=(0,), **kw) -> ops.ConvOp:
         """Plain [rows, cin] x [N, cin]^T GEMM (1x1 conv on a dense matrix / im2col output)."""
