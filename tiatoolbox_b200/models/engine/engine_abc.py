@@ -175,9 +175,32 @@ class EngineABC:
         n = len(patches)
         if n == 0:
             return
-        pin = torch.empty((min(self.batch_size, n), *patches.shape[1:]), dtype=torch.uint8).pin_memory()
-        for i in range(0, n, self.batch_size):
+        # two pinned staging buffers: the host fills one while the H2D copy of the other may still be in flight
+        shape = (min(self.batch_size, n), *patches.shape[1:])
+        pins = [self._pinned(("h2d", k), shape, torch.uint8) for k in range(2)]
+        done = [None, None]
+        for b, i in enumerate(range(0, n, self.batch_size)):
             chunk = patches[i:i + self.batch_size]
+            pin = pins[b & 1]
+            if done[b & 1] is not None:
+                done[b & 1].synchronize()
             pin[: len(chunk)].copy_(torch.from_numpy(chunk))
             x = pin[: len(chunk)].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            done[b & 1] = ev
             yield self._device_preproc(x)
+
+    def _pinned(self, key, shape, dtype) -> torch.Tensor:
+        """Cached pinned host buffer (cudaHostAlloc costs milliseconds; engines are called once per slide region)."""
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        k = (key, tuple(shape), dtype)
+        if k not in cache:
+            cache[k] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        return cache[k]
+
+    def _to_host_async(self, key, t: torch.Tensor) -> torch.Tensor:
+        """Start a device -> pinned-host copy on the current stream; the caller synchronises on an event before reading."""
+        buf = self._pinned(key, (max(self.batch_size, t.shape[0]), *t.shape[1:]), t.dtype)[: t.shape[0]]
+        buf.copy_(t, non_blocking=True)
+        return buf

@@ -21,31 +21,44 @@ class MultiTaskSegmentor(EngineABC):
     with_contours = True
 
     def infer_patches(self, patches: np.ndarray):
-        insts, tables, heads = [], [], []
-        for x in self._batches(patches):
+        """GPU: stain -> network -> post-processing per batch, all asynchronous.  Host: the instance dictionaries (contour tracing
+        with cv2) of batch i are built while the GPU already works on batch i + 1 (results travel through pinned buffers)."""
+        insts, infos, heads = [], [], []
+        pending = None
+
+        def finish(p):
+            ev, inst_h, table_h = p
+            ev.synchronize()
+            inst_np = inst_h.numpy()
+            t = {k: v.numpy() for k, v in table_h.items()}
+            for i in range(len(t["count"])):
+                infos.append(pp.instance_info(inst_np[i], {key: v[i] for key, v in t.items()}, with_contours=self.with_contours))
+
+        for b, x in enumerate(self._batches(patches)):
             outs = type(self.model).infer_batch_device(self.model, x, device=self.device)
             np_map, hv_map = outs[0], outs[1]
             tp_map = outs[2] if len(outs) > 2 else None
             inst, table = pp.proc_np_hv_batch(np_map, hv_map, tp_map)
             insts.append(inst)
-            tables.append({k: v.cpu().numpy() for k, v in table.items()})
+            slot = b & 1
+            inst_h = self._to_host_async(("inst", slot), inst)
+            table_h = {k: self._to_host_async(("tab", k, slot), v) for k, v in table.items()}
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
             if self.return_probabilities:
                 heads.append([o.clone() for o in outs])
-        return insts, tables, heads
+            if pending is not None:
+                finish(pending)
+            pending = (ev, inst_h, table_h)
+        if pending is not None:
+            finish(pending)
+        return insts, infos, heads
 
     def post_process_patches(self, raw, n_total: int) -> dict:
-        insts, tables, heads = raw
+        insts, infos, heads = raw
         dist, rank, world = self._dist()
         local = torch.cat(insts) if insts else torch.empty((0, 1, 1), dtype=torch.int32, device=self.device)
         inst_all = self._all_gather_rows(local, n_total).cpu().numpy()
-        lo, _ = self.shard_bounds(n_total, rank, world)
-        infos = []
-        k = lo
-        for t in tables:
-            for i in range(len(t["count"])):
-                row = {key: v[i] for key, v in t.items()}
-                infos.append(pp.instance_info(inst_all[k], row, with_contours=self.with_contours))
-                k += 1
         if dist is not None:
             gathered = [None] * world
             dist.all_gather_object(gathered, infos)
