@@ -202,6 +202,20 @@ int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv
 int tiab_softmax_up2_crop(tiab_handle_t h, const float* logits, int N, int H, int W, int C, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * WSI stitching on the device.  Replaces the Python block loops of
+ * tiatoolbox/models/engine/semantic_segmentor.py: merge_batch_to_canvas :1141-1183, merge_horizontal :1186-1263,
+ * merge_vertical_chunkwise :1398-1534.  blocks_dev: N*bh*bw*C float32 patch predictions (device); locs_host: N*4 int32
+ * [xs, ys, xe, ye] (host).  Sums are formed in the reference's order, so float32 results equal numpy's bit for bit.
+ * ------------------------------------------------------------------------------------------- */
+/* one patch row -> canvas (H*W*C float32, every block placed at row 0) + count (H*W uint8); all-zero blocks are skipped and not counted */
+int tiab_merge_batch_to_canvas(tiab_handle_t h, const float* blocks_dev, int N, int bh, int bw, int C, const int* locs_host, int H, int W,
+                               float* canvas_dev, uint8_t* count_dev, void* stream);
+/* the whole merge of SemanticSegmentor.infer_wsi for in-memory patches in row-major grid order (a new patch row starts when ys changes):
+ * row canvases of width canvas_width, seam folding of neighbouring rows, count normalisation (0 -> 1), clip to out_H x out_W. */
+int tiab_stitch_patches(tiab_handle_t h, const float* blocks_dev, int N, int bh, int bw, int C, const int* locs_host, int canvas_width,
+                        int out_H, int out_W, float* prob_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HoVer-Net post-processing on the device: HoVerNet._proc_np_hv + get_instance_info (without contours)
  * (tiatoolbox/models/architecture/hovernet.py:502-748).  np_map N*H*W*1, hv_map N*H*W*2, tp_map N*H*W*1 (or NULL),
  * all float32 device pointers as returned by infer_batch.  Outputs (device): inst_map N*H*W int32;

@@ -175,3 +175,22 @@ def load_models():
     mods.vanilla = importlib.import_module("tiatoolbox.models.architecture.vanilla")
     _loaded["models"] = mods
     return mods
+
+
+def load_semseg_merge():
+    """The reference's pure-numpy stitching helpers of tiatoolbox/models/engine/semantic_segmentor.py, executed from their
+    unmodified source text (the module itself imports dask / zarr / psutil, which this image does not have):
+    merge_batch_to_canvas :1141-1183, clip_probabilities_to_shape :1537-1557, concatenate_none :1112-1138 (numpy branch)."""
+    if "semseg_merge" in _loaded:
+        return _loaded["semseg_merge"]
+    src = (REF_PKG / "models" / "engine" / "semantic_segmentor.py").read_text()
+    wanted = {"merge_batch_to_canvas", "clip_probabilities_to_shape"}
+    code = "from __future__ import annotations\nimport numpy as np\n" + "\n\n".join(
+        ast.get_source_segment(src, n)
+        for n in ast.parse(src).body
+        if isinstance(n, ast.FunctionDef) and n.name in wanted
+    )
+    mod = types.ModuleType("tiatoolbox_ref_semseg_merge")
+    exec(compile(code, "semantic_segmentor.py[merge helpers]", "exec"), mod.__dict__)  # noqa: S102
+    _loaded["semseg_merge"] = mod
+    return mod

@@ -102,6 +102,8 @@ SIGNATURES = {
     "tiab_gap_fc_softmax": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tiab_hovernet_heads": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_longlong, _vp, _vp, _vp, _vp]),
     "tiab_softmax_up2_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "tiab_merge_batch_to_canvas": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "tiab_stitch_patches": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_hovernet_postproc": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tiab_dbg_sobel_kernels": (C.c_int, [_vp, _vp]),
     "tiab_dbg_postproc_fetch": (C.c_int, [_vp, C.c_int, _vp, _vp]),
