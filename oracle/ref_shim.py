@@ -194,3 +194,82 @@ def load_semseg_merge():
     exec(compile(code, "semantic_segmentor.py[merge helpers]", "exec"), mod.__dict__)  # noqa: S102
     _loaded["semseg_merge"] = mod
     return mod
+
+
+class _Box:
+    """Restatement of the only shapely geometry the tile merge uses: an axis-aligned `shapely.box(minx, miny, maxx, maxy)` (shapely is a
+    pinned but absent dependency of the reference; `requirements/requirements.txt`).  `contains` follows the DE-9IM definition for
+    rectangles: every point of `other` lies in self and the interiors meet, i.e. closed-interval inclusion in a self that has area."""
+
+    def __init__(self, minx, miny, maxx, maxy):
+        self.b = (min(minx, maxx), min(miny, maxy), max(minx, maxx), max(miny, maxy))
+
+    def contains(self, other: "_Box") -> bool:
+        a, o = self.b, other.b
+        if a[2] <= a[0] or a[3] <= a[1]:
+            return False   # a line / point has no interior that a rectangle could share
+        inside = a[0] <= o[0] and a[1] <= o[1] and o[2] <= a[2] and o[3] <= a[3]
+        return bool(inside)
+
+
+class _STRtree:
+    """`STRtree(geoms).query(geom)` without a predicate: the indices of the geometries whose envelopes intersect the envelope of `geom`
+    (closed intervals: touching counts).  shapely returns them in tree order; every call site in the reference only uses them as a set."""
+
+    def __init__(self, geoms):
+        self.bounds = np.array([g.b for g in geoms], dtype=np.float64).reshape(-1, 4)
+
+    def query(self, geom):
+        q = geom.b
+        b = self.bounds
+        hit = (b[:, 0] <= q[2]) & (b[:, 2] >= q[0]) & (b[:, 1] <= q[3]) & (b[:, 3] >= q[1])
+        return np.nonzero(hit)[0]
+
+
+_WSI_MERGE_FUNCS = [
+    "_process_instance_predictions", "retrieve_sel_uids", "_get_sel_indices_margin_lines", "_get_margin_lines",
+    "_move_tile_space_to_wsi_space", "_get_inst_info_dicts", "_update_tile_based_predictions_array", "_build_tile_tasks",
+    "_compute_info_dict_for_merge",
+]
+
+
+def load_wsi_merge():
+    """The reference's WSI tile-mode merging of tiatoolbox/models/engine/multi_task_segmentor.py, executed from the unmodified source
+    text of its functions (the module imports dask / zarr / shapely / matplotlib / psutil, none of which this image has):
+    `_get_tile_info` :1362-1554 (a method: loaded as a plain function taking `self`), `_process_instance_predictions` :2833-2933 and
+    its helpers :2936-3058, `_get_inst_info_dicts` :3061, `_update_tile_based_predictions_array` :3160-3212, `_build_tile_tasks` :3215,
+    `_compute_info_dict_for_merge` :3269; plus `PatchExtractor.get_coordinates` (tools/patchextraction.py:488-613) and `validate_shape`.
+    shapely's `box` / `STRtree` are the restatements above."""
+    if "wsi_merge" in _loaded:
+        return _loaded["wsi_merge"]
+    import textwrap
+    import uuid
+    from collections import deque
+
+    mod = types.ModuleType("tiatoolbox_ref_wsi_merge")
+    pe_src = (REF_PKG / "tools" / "patchextraction.py").read_text()
+    pe_tree = ast.parse(pe_src)
+    parts = ["from __future__ import annotations", "import numpy as np"]
+    for n in pe_tree.body:
+        if isinstance(n, ast.FunctionDef) and n.name == "validate_shape":
+            parts.append(ast.get_source_segment(pe_src, n))
+        if isinstance(n, ast.ClassDef) and n.name == "PatchExtractor":
+            for m in n.body:
+                if isinstance(m, ast.FunctionDef) and m.name == "get_coordinates":
+                    parts.append("class PatchExtractor:\n    @staticmethod\n" + textwrap.indent(textwrap.dedent(
+                        "    " * 0 + ast.get_source_segment(pe_src, m, padded=True)), "    "))
+    src = (REF_PKG / "models" / "engine" / "multi_task_segmentor.py").read_text()
+    tree = ast.parse(src)
+    for n in tree.body:
+        if isinstance(n, ast.FunctionDef) and n.name in _WSI_MERGE_FUNCS:
+            parts.append(ast.get_source_segment(src, n))
+        if isinstance(n, ast.ClassDef) and n.name == "MultiTaskSegmentor":
+            for m in n.body:
+                if isinstance(m, ast.FunctionDef) and m.name == "_get_tile_info":
+                    parts.append(textwrap.dedent(ast.get_source_segment(src, m, padded=True)))
+    shapely = types.SimpleNamespace(box=_Box)
+    mod.__dict__.update({"shapely": shapely, "STRtree": _STRtree, "uuid": uuid, "deque": deque,
+                         "tqdm": lambda it, **_k: it})
+    exec(compile("\n\n".join(parts), "multi_task_segmentor.py[wsi merge]", "exec"), mod.__dict__)  # noqa: S102
+    _loaded["wsi_merge"] = mod
+    return mod

@@ -1,0 +1,232 @@
+"""WSI tile-mode bookkeeping of MultiTaskSegmentor (mirror of tiatoolbox/models/engine/multi_task_segmentor.py:1362-1554, 2833-3296).
+
+The reference post-processes a WSI-scale probability map tile by tile — a non-overlapping tile grid, then vertical strips, horizontal
+strips and cross-sections straddling the tile seams — and merges the per-tile instance dictionaries *in that order*: instances that sit
+wholly inside (grid / cross tiles) or that touch (strips) a flagged margin of their tile are dropped, and a cross tile evicts the
+already accumulated instances its inner margin lines cut.  On the B200 path the per-tile watershed runs on the device
+(`postproc.proc_np_hv_batch`) and on any rank; what is left is this order-dependent index arithmetic, replayed on rank 0 after the
+gather.  The reference drives it through shapely boxes and a fresh STRtree per tile; all geometries are axis-aligned
+rectangles, so here it is closed-interval arithmetic on int64 arrays (no shapely on this path).
+
+Every function cites the reference function it replaces; `tests/test_oracle_wsi.py` replays random tile sequences through the unmodified reference functions, the oracle and this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from tiatoolbox_b200.tools.patchextraction import PatchExtractor
+
+INFO_KEYS = ("box", "centroid", "contours", "prob", "type")
+
+
+def boxes_intersect(boxes: np.ndarray, query) -> np.ndarray:
+    """STRtree.query(box) without predicate: envelopes intersect, closed intervals (touching counts)."""
+    b = np.asarray(boxes).reshape(-1, 4)
+    x0, y0, x1, y1 = (min(query[0], query[2]), min(query[1], query[3]), max(query[0], query[2]), max(query[1], query[3]))
+    return (b[:, 0] <= x1) & (b[:, 2] >= x0) & (b[:, 1] <= y1) & (b[:, 3] >= y0)
+
+
+def box_contains(outer, boxes: np.ndarray) -> np.ndarray:
+    """shapely `outer.contains(box)` for rectangles: closed inclusion in an `outer` that has area (a line contains no rectangle)."""
+    b = np.asarray(boxes).reshape(-1, 4)
+    if outer[2] <= outer[0] or outer[3] <= outer[1]:
+        return np.zeros(len(b), dtype=bool)
+    return (outer[0] <= b[:, 0]) & (outer[1] <= b[:, 1]) & (b[:, 2] <= outer[2]) & (b[:, 3] <= outer[3])
+
+
+def _shifted(v, shift) -> np.ndarray:
+    v = np.asarray(v)
+    return (v + shift).astype(v.dtype)
+
+
+def get_tile_info(image_shape, tile_shape, patch_output_shape, margin) -> list[list[np.ndarray]]:
+    """`MultiTaskSegmentor._get_tile_info` (:1362-1554) without a mask reader: tile placement + removal flags [top, bottom, left, right]
+    for the four tile sets (grid, vertical strips, horizontal strips, cross-sections).  `image_shape` is (width, height)."""
+    margin = 0 if margin is None else int(margin)
+    pos = np.asarray(patch_output_shape)
+    tile_shape = (np.floor(np.asarray(tile_shape) / pos) * pos).astype(np.int32)
+    image_shape = np.asarray(image_shape)
+    boxes = PatchExtractor.get_coordinates(image_shape=image_shape, patch_input_shape=tile_shape, patch_output_shape=tile_shape,
+                                           stride_shape=tile_shape)[1]
+    if np.all(image_shape <= tile_shape):
+        return [[boxes, np.zeros([boxes.shape[0], 4], dtype=np.int32)]]
+    w, h = (int(v) for v in image_shape)
+    edges = ((0, 0, w, 0), (0, h, w, h), (0, 0, 0, h), (w, 0, w, h))   # top, bottom, left, right image borders
+
+    def unset_removal_flag(bx: np.ndarray, flag: np.ndarray) -> np.ndarray:
+        for idx, edge in enumerate(edges):
+            flag[boxes_intersect(bx, edge), idx] = 0
+        return flag
+
+    flag = unset_removal_flag(boxes, np.ones([boxes.shape[0], 4], dtype=np.int32))
+    info = [[boxes, flag]]
+    x0, y0, x1, y1 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+    # vertical strips over the right edge of every tile whose right side is removed; their top / bottom are removed
+    s = np.nonzero(flag[:, 3])[0]
+    vb = np.stack([x1[s] - margin, y0[s], x1[s] + margin, y1[s]], axis=-1)
+    vf = np.zeros([len(s), 4], dtype=np.int32)
+    vf[:, [0, 1]] = 1
+    info.append([vb, unset_removal_flag(vb, vf)])
+    # horizontal strips over the bottom edge; their left / right are removed
+    s = np.nonzero(flag[:, 1])[0]
+    hb = np.stack([x0[s], y1[s] - margin, x1[s], y1[s] + margin], axis=-1)
+    hf = np.zeros([len(s), 4], dtype=np.int32)
+    hf[:, [2, 3]] = 1
+    info.append([hb, unset_removal_flag(hb, hf)])
+    # cross-sections around the bottom-right corner; all sides removed
+    s = np.nonzero(flag[:, 1] * flag[:, 3])[0]
+    cb = np.stack([x1[s] - 2 * margin, y1[s] - 2 * margin, x1[s] + 2 * margin, y1[s] + 2 * margin], axis=-1)
+    info.append([cb, np.ones([len(s), 4], dtype=np.int32)])
+    return info
+
+
+def build_tile_tasks(tile_info_sets) -> list[tuple[np.ndarray, np.ndarray, int]]:
+    """`_build_tile_tasks` (:3215-3266): [(tile_bounds, tile_flag, tile_mode)] in processing order (set by set)."""
+    return [(bounds, set_flags[i], set_idx) for set_idx, (set_bounds, set_flags) in enumerate(tile_info_sets)
+            for i, bounds in enumerate(set_bounds)]
+
+
+def select_tile_removals(inst_boxes: np.ndarray, tile_shape, tile_flag, tile_mode: int, margin) -> np.ndarray:
+    """`_get_sel_indices_margin_lines` (:2944-3020), first result: bool mask of the tile's instances to drop (boxes in tile space)."""
+    if tile_mode not in (0, 1, 2, 3):
+        msg = f"Unknown tile mode {tile_mode}."
+        raise ValueError(msg)
+    margin = 0 if margin is None else int(margin)
+    width, height = (int(v) for v in tile_shape)
+    boundary_lines = ((0, 0, width, 1), (0, height - 1, width, height), (0, 0, 1, height), (width - 1, 0, width, height))
+    margin_boxes = ((0, 0, width, margin), (0, height - margin, width, height), (0, 0, margin, height), (width - margin, 0, width, height))
+    b = np.asarray(inst_boxes).reshape(-1, 4)
+    drop = np.zeros(len(b), dtype=bool)
+    if tile_mode in (0, 3):
+        for idx, mb in enumerate(margin_boxes):
+            if tile_flag[idx] or tile_mode == 3:  # noqa: PLR2004
+                drop |= box_contains(mb, b)
+        return drop
+    for idx, flag in enumerate(tile_flag):
+        drop |= boxes_intersect(b, margin_boxes[idx] if flag else boundary_lines[idx])
+    return drop
+
+
+def margin_lines(margin, tile_shape, tile_tl) -> np.ndarray:
+    """`_get_margin_lines` (:3023-3038): the four inner margin lines of a tile in WSI space as (4, 4) [x0, y0, x1, y1] rows."""
+    margin = 0 if margin is None else int(margin)
+    width, height = (int(v) for v in tile_shape)
+    lines = np.array([[margin, margin, width - margin, margin], [margin, height - margin, width - margin, height - margin],
+                      [margin, margin, margin, height - margin], [width - margin, margin, width - margin, height - margin]], dtype=np.int64)
+    return lines + np.concatenate([np.asarray(tile_tl), np.asarray(tile_tl)])[None]
+
+
+class WsiInstanceStore:
+    """The accumulated `wsi_info_dict[task]["info_dict"]` of `_process_tile_mode` (:1230-1279): an insertion-ordered set of instance
+    records with evictions.  Boxes are mirrored in a growing int64 array so that a cross tile's eviction query is one vectorised
+    interval test instead of an STRtree rebuilt over every accumulated instance (`_compute_info_dict_for_merge` :3269-3296)."""
+
+    def __init__(self) -> None:
+        self.records: list[dict] = []
+        self._boxes = np.empty((1024, 4), dtype=np.int64)
+        self._alive = np.zeros(1024, dtype=bool)
+        self.n = 0
+
+    def __len__(self) -> int:
+        return int(self._alive[: self.n].sum())
+
+    def _append(self, rec: dict) -> None:
+        if self.n == len(self._boxes):
+            self._boxes = np.concatenate([self._boxes, np.empty_like(self._boxes)])
+            self._alive = np.concatenate([self._alive, np.zeros_like(self._alive)])
+        self._boxes[self.n] = rec["box"]
+        self._alive[self.n] = True
+        self.records.append(rec)
+        self.n += 1
+
+    def merge_tile(self, inst_dict: dict, *, tile_bounds, tile_flag, tile_mode: int, margin) -> tuple[int, int]:
+        """`_compute_info_dict_for_merge` + the update / pop of `_process_tile_mode` for one tile.  `inst_dict` = {k: record} in tile
+        space (record keys: box [x0, y0, x1, y1], centroid, contours, prob, type), in the order of the tile's info_dict.
+        Returns (#added, #evicted)."""
+        if len(inst_dict) == 0:   # :2903-2904 — an empty cross tile evicts nothing either
+            return 0, 0
+        tile_bounds = np.asarray(tile_bounds)
+        tile_tl = tile_bounds[:2]
+        tile_shape = tile_bounds[2:] - tile_bounds[:2]
+        recs = list(inst_dict.values())
+        boxes = np.array([r["box"] for r in recs]).reshape(-1, 4)
+        drop = select_tile_removals(boxes, tile_shape, tile_flag, tile_mode, margin)
+        evicted = 0
+        if tile_mode == 3:  # noqa: PLR2004
+            hit = np.zeros(self.n, dtype=bool)
+            for line in margin_lines(margin, tile_shape, tile_tl):
+                hit |= boxes_intersect(self._boxes[: self.n], line)
+            hit &= self._alive[: self.n]
+            evicted = int(hit.sum())
+            self._alive[: self.n][hit] = False
+        shift4 = np.concatenate([tile_tl, tile_tl])
+        added = 0
+        for rec, d in zip(recs, drop):
+            if d:
+                continue
+            moved = dict(rec)    # `_move_tile_space_to_wsi_space` (:3041-3058): in-place `+=`, i.e. every array keeps its dtype
+            moved["box"] = _shifted(rec["box"], shift4)
+            if "centroid" in rec:
+                moved["centroid"] = _shifted(rec["centroid"], tile_tl)
+            moved["contours"] = _shifted(rec["contours"], tile_tl)
+            self._append(moved)
+            added += 1
+        return added, evicted
+
+    def alive_records(self) -> list[dict]:
+        return [r for r, a in zip(self.records, self._alive[: self.n]) if a]
+
+    def to_info_dict(self, offset=(0, 0)) -> dict:
+        """`_inst_dict_for_dask_processing` (:1289-1328): {key: object array over the surviving instances, insertion order}; the mask
+        offset is added to box / centroid / contours (`apply_coordinate_offset` :3760-3826).  No instances -> {} like the reference."""
+        recs = self.alive_records()
+        if not recs:
+            return {}
+        dx, dy = (int(v) for v in offset)
+        out = {}
+        for key in recs[0]:
+            col = np.empty(len(recs), dtype=object)
+            for i, r in enumerate(recs):
+                v = r[key]
+                if key in ("centroid", "box", "contours") and not dx == dy == 0:
+                    v = np.asarray(v)
+                    shift = np.array([dx, dy, dx, dy]) if (v.size == 4 and v.ndim == 1) else np.array([dx, dy])  # noqa: PLR2004
+                    v = (v + shift).astype(v.dtype)
+                col[i] = v
+            out[key] = col
+        return out
+
+
+def tile_instance_dict(info_dict: dict) -> dict:
+    """`_get_inst_info_dicts` (:3061-3083) for one task: {i + 1: {key: values[i]}} from a tile's packed `info_dict` columns."""
+    keys = list(info_dict.keys())
+    n = len(info_dict[keys[0]]) if keys else 0
+    return {i + 1: {key: info_dict[key][i] for key in keys} for i in range(n)}
+
+
+def update_tile_based_predictions_array(new_pred: np.ndarray, wsi_pred: np.ndarray, bounds, offset=(0, 0),
+                                        max_inst_value: int | None = None, seg_type: str = "instance") -> int | None:
+    """`_update_tile_based_predictions_array` (:3160-3212) for one task: paste a tile's prediction map into the WSI array in place.
+    Instance maps keep what is already there, skip every new instance that overlaps it, and shift the new ids by the running
+    `max_inst_value` — an order-dependent recurrence, hence replayed in tile order on one rank."""
+    x_start, y_start, x_end, y_end = (int(v) for v in bounds)
+    x_start, x_end = x_start + int(offset[0]), x_end + int(offset[0])
+    y_start, y_end = y_start + int(offset[1]), y_end + int(offset[1])
+    max_h, max_w = wsi_pred.shape
+    x_end, y_end = min(x_end, max_w), min(y_end, max_h)
+    new = new_pred[0: y_end - y_start, 0: x_end - x_start]
+    if seg_type == "instance":
+        prev = wsi_pred[y_start:y_end, x_start:x_end]
+        overlap = (new > 0) & (prev > 0)
+        max_inst_value = 0 if max_inst_value is None else max_inst_value
+        keep = new > 0
+        if np.any(overlap):
+            ids = np.unique(new[overlap])
+            ids = ids[ids > 0]
+            keep = (new > 0) & (~np.isin(new, ids))
+        combined = prev.copy()
+        combined[keep] = new[keep] + max_inst_value
+        new = combined
+        max_inst_value = (np.max(new) + max_inst_value) if np.any(keep) else max_inst_value
+    wsi_pred[y_start:y_end, x_start:x_end] = new
+    return max_inst_value
