@@ -125,7 +125,7 @@ def get_instance_info(pred_inst: np.ndarray, pred_type: np.ndarray | None = None
         if contour.shape[0] < 3 or len(contour.shape) != 2:
             continue
         centroid = np.array([mom["m10"] / mom["m00"], mom["m01"] / mom["m00"]]) + tl
-        contour = contour + tl[None]
+        contour += tl[None]   # in place like hovernet.py:705 — the contour stays int32
         box = box.copy()
         box[:2] += offset
         box[2:] += offset

@@ -1,0 +1,208 @@
+"""WSI mode of NucleusInstanceSegmentor — host logic (banding, strided patch views, row stitching order, tile batching, gather, replay)
+exercised WITHOUT a GPU: the three device primitives of `WsiTileModeMixin` are replaced by oracle-backed CPU stand-ins (tests may use the
+oracle as the checker; the product engine itself refuses non-CUDA devices).  The "network" is a pixel-wise decoder of a synthetic slide
+whose RGB channels encode HoVer-Net head maps, so the WSI-scale head canvases — and therefore the expected result of the reference's
+tile-mode flow, computed independently with oracle/wsi_oracle.py + oracle/hovernet_postproc_oracle.py — are known exactly.
+world_size 1 and 2 (gloo) must give the same answer."""
+from __future__ import annotations
+
+import os
+from types import SimpleNamespace
+
+import cv2
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import hovernet_postproc_oracle as ppo
+from oracle import wsi_oracle as wo
+from tiatoolbox_b200.models.architecture import IOConfig
+from tiatoolbox_b200.models.engine.nucleus_instance_segmentor import NucleusInstanceSegmentor
+from tiatoolbox_b200.models.engine.wsi import WsiTilePlan
+
+IO_SMALL = IOConfig(patch_input_shape=(64, 64), stride_shape=(40, 40), patch_output_shape=(40, 40), margin=24, tile_shape=(170, 170))
+
+
+def synthetic_slide(h: int, w: int, seed: int = 0, n_nuclei: int = 90) -> np.ndarray:
+    """RGB = (np * 255, (hv_x + 1) * 127.5, (hv_y + 1) * 127.5) of disc-shaped nuclei; the decoder below inverts it pixel by pixel."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    inst = np.zeros((h, w), np.int32)
+    for j in range(1, n_nuclei + 1):
+        cy, cx, r = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(4, 9)
+        inst[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = j
+    npm = np.where(inst > 0, 0.93, 0.04) + rng.normal(0, 0.01, (h, w))
+    hv = np.zeros((h, w, 2), np.float32)
+    for j in np.unique(inst)[1:]:
+        ys, xs = np.nonzero(inst == j)
+        for c, v in ((0, xs - xs.mean()), (1, ys - ys.mean())):
+            hv[ys, xs, c] = v / max(np.abs(v).max(), 1e-6)
+    img = np.stack([npm * 255.0, (hv[..., 0] + 1) * 127.5, (hv[..., 1] + 1) * 127.5], axis=-1)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def decode_heads(rgb: np.ndarray) -> list[np.ndarray]:
+    """(..., 3) uint8 -> [np (..., 1), hv (..., 2), tp (..., 1)] float32, pixel-wise (the stand-in 'network')."""
+    f = rgb.astype(np.float32)
+    npm = f[..., 0:1] / np.float32(255.0)
+    hv = f[..., 1:3] / np.float32(127.5) - np.float32(1.0)
+    tp = np.where(npm > 0.5, 1.0 + ((rgb[..., 1:2] // 16) % 5), 0.0).astype(np.float32)
+    return [npm, hv, tp]
+
+
+def table_from_inst(inst: np.ndarray, tp: np.ndarray, max_inst: int) -> dict:
+    """The device instance table (include/tiab200.h: tiab_hovernet_postproc) rebuilt on the CPU: every labelled instance in ascending id
+    order — box, cv2.moments centroid, majority type (hovernet.py:719-746)."""
+    ids = [int(v) for v in np.unique(inst) if v > 0]
+    t = {"count": np.int32(len(ids)), "id": np.zeros(max_inst, np.int32), "box": np.zeros((max_inst, 4), np.int32),
+         "centroid": np.zeros((max_inst, 2), np.float64), "type": np.zeros(max_inst, np.int32), "prob": np.zeros(max_inst, np.float64)}
+    pred_type = np.around(tp[..., 0]).astype("uint8")
+    for k, i in enumerate(ids):
+        m = inst == i
+        box = ppo.get_bounding_box(m)
+        crop = m[box[1]:box[3], box[0]:box[2]]
+        mom = cv2.moments(crop.astype(np.uint8))
+        types, cnt = np.unique(pred_type[box[1]:box[3], box[0]:box[2]][crop], return_counts=True)
+        order = sorted(zip(types, cnt), key=lambda x: x[1], reverse=True)
+        ty = order[0][0]
+        if ty == 0 and len(order) > 1:
+            ty = order[1][0]
+        t["id"][k], t["box"][k] = i, box
+        t["centroid"][k] = [mom["m10"] / mom["m00"] + box[0], mom["m01"] / mom["m00"] + box[1]]
+        t["type"][k], t["prob"][k] = int(ty), float(dict(order)[ty] / (crop.sum() + 1.0e-6))
+    return t
+
+
+class StubEngine(NucleusInstanceSegmentor):
+    """CPU stand-ins for the three device primitives (forward / stitch / post-processing)."""
+
+    def __init__(self, batch_size: int = 5) -> None:   # noqa: D107 — bypasses EngineABC.__init__ (which insists on CUDA)
+        self.batch_size = batch_size
+        self.device = torch.device("cpu")
+        self.ioconfig = IO_SMALL
+        self.model = SimpleNamespace(_plan_batch=None)
+        self.return_probabilities = False
+        self.forward_calls = 0
+
+    def _wsi_forward(self, x):
+        assert x.dtype == torch.uint8 and x.is_contiguous() and x.shape[1:] == (64, 64, 3) and x.shape[0] <= self.batch_size
+        self.forward_calls += 1
+        return [torch.from_numpy(np.ascontiguousarray(h)) for h in decode_heads(x.numpy()[:, 12:52, 12:52])]
+
+    def _wsi_stitch_row(self, blocks, locs, width, out):
+        from oracle import stitch_oracle
+
+        res = stitch_oracle.stitch(blocks.numpy(), locs, canvas_width=width, output_shape=(out.shape[0], out.shape[1]))
+        out.copy_(torch.from_numpy(res))
+
+    def _wsi_postproc(self, np_map, hv_map, tp_map):
+        n, h, w = np_map.shape[:3]
+        max_inst = max(16, (h * w) // 10 + 1)
+        insts, rows = [], []
+        for i in range(n):
+            inst = ppo.proc_np_hv(np_map[i].numpy(), hv_map[i].numpy())
+            insts.append(inst.astype(np.int32))
+            rows.append(table_from_inst(inst, tp_map[i].numpy(), max_inst))
+        table = {k: torch.from_numpy(np.stack([r[k] for r in rows])) for k in rows[0]}
+        return torch.from_numpy(np.stack(insts)), table
+
+
+def expected_result(image: np.ndarray, io: IOConfig):
+    """The reference flow restated with the oracles: WSI head maps -> tile sets -> per-tile postproc -> ordered merge / paste."""
+    heads = decode_heads(image)
+    h, w = image.shape[:2]
+    sets = wo.get_tile_info((w, h), io.tile_shape, io.patch_output_shape, io.margin)
+    tiles = []
+    wsi_pred = np.zeros((h, w), np.int32)
+    mx = None
+    for bounds, flag, mode in wo.build_tile_tasks(sets):
+        x0, y0, x1, y1 = (int(v) for v in bounds)
+        crop = [hd[max(y0, 0):y1, max(x0, 0):x1] for hd in heads]
+        inst, info = ppo.postproc(*crop)
+        mx = wo.paste_instance_tile(wsi_pred, inst, bounds, mx)
+        tiles.append((bounds, flag, mode, list(info.values())))
+    return wo.replay_merge(tiles, io.margin), wsi_pred, heads
+
+
+def check(out: dict, kept: list[dict], wsi_pred: np.ndarray) -> None:
+    assert len(kept) > 20
+    assert len(out["box"]) == len(kept)
+    for i, rec in enumerate(kept):
+        assert np.array_equal(out["box"][i], rec["box"]), i
+        assert np.array_equal(out["contours"][i], rec["contours"]) and out["contours"][i].dtype == np.int32, i
+        np.testing.assert_allclose(out["centroid"][i], rec["centroid"], rtol=0, atol=1e-9)
+        assert out["type"][i] == rec["type"] and abs(out["prob"][i] - rec["prob"]) < 1e-12, i
+    assert np.array_equal(out["predictions"], wsi_pred)
+
+
+def test_plan_covers_every_tile_once_and_reads_enough():
+    for world in (1, 2, 3, 5):
+        owned = []
+        for r in range(world):
+            p = WsiTilePlan((450, 390), IO_SMALL, r, world)
+            owned += p.my_tasks
+            for i in p.my_tasks:
+                y0, y1 = max(int(p.tasks[i][0][1]), 0), min(int(p.tasks[i][0][3]), p.H)
+                assert p.canvas_y0 <= y0 and y1 <= p.canvas_y1
+            if len(p.my_patches):
+                assert np.array_equal(p.my_patches, np.arange(p.my_patches[0], p.my_patches[-1] + 1))   # whole patch rows, contiguous
+        assert sorted(owned) == list(range(len(p.tasks)))
+    one = WsiTilePlan((150, 120), IO_SMALL)          # fits one tile: `_process_full_wsi`
+    assert not one.tile_mode and len(one.tasks) == 1 and one.my_tasks == [0]
+
+
+def test_wsi_mode_single_rank_matches_the_oracle_flow():
+    image = synthetic_slide(390, 450, seed=3)
+    kept, wsi_pred, heads = expected_result(image, IO_SMALL)
+    eng = StubEngine()
+    eng.return_probabilities = True
+    out = eng.run(image, patch_mode=False, return_predictions=(True,))
+    check(out, kept, wsi_pred)
+    for got, want in zip(out["probabilities"], heads):     # the stitched head canvases equal the pixel-wise decode of the slide
+        assert np.array_equal(got, want)
+    assert out["coordinates"].shape == (10 * 12, 4) and eng.forward_calls == 10 * 3   # 12 patches per row in batches of 5
+    # a list of slides gives a list of results; a region that fits one tile takes the un-tiled branch
+    small = image[:120, :150]
+    outs = eng.run([small], patch_mode=False)
+    inst, info = ppo.postproc(*decode_heads(small))
+    assert isinstance(outs, list) and len(outs[0]["box"]) == len(info) and "predictions" not in outs[0]
+    assert all(np.array_equal(a, r["box"]) for a, r in zip(outs[0]["box"], info.values()))
+    with pytest.raises(ValueError, match="uint8"):
+        eng.run(image.astype(np.float32), patch_mode=False)
+    with pytest.raises(NotImplementedError, match="dict"):
+        eng.run(image, patch_mode=False, output_type="zarr")
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    image = synthetic_slide(390, 450, seed=3)
+    eng = StubEngine()
+    out = eng.run(image, patch_mode=False, return_predictions=True)
+    q.put((rank, eng.forward_calls, {k: (list(v) if v.dtype == object else v) for k, v in out.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_wsi_mode_world2_equals_world1():
+    image = synthetic_slide(390, 450, seed=3)
+    kept, wsi_pred, _ = expected_result(image, IO_SMALL)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    calls = {r: c for r, c, _ in res}
+    # each rank infers only its band (+ halo): rank 1 owns the last tile row = 2 of the 10 patch rows; rank 0's two tile rows plus
+    # their 2 x margin halo happen to reach the slide's last patch row on this small slide
+    assert calls[1] == 2 * 3 and 0 < calls[0] <= 30
+    for _, _, out in res:                               # every rank returns the full result
+        check(out, kept, wsi_pred)

@@ -11,14 +11,40 @@ import torch
 
 from tiatoolbox_b200.models import postproc as pp
 from tiatoolbox_b200.models.engine.engine_abc import EngineABC
+from tiatoolbox_b200.models.engine.wsi import WsiTileModeMixin
 
 
-class MultiTaskSegmentor(EngineABC):
+class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
     """run(...) -> single task flattened (multi_task_segmentor.py:1697-1704):
     {"predictions": (N, h, w) int32, "box", "centroid", "contours", "prob", "type": length-N lists,
      ["probabilities": [np, hv, tp]]}."""
 
     with_contours = True
+
+    def run(self, images, *, patch_mode: bool = True, ioconfig=None, return_predictions=None, **kwargs):
+        """Patch mode: EngineABC.run.  `patch_mode=False` with in-memory slides — one (H, W, 3) uint8 array or a list of them — runs the
+        WSI data flow of multi_task_segmentor.py:477-731, 836-1287 on the device (`WsiTileModeMixin.run_wsi`) and returns one result
+        dict per slide (a single array gives a single dict).  `return_predictions` follows the reference: a tuple of per-task flags
+        (one task here) or a bool."""
+        if patch_mode:
+            return super().run(images, patch_mode=True, ioconfig=ioconfig, **kwargs)
+        if kwargs.get("output_type", "dict").lower() != "dict":
+            msg = "only output_type='dict' is produced on the B200 path (zarr / AnnotationStore are result persistence)"
+            raise NotImplementedError(msg)
+        single = isinstance(images, np.ndarray) and images.ndim == 3  # noqa: PLR2004
+        slides = [images] if single else list(images)
+        if not slides or not all(isinstance(s, np.ndarray) for s in slides):
+            msg = "WSI mode takes in-memory (H, W, 3) uint8 arrays (slide files are read by WSIReader, outside the B200 path)"
+            raise NotImplementedError(msg)
+        for k, v in kwargs.items():
+            if k not in ("masks", "input_resolutions", "patch_input_shape", "save_dir", "overwrite", "output_type"):
+                setattr(self, k, v)
+        want_pred = bool(return_predictions[0]) if isinstance(return_predictions, (tuple, list)) else bool(return_predictions)
+        outs = [self.run_wsi(s, ioconfig=ioconfig, return_predictions=want_pred, return_probabilities=bool(self.return_probabilities))
+                for s in slides]
+        return outs[0] if single else outs
+
+    predict = run
 
     def infer_patches(self, patches: np.ndarray):
         """GPU: stain -> network -> post-processing per batch, all asynchronous.  Host: the instance dictionaries (contour tracing

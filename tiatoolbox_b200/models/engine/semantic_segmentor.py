@@ -63,12 +63,13 @@ def merge_batch_to_canvas(blocks, output_locations, merged_shape):
     return canvas, count
 
 
-def stitch_patches(blocks, output_locations, canvas_width: int | None = None, output_shape=None):
+def stitch_patches(blocks, output_locations, canvas_width: int | None = None, output_shape=None, out: torch.Tensor | None = None):
     """The merging of SemanticSegmentor.infer_wsi (merge_horizontal :1186-1263 per patch row, merge_vertical_chunkwise :1398-1534,
     clip_probabilities_to_shape :1537-1557) for patch predictions that are all in memory, in one device pass.
 
     blocks (N, h, w, C) float32 in row-major grid order (x fastest; a new patch row starts when start_y changes);
-    returns the (H, W, C) float32 probability map = overlap sums / counts (uncovered pixels divide by 1)."""
+    returns the (H, W, C) float32 probability map = overlap sums / counts (uncovered pixels divide by 1).  `out`: an optional
+    contiguous (H, W, C) float32 CUDA tensor to write into (e.g. a row slice of a WSI canvas) instead of a fresh allocation."""
     t, locs, was_numpy = _prep(blocks, output_locations)
     n, bh, bw, c = t.shape
     if n == 0:
@@ -78,7 +79,11 @@ def stitch_patches(blocks, output_locations, canvas_width: int | None = None, ou
     if output_shape is None:
         output_shape = (int(locs[:, 3].max() - locs[0, 1]), width)
     H, W = int(output_shape[0]), min(int(output_shape[1]), width)
-    out = torch.empty((H, W, c), dtype=torch.float32, device=t.device)
+    if out is None:
+        out = torch.empty((H, W, c), dtype=torch.float32, device=t.device)
+    elif (tuple(out.shape) != (H, W, c) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != t.device or was_numpy):
+        msg = f"out must be a contiguous float32 tensor of shape {(H, W, c)} on the blocks' device"
+        raise ValueError(msg)
     h = _lib.handle(t.device.index or 0)
     _lib.check(h, _lib.lib().tiab_stitch_patches(h, t.data_ptr(), n, bh, bw, c, locs.ctypes.data_as(C.c_void_p), width, H, W, out.data_ptr(),
                                                  torch.cuda.current_stream(t.device).cuda_stream))

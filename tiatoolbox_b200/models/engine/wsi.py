@@ -1,0 +1,292 @@
+"""WSI mode of MultiTaskSegmentor / NucleusInstanceSegmentor on the B200 (BASELINE config 5).
+
+Reference data flow (tiatoolbox/models/engine/multi_task_segmentor.py): `infer_wsi` :477-731 reads patches through WSIReader (255-padded
+outside the slide, dataset_abc.py:419-431), runs `infer_batch` per batch with a blocking D2H, and stitches WSI-scale head maps on
+the host (dask / zarr spill); `post_process_wsi` :836-997 then slices those maps tile by tile (`_process_tile_mode` :1078-1287), runs
+`postproc_func` per tile on a dask thread pool and merges the per-tile instance dictionaries in order.
+
+Here the slide band of a rank is uploaded ONCE, and everything up to the per-tile instance tables stays in HBM:
+
+  slide band (uint8, 255 border)  --strided view-->  patch batches  --stain normaliser / network-->  head outputs
+      --device stitcher (csrc/stitch.cu)-->  head canvases (float32, H x W x {1, 2, 1})
+      --tile slices-->  on-device watershed + instance table (csrc/postproc.cu)  --D2H-->  contours (cv2) + `wsi_merge` replay
+
+Multi-GPU (one process per GPU): the post-processing tile grid is cut into contiguous bands of tile rows; a rank owns the grid tiles
+of its band and the strips / cross-sections anchored in it, infers exactly the patch rows those tiles read (a halo of at most
+2 x margin below the band is recomputed by both neighbours, no traffic during compute), and the ranks exchange only the final
+per-tile results: one all-gather of the flattened int32 tile instance maps (NCCL) + an object all-gather of the ragged instance
+records.  Every rank then replays the order-dependent merge (`wsi_merge.WsiInstanceStore`), which is deterministic, so the result is
+identical for any number of ranks.
+
+Inputs are in-memory RGB arrays: reading slide files (WSIReader / openslide / tifffile) is file I/O outside the B200 path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from tiatoolbox_b200.models import postproc as pp
+from tiatoolbox_b200.models.engine import wsi_merge as wm
+from tiatoolbox_b200.tools.patchextraction import PatchExtractor
+
+
+class WsiTilePlan:
+    """Host-side geometry of one slide for one rank: patch grid, post-processing tiles, and what this rank owns."""
+
+    def __init__(self, image_wh, ioconfig, rank: int = 0, world: int = 1) -> None:
+        self.W, self.H = int(image_wh[0]), int(image_wh[1])
+        self.margin = 0 if ioconfig.margin is None else int(ioconfig.margin)
+        self.patch_in = tuple(int(v) for v in ioconfig.patch_input_shape)
+        self.patch_out = tuple(int(v) for v in (ioconfig.patch_output_shape or ioconfig.patch_input_shape))
+        self.stride = tuple(int(v) for v in ioconfig.stride_shape)
+        self.in_boxes, self.out_boxes = PatchExtractor.get_coordinates(
+            image_shape=(self.W, self.H), patch_input_shape=self.patch_in, patch_output_shape=self.patch_out, stride_shape=self.stride)
+        tile_shape = ioconfig.tile_shape if ioconfig.tile_shape is not None else (self.W, self.H)
+        # post_process_wsi :939-941: tile mode only when the map is larger than one tile; otherwise one "tile" = the whole map
+        if self.H > int(tile_shape[0]) or self.W > int(tile_shape[1]):
+            sets = wm.get_tile_info((self.W, self.H), tile_shape, self.patch_out, self.margin)
+            self.tile_mode = True
+        else:
+            sets = [[np.array([[0, 0, self.W, self.H]], dtype=np.int64), np.zeros((1, 4), dtype=np.int32)]]
+            self.tile_mode = False
+        self.tasks = wm.build_tile_tasks(sets)
+        # ---- ownership: bands of grid-tile rows; strips / crosses follow the tile row their top edge lies in
+        grid = sets[0][0]
+        row_ys = np.unique(grid[:, 1])
+        tile_h = int(grid[0, 3] - grid[0, 1])
+        per = -(-len(row_ys) // world)
+        lo, hi = min(len(row_ys), rank * per), min(len(row_ys), (rank + 1) * per)
+        rows_of = [int(np.clip(int(b[1]) // tile_h, 0, len(row_ys) - 1)) for b, _, _ in self.tasks]
+        self.my_tasks = [i for i, r in enumerate(rows_of) if lo <= r < hi]
+        # ---- the patch rows this rank must infer: every patch whose output rows meet the y-range its tiles read
+        if self.my_tasks:
+            ya = max(0, min(int(self.tasks[i][0][1]) for i in self.my_tasks))
+            yb = min(self.H, max(int(self.tasks[i][0][3]) for i in self.my_tasks))
+            sel = (self.out_boxes[:, 3] > ya) & (self.out_boxes[:, 1] < yb)
+        else:
+            sel = np.zeros(len(self.out_boxes), dtype=bool)
+        self.my_patches = np.nonzero(sel)[0]
+        if len(self.my_patches):
+            self.canvas_y0 = int(self.out_boxes[self.my_patches, 1].min())
+            self.canvas_y1 = min(self.H, int(self.out_boxes[self.my_patches, 3].max()))
+            # image rows the band's patches read (may reach outside the slide: padded with 255)
+            self.read_y0 = int(self.in_boxes[self.my_patches, 1].min())
+            self.read_y1 = int(self.in_boxes[self.my_patches, 3].max())
+            self.read_x0 = int(self.in_boxes[self.my_patches, 0].min())
+            self.read_x1 = int(self.in_boxes[self.my_patches, 2].max())
+        else:
+            self.canvas_y0 = self.canvas_y1 = self.read_y0 = self.read_y1 = self.read_x0 = self.read_x1 = 0
+
+    def patch_rows(self):
+        """Yield (patch indices of one grid row) for this rank, top to bottom."""
+        if not len(self.my_patches):
+            return
+        ys = self.out_boxes[self.my_patches, 1]
+        for y in np.unique(ys):
+            yield self.my_patches[ys == y]
+
+
+class WsiTileModeMixin:
+    """`run(image, patch_mode=False)` for instance-segmentation engines.  The three device primitives are methods so that the host
+    logic (banding, stitching order, tile batching, gather, replay) can be exercised without a GPU by the gloo tests."""
+
+    tile_batch = 4   # same-shape tiles post-processed per device call
+    min_tile = 11    # smallest tile side tiab_hovernet_postproc accepts
+
+    # ---- device primitives -------------------------------------------------------------------------------------------------
+    def _wsi_forward(self, x: torch.Tensor) -> list[torch.Tensor]:
+        """uint8 (n, h, w, 3) device patches -> head maps [(n, oh, ow, C) float32] (preproc_func = stain normaliser runs on the device)."""
+        x = self._device_preproc(x)
+        outs = type(self.model).infer_batch_device(self.model, x, device=self.device)
+        return list(outs)
+
+    def _wsi_stitch_row(self, blocks: torch.Tensor, locs: np.ndarray, width: int, out: torch.Tensor) -> None:
+        """One patch row of head outputs -> rows of the head canvas (device overlap-add / count normalisation, csrc/stitch.cu)."""
+        from tiatoolbox_b200.models.engine.semantic_segmentor import stitch_patches
+
+        stitch_patches(blocks, locs, canvas_width=width, output_shape=(out.shape[0], out.shape[1]), out=out)
+
+    def _wsi_postproc(self, np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.Tensor | None):
+        """(n, h, w, C) head tiles -> (inst (n, h, w) int32, instance table) on the device (csrc/postproc.cu)."""
+        return pp.proc_np_hv_batch(np_map, hv_map, tp_map)
+
+    # ---- stages ------------------------------------------------------------------------------------------------------------
+    def _wsi_upload(self, image: np.ndarray, plan: WsiTilePlan) -> torch.Tensor:
+        """The image rows / columns the band's patches read, as one device uint8 tensor with a 255 border where patches leave the
+        slide (`read_bounds(..., pad_constant_values=255)`, dataset_abc.py:419-431)."""
+        y0, y1, x0, x1 = plan.read_y0, plan.read_y1, plan.read_x0, plan.read_x1
+        host = torch.full((y1 - y0, x1 - x0, 3), 255, dtype=torch.uint8)
+        if self.device.type == "cuda":
+            host = host.pin_memory()
+        sy0, sy1, sx0, sx1 = max(y0, 0), min(y1, plan.H), max(x0, 0), min(x1, plan.W)
+        host[sy0 - y0: sy1 - y0, sx0 - x0: sx1 - x0] = torch.from_numpy(image[sy0:sy1, sx0:sx1])
+        return host.to(self.device, non_blocking=True)
+
+    def _wsi_infer(self, band: torch.Tensor, plan: WsiTilePlan) -> list[torch.Tensor]:
+        """All patch rows of the band -> head canvases [(canvas rows, W, C) float32] in HBM."""
+        pw, ph = plan.patch_in
+        Wp = band.shape[1]
+        canvases: list[torch.Tensor] | None = None
+        rowbufs: list[torch.Tensor] | None = None
+        for idx in plan.patch_rows():
+            nx = len(idx)
+            ins, outs = plan.in_boxes[idx], plan.out_boxes[idx]
+            # strided view of the row's (overlapping) input windows: no host loop, the copy happens in .contiguous() per batch
+            yoff, xoff = int(ins[0, 1]) - plan.read_y0, int(ins[0, 0]) - plan.read_x0
+            sx = plan.stride[0]
+            base = band[yoff: yoff + ph]
+            view = base.as_strided((nx, ph, pw, 3), (sx * 3, Wp * 3, 3, 1), base.storage_offset() + xoff * 3)
+            for k0 in range(0, nx, self.batch_size):
+                k1 = min(nx, k0 + self.batch_size)
+                heads = self._wsi_forward(view[k0:k1].contiguous())
+                if canvases is None:   # head count / channels are known after the first forward (infer_wsi :581-589)
+                    ch = plan.canvas_y1 - plan.canvas_y0
+                    canvases = [torch.zeros((ch, plan.W, h.shape[3]), dtype=torch.float32, device=self.device) for h in heads]
+                if rowbufs is None or rowbufs[0].shape[0] < nx:
+                    rowbufs = [torch.empty((nx, *h.shape[1:]), dtype=torch.float32, device=self.device) for h in heads]
+                for buf, h in zip(rowbufs, heads):
+                    buf[k0:k1].copy_(h)
+            y0 = int(outs[0, 1]) - plan.canvas_y0
+            y1 = min(int(outs[0, 3]) - plan.canvas_y0, canvases[0].shape[0])
+            locs = outs.astype(np.int32)
+            for buf, canvas in zip(rowbufs, canvases):
+                self._wsi_stitch_row(buf[:nx], locs, plan.W, canvas[y0:y1])
+        return canvases or []
+
+    def _wsi_postproc_tiles(self, canvases: list[torch.Tensor], plan: WsiTilePlan, *, keep_maps: bool):
+        """This rank's tiles -> [(task index, tile instance dict, tile inst map (device int32) | None)] in task order."""
+        results = []
+        if not canvases:
+            return results
+        has_tp = len(canvases) > 2
+
+        def clipped(i):
+            x0, y0, x1, y1 = (int(v) for v in plan.tasks[i][0])
+            return max(x0, 0), max(y0, 0), min(x1, plan.W), min(y1, plan.H)
+
+        group: list[int] = []
+
+        def flush():
+            if not group:
+                return
+            tiles = []
+            for i in group:
+                x0, y0, x1, y1 = clipped(i)
+                tiles.append([c[y0 - plan.canvas_y0: y1 - plan.canvas_y0, x0:x1] for c in canvases])
+            stacks = [torch.stack([t[h] for t in tiles]).contiguous() for h in range(len(canvases))]
+            th, tw = stacks[0].shape[1:3]
+            if th < self.min_tile or tw < self.min_tile:
+                # a sliver left over at the slide's right / bottom edge: the device kernels (21-tap Sobel) need >= 11 px per side, so the
+                # sliver is extended with background (all heads 0) and the instance map cropped back
+                pad = (0, 0, 0, max(self.min_tile - tw, 0), 0, max(self.min_tile - th, 0))
+                stacks = [torch.nn.functional.pad(s, pad).contiguous() for s in stacks]
+            inst, table = self._wsi_postproc(stacks[0], stacks[1], stacks[2] if has_tp else None)
+            inst = inst[:, :th, :tw]
+            inst_h = inst.cpu().numpy()
+            tab = {k: v.cpu().numpy() for k, v in table.items()}
+            for j, i in enumerate(group):
+                info = pp.instance_info(inst_h[j], {k: v[j] for k, v in tab.items()}, with_contours=True)
+                results.append((i, {k + 1: rec for k, rec in enumerate(info.values())}, inst[j] if keep_maps else None))
+            group.clear()
+
+        shape = None
+        for i in plan.my_tasks:
+            x0, y0, x1, y1 = clipped(i)
+            s = (y1 - y0, x1 - x0)
+            if s[0] <= 0 or s[1] <= 0:
+                results.append((i, {}, None))
+                continue
+            if s != shape or len(group) >= self.tile_batch:
+                flush()
+                shape = s
+            group.append(i)
+        flush()
+        results.sort(key=lambda r: r[0])
+        return results
+
+    def _wsi_gather(self, results, plan: WsiTilePlan, *, keep_maps: bool):
+        """Exchange the per-tile results: object all-gather of the instance records, ONE tensor all-gather of the flattened instance
+        maps.  Returns {task index: (inst_dict, inst_map numpy | None)} on every rank."""
+        dist, rank, world = self._dist()
+        merged = {}
+        if dist is None:
+            for i, d, m in results:
+                merged[i] = (d, None if m is None else m.cpu().numpy())
+            return merged
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [(i, d, None if m is None else tuple(m.shape)) for i, d, m in results])
+        maps_by_rank = [None] * world
+        if keep_maps:
+            flat = [m.reshape(-1) for _, _, m in results if m is not None]
+            mine = torch.cat(flat) if flat else torch.empty(0, dtype=torch.int32, device=self.device)
+            n = torch.tensor([mine.numel()], dtype=torch.long, device=self.device)
+            sizes = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(sizes, n)
+            cap = max(int(s.item()) for s in sizes)
+            padded = torch.zeros(max(cap, 1), dtype=torch.int32, device=self.device)
+            padded[: mine.numel()] = mine
+            out = torch.empty(world * max(cap, 1), dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(out, padded)
+            out = out.view(world, -1).cpu().numpy()
+            maps_by_rank = [out[r, : int(sizes[r].item())] for r in range(world)]
+        for r, part in enumerate(gathered):
+            off = 0
+            for i, d, shp in part:
+                m = None
+                if shp is not None and keep_maps:
+                    cnt = int(shp[0]) * int(shp[1])
+                    m = maps_by_rank[r][off: off + cnt].reshape(shp)
+                    off += cnt
+                merged[i] = (d, m)
+        return merged
+
+    def _wsi_replay(self, merged: dict, plan: WsiTilePlan, *, return_predictions: bool) -> dict:
+        """`_process_tile_mode`'s merge loop (:1230-1279) over all tiles in task order -> the task's output entries."""
+        store = wm.WsiInstanceStore()
+        wsi_pred = np.zeros((plan.H, plan.W), dtype=np.int32) if return_predictions else None
+        max_inst = None
+        for i, (bounds, flag, mode) in enumerate(plan.tasks):
+            inst_dict, inst_map = merged.get(i, ({}, None))
+            if wsi_pred is not None and inst_map is not None:
+                max_inst = wm.update_tile_based_predictions_array(inst_map, wsi_pred, bounds, (0, 0), max_inst)
+            if plan.tile_mode:
+                store.merge_tile(inst_dict, tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin)
+            else:   # `_process_full_wsi` :999-1076: one postproc call over the whole map, nothing to merge
+                for rec in inst_dict.values():
+                    store._append(rec)  # noqa: SLF001
+        out = dict(store.to_info_dict())
+        if wsi_pred is not None:
+            out["predictions"] = wsi_pred
+        return out
+
+    # ---- entry ---------------------------------------------------------------------------------------------------------------
+    def run_wsi(self, image: np.ndarray, *, ioconfig=None, return_predictions: bool = False, return_probabilities: bool = False) -> dict:
+        """One in-memory slide / region (H, W, 3) uint8 -> {"box", "centroid", "contours", "prob", "type": object arrays over the merged
+        instances in WSI coordinates (absent when nothing was found, like the reference), "coordinates": (N, 4) patch input boxes,
+        ["predictions": (H, W) int32 instance map], ["probabilities": [np, hv, tp] WSI head maps (single-rank runs only)]}."""
+        image = np.ascontiguousarray(image)
+        if image.ndim != 3 or image.shape[2] != 3 or image.dtype != np.uint8:  # noqa: PLR2004
+            msg = "WSI mode expects an in-memory (H, W, 3) uint8 array (slide files are read by WSIReader, outside the B200 path)"
+            raise ValueError(msg)
+        io = ioconfig or self.ioconfig
+        if io is None or io.patch_output_shape is None:
+            msg = "an ioconfig with patch_input_shape / patch_output_shape / stride_shape is required for WSI mode"
+            raise ValueError(msg)
+        dist, rank, world = self._dist()
+        plan = WsiTilePlan((image.shape[1], image.shape[0]), io, rank, world)
+        self.model._plan_batch = self.batch_size  # noqa: SLF001
+        canvases = []
+        if len(plan.my_patches):
+            band = self._wsi_upload(image, plan)
+            canvases = self._wsi_infer(band, plan)
+            del band
+        results = self._wsi_postproc_tiles(canvases, plan, keep_maps=return_predictions)
+        merged = self._wsi_gather(results, plan, keep_maps=return_predictions)
+        out = self._wsi_replay(merged, plan, return_predictions=return_predictions)
+        out["coordinates"] = plan.in_boxes
+        if return_probabilities:
+            if world > 1:
+                msg = "return_probabilities in WSI mode is only available on a single rank (the head maps are not gathered)"
+                raise NotImplementedError(msg)
+            out["probabilities"] = [c.cpu().numpy() for c in canvases]
+        return out

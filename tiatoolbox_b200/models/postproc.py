@@ -71,7 +71,7 @@ def instance_info(inst_map: np.ndarray, table_row: dict, offset=(0, 0), with_con
             contour = np.squeeze(contour)
             if contour.shape[0] < 3 or len(contour.shape) != 2:  # hovernet.py:696-701
                 continue
-            rec["contours"] = contour + (box[:2] + offset)[None]
+            rec["contours"] = (contour + (box[:2] + offset)[None]).astype(np.int32)   # hovernet.py:705 adds in place: stays int32
         rec["centroid"] = table_row["centroid"][k] + offset
         box[:2] += offset
         box[2:] += offset
