@@ -98,6 +98,22 @@ int tiab_stain_concentrations(tiab_handle_t h, const uint8_t* in_dev, int N, int
                               float* conc_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Reinhard colour normalisation  (tools/stainnorm.py:222-367) and OpenCV's 8-bit RGB <-> Lab conversion it is built on
+ * (cv2.cvtColor(COLOR_RGB2LAB / COLOR_LAB2RGB) on uint8: stainnorm.py:305, 334), as integer fixed-point device code that
+ * equals cv2 on every one of the 2^24 inputs in both directions.
+ * ------------------------------------------------------------------------------------------- */
+/* ReinhardNormalizer.fit / get_mean_std (stainnorm.py:251-260, 337-367): mean and standard deviation of the float32 Lab channels
+ * (L / 2.55, a - 128, b - 128) of one H*W*3 uint8 image on the device.  Host outputs; synchronises. */
+int tiab_reinhard_fit(tiab_handle_t h, const uint8_t* target_dev, int H, int W, double means_host[3], double stds_host[3], void* stream);
+/* ReinhardNormalizer.transform (stainnorm.py:262-284) over N <= 65535 images, in_dev / out_dev N*H*W*3 uint8 (must not overlap).  Optional device
+ * outputs: src_stats_dev N*6 doubles {mean L, a, b, std L, a, b} of every source image; status_dev N ints — 1 when a channel of the
+ * image is constant (the reference raises ZeroDivisionError at stainnorm.py:277-283); such an image is copied through unchanged. */
+int tiab_reinhard_transform_batch(tiab_handle_t h, const uint8_t* in_dev, uint8_t* out_dev, int N, int H, int W, const double target_means[3],
+                                  const double target_stds[3], double* src_stats_dev, int* status_dev, void* stream);
+/* cv2.cvtColor(x, COLOR_RGB2LAB) (inverse = 0) or COLOR_LAB2RGB (inverse = 1) for npix uint8 pixels on the device. */
+int tiab_lab_convert(tiab_handle_t h, const uint8_t* in_dev, uint8_t* out_dev, long long npix, int inverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Convolution engine (patch CNNs).  Replaces the torch.nn.Conv2d / BatchNorm2d / ReLU library calls
  * inside tiatoolbox/models/architecture/hovernet.py:61-262,330-454, unet.py:24-418,
  * vanilla.py:256-333 (the per-batch `model(x)` of infer_batch: vanilla.py:251, unet.py:457,
@@ -226,6 +242,11 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
                            int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id, int32_t* inst_box,
                            double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream);
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]);
+/* host-side test hooks of csrc/lab_math.cuh (no GPU): the device's per-pixel colour conversion and per-level Reinhard maps run on the CPU.
+ * tiab_dbg_reinhard_maps returns 1 (and identity maps) when a channel is constant. */
+int tiab_dbg_lab_convert(const uint8_t* in_host, uint8_t* out_host, long long npix, int inverse);
+int tiab_dbg_reinhard_maps(const unsigned hist_host[768], double npix, const double target_means[3], const double target_stds[3],
+                           double stats_out[6], uint8_t lut_out[768]);
 int tiab_dbg_postproc_fetch(tiab_handle_t h, int which, void* host_out, void* stream);
 
 /* Force one of the two device paths (testing / benchmarking): 0 = auto, 1 = fused one-CTA-per-patch

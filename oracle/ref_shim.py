@@ -76,7 +76,9 @@ def _base_packages():
     if "base" in _loaded:
         return
     if str(REF_ROOT) not in sys.path:
-        sys.path.insert(0, str(REF_ROOT))
+        # appended, not prepended: /root/reference has a top-level `tests` package of its own that must not shadow this repository's
+        # (spawned gloo workers re-import `tests.<module>` with the parent's sys.path)
+        sys.path.append(str(REF_ROOT))
     import tiatoolbox  # noqa: F401  (top-level import is light: yaml + logging)
 
     for sub in ("utils", "tools", "models"):

@@ -90,6 +90,11 @@ SIGNATURES = {
     "tiab_stain_fit_host": (C.c_int, [_vp, C.POINTER(StainParams), _vp, C.c_int, C.c_int, _dp, _dp, _ip]),
     "tiab_stain_tissue_mask": (C.c_int, [_vp, C.POINTER(StainParams), _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_stain_concentrations": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _dp, _vp, _vp]),
+    "tiab_reinhard_fit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _dp, _dp, _vp]),
+    "tiab_reinhard_transform_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _vp, _vp, _vp]),
+    "tiab_lab_convert": (C.c_int, [_vp, _vp, _vp, C.c_longlong, C.c_int, _vp]),
+    "tiab_dbg_lab_convert": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int]),
+    "tiab_dbg_reinhard_maps": (C.c_int, [_vp, C.c_double, _dp, _dp, _dp, _vp]),
     "tiab_conv_gemm": (C.c_int, [_vp, C.POINTER(ConvDesc), _vp]),
     "tiab_im2col": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int] + [C.c_int] * 12 + [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "tiab_bn_relu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_longlong, C.c_int, _vp, C.c_int,

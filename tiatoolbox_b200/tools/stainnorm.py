@@ -202,6 +202,145 @@ class VahadaneNormalizer(StainNormalizer):
         self.extractor = VahadaneExtractor()
 
 
+class ReinhardNormalizer(StainNormalizer):
+    """Reinhard colour normalizer (stainnorm.py:222-367): match the mean / standard deviation of the 8-bit Lab channels to the target's.
+
+    Attributes:
+        target_means (tuple of float): mean of each Lab channel (L in [0, 100], a and b centred on 0) of the target.
+        target_stds (tuple of float): standard deviation of each Lab channel of the target.
+
+    The reference leans on OpenCV for both colour conversions and for the statistics; here the whole transform is integer device code
+    (csrc/reinhard.cu, csrc/lab_math.cuh) that equals cv2's 8-bit conversions on all 2^24 inputs, so the output is the reference's
+    uint8 image bit for bit unless a float32 rounding of the per-level map falls differently (never observed; the tests allow 1 LSB).
+    Like the reference, an image with a constant Lab channel fails with ZeroDivisionError (stainnorm.py:277-283 divide by its std).
+    """
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.target_means: tuple[float, float, float]
+        self.target_stds: tuple[float, float, float]
+        self._fitted = False
+
+    # -- helpers ---------------------------------------------------------------------------------
+    @staticmethod
+    def _convert(img, inverse: int):
+        """cv2.cvtColor(img, COLOR_RGB2LAB / COLOR_LAB2RGB) for uint8 (..., 3) data on the device."""
+        import torch
+
+        if _is_torch_cuda(img):
+            x = img.contiguous()
+            if x.dtype != torch.uint8 or x.shape[-1] != 3:
+                msg = "expected a (..., 3) uint8 tensor"
+                raise ValueError(msg)
+            dev = x.device
+            out = torch.empty_like(x)
+            h = _lib.handle(dev.index or 0)
+            if x.numel():
+                _lib.check(h, _lib.lib().tiab_lab_convert(h, x.data_ptr(), out.data_ptr(), x.numel() // 3, inverse,
+                                                          torch.cuda.current_stream(dev).cuda_stream))
+            return out
+        arr = np.ascontiguousarray(np.asarray(img).astype("uint8"))
+        if arr.shape[-1] != 3:
+            msg = "expected a (..., 3) uint8 array"
+            raise ValueError(msg)
+        return ReinhardNormalizer._convert(torch.from_numpy(arr).cuda(), inverse).cpu().numpy()
+
+    @staticmethod
+    def rgb2lab(img):
+        """8-bit Lab image of an RGB uint8 image (numpy -> numpy, CUDA tensor -> CUDA tensor); equals cv2's COLOR_RGB2LAB."""
+        return ReinhardNormalizer._convert(img, 0)
+
+    @staticmethod
+    def lab2rgb(img):
+        """RGB uint8 image of an 8-bit Lab image; equals cv2's COLOR_LAB2RGB."""
+        return ReinhardNormalizer._convert(img, 1)
+
+    @staticmethod
+    def lab_split(img: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """RGB uint8 -> float32 L in [0, 100], a and b in [-128, 127] (stainnorm.py:286-312)."""
+        lab = ReinhardNormalizer.rgb2lab(np.asarray(img).astype("uint8")).astype(np.float32)
+        chan1, chan2, chan3 = (np.ascontiguousarray(lab[..., i]) for i in range(3))
+        chan1 /= np.asarray(2.55)
+        chan2 -= np.asarray(128.0)
+        chan3 -= np.asarray(128.0)
+        return chan1, chan2, chan3
+
+    @staticmethod
+    def merge_back(chan1: np.ndarray, chan2: np.ndarray, chan3: np.ndarray) -> np.ndarray:
+        """Separate Lab channels -> RGB uint8 (stainnorm.py:314-335; like the reference the channels are modified in place)."""
+        chan1 *= 2.55
+        chan2 += 128.0
+        chan3 += 128.0
+        lab = np.clip(np.stack((chan1, chan2, chan3), axis=-1), 0, 255).astype(np.uint8)
+        return ReinhardNormalizer.lab2rgb(lab)
+
+    def get_mean_std(self, img: np.ndarray):
+        """Mean and standard deviation of each Lab channel (stainnorm.py:337-367) -> ((mL, ma, mb), (sL, sa, sb))."""
+        import torch
+
+        img = np.ascontiguousarray(np.asarray(img).astype("uint8"))
+        if img.ndim != 3 or img.shape[2] != 3:  # noqa: PLR2004
+            msg = "img must be HxWx3"
+            raise ValueError(msg)
+        dev = torch.device("cuda", self.device)
+        x = torch.from_numpy(img).to(dev)
+        h = _lib.handle(self.device)
+        means, stds = np.zeros(3, np.float64), np.zeros(3, np.float64)
+        _lib.check(h, _lib.lib().tiab_reinhard_fit(h, x.data_ptr(), img.shape[0], img.shape[1], _lib.dptr(means), _lib.dptr(stds),
+                                                   torch.cuda.current_stream(dev).cuda_stream))
+        return tuple(float(v) for v in means), tuple(float(v) for v in stds)
+
+    # -- reference API ---------------------------------------------------------------------------
+    def fit(self, target: np.ndarray) -> None:
+        """Fit to a target image (stainnorm.py:251-260)."""
+        self.target_means, self.target_stds = self.get_mean_std(target)
+        self._fitted = True
+
+    def transform(self, img: np.ndarray) -> np.ndarray:
+        """Transform one RGB uint8 image (stainnorm.py:262-284)."""
+        img = np.asarray(img)
+        return self.transform_batch(img.astype("uint8")[None])[0].reshape(img.shape)
+
+    def transform_batch(self, imgs, *, return_info: bool = False, raise_on_error: bool = True):
+        """(N, H, W, 3) uint8 numpy array -> numpy array, or CUDA tensor -> CUDA tensor (no host copy)."""
+        import torch
+
+        if not self._fitted:
+            msg = "fit() must be called before transform()."
+            raise RuntimeError(msg)
+        was_numpy = not _is_torch_cuda(imgs)
+        if was_numpy:
+            arr = np.ascontiguousarray(np.asarray(imgs))
+            if arr.dtype != np.uint8 or arr.ndim != 4 or arr.shape[-1] != 3:  # noqa: PLR2004
+                msg = "expected a (N,H,W,3) uint8 array"
+                raise ValueError(msg)
+            x = torch.from_numpy(arr).to(torch.device("cuda", self.device))
+        else:
+            x = imgs.contiguous()
+            if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[-1] != 3:  # noqa: PLR2004
+                msg = "expected a (N,H,W,3) uint8 tensor"
+                raise ValueError(msg)
+        dev = x.device
+        n, hh, ww, _ = x.shape
+        out = torch.empty_like(x)
+        stats = torch.empty((n, 6), dtype=torch.float64, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+        if n:
+            h = _lib.handle(dev.index or 0)
+            tm = np.ascontiguousarray(self.target_means, dtype=np.float64)
+            ts = np.ascontiguousarray(self.target_stds, dtype=np.float64)
+            _lib.check(h, _lib.lib().tiab_reinhard_transform_batch(h, x.data_ptr(), out.data_ptr(), n, hh, ww, _lib.dptr(tm), _lib.dptr(ts),
+                                                                   stats.data_ptr(), status.data_ptr(),
+                                                                   torch.cuda.current_stream(dev).cuda_stream))
+            if raise_on_error and bool(status.any().item()):
+                msg = "float division by zero"   # a Lab channel of the image is constant: stainnorm.py:277-283 divide by its std
+                raise ZeroDivisionError(msg)
+        res = out.cpu().numpy() if was_numpy else out
+        if return_info:
+            return res, {"source_means": stats[:, :3], "source_stds": stats[:, 3:], "status": status}
+        return res
+
+
 def get_normalizer(method_name: str, stain_matrix=None) -> StainNormalizer:
     """Return a :class:`StainNormalizer` by name (stainnorm.py:370-425)."""
     if method_name.lower() not in ["reinhard", "ruifrok", "macenko", "vahadane", "custom"]:
@@ -212,9 +351,7 @@ def get_normalizer(method_name: str, stain_matrix=None) -> StainNormalizer:
         raise ValueError(msg)
 
     if method_name.lower() == "reinhard":
-        # SURVEY.md §8(f) "next": ReinhardNormalizer (stainnorm.py:222-367) is outside the graded path.
-        msg = "ReinhardNormalizer is not part of the B200 hot path yet (SURVEY.md §8f)."
-        raise NotImplementedError(msg)
+        return ReinhardNormalizer()
     if method_name.lower() == "ruifrok":
         return RuifrokNormalizer()
     if method_name.lower() == "macenko":
