@@ -97,6 +97,12 @@ int tiab_stain_tissue_mask(tiab_handle_t h, const tiab_stain_params_t* p, const 
 int tiab_stain_concentrations(tiab_handle_t h, const uint8_t* in_dev, int N, int H, int W, const double M[6],
                               float* conc_dev, void* stream);
 
+/* StainAugmentor.augment (tools/stainaugment.py:171-206): out = uint8(clip(255 * exp(-(C' . M)), 0, 255)) with
+ * C'[:, i] = C[:, i] * alpha[i] + beta[i] on the pixels where mask_dev != 0 (mask_dev = NULL: every pixel, `augment_background=True`).
+ * conc_dev npix*2 float32 (tiab_stain_concentrations), mask_dev npix bytes (tiab_stain_tissue_mask), out_dev npix*3 uint8. */
+int tiab_stain_augment(tiab_handle_t h, const float* conc_dev, const uint8_t* mask_dev, long long npix, const double M[6],
+                       const double alpha[2], const double beta[2], uint8_t* out_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Reinhard colour normalisation  (tools/stainnorm.py:222-367) and OpenCV's 8-bit RGB <-> Lab conversion it is built on
  * (cv2.cvtColor(COLOR_RGB2LAB / COLOR_LAB2RGB) on uint8: stainnorm.py:305, 334), as integer fixed-point device code that

@@ -275,3 +275,25 @@ def load_wsi_merge():
     exec(compile("\n\n".join(parts), "multi_task_segmentor.py[wsi merge]", "exec"), mod.__dict__)  # noqa: S102
     _loaded["wsi_merge"] = mod
     return mod
+
+
+def load_stainaugment():
+    """The reference's `tiatoolbox.tools.stainaugment` module, unmodified, with albumentations' `ImageOnlyTransform` base class (absent
+    here) replaced by a two-argument stand-in — the reference only uses its constructor (stainaugment.py:111)."""
+    if "stainaugment" in _loaded:
+        return _loaded["stainaugment"]
+    load_stain()
+
+    class ImageOnlyTransform:
+        def __init__(self, always_apply=False, p=0.5):
+            self.always_apply, self.p = always_apply, p
+
+    if "albumentations" not in sys.modules:
+        a = _stub("albumentations")
+        a.__path__ = []
+        c = _stub("albumentations.core")
+        c.__path__ = []
+        _stub("albumentations.core.transforms_interface", ImageOnlyTransform=ImageOnlyTransform)
+    mod = importlib.import_module("tiatoolbox.tools.stainaugment")
+    _loaded["stainaugment"] = mod
+    return mod

@@ -316,3 +316,25 @@ def transform_float(method, img, m_target, max_c_target, stain_matrix=None, *, d
 
 def transform(method, img, m_target, max_c_target, stain_matrix=None):
     return transform_float(method, img, m_target, max_c_target, stain_matrix).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------
+# tools/stainaugment.py:143-206 StainAugmentor.fit / augment with the random draws made explicit
+# ---------------------------------------------------------------------------------------
+
+
+def augment(img: np.ndarray, stain_matrix: np.ndarray, alphas, betas, *, threshold: float = 0.85, augment_background: bool = False) -> np.ndarray:
+    """`fit(img, threshold)` followed by `augment()` for given per-stain (alpha_i, beta_i) (the reference draws them in `get_params`,
+    stainaugment.py:231-236, once per stain inside the loop of :189-196)."""
+    conc = get_concentrations(np.array(img, copy=True), stain_matrix).copy()
+    if augment_background:
+        for i in range(conc.shape[1]):
+            conc[:, i] *= alphas[i]
+            conc[:, i] += betas[i]
+    else:
+        mask = get_luminosity_tissue_mask(img, threshold).ravel()
+        for i in range(conc.shape[1]):
+            conc[mask, i] *= alphas[i]
+            conc[mask, i] += betas[i]
+    out = 255 * np.exp(-1 * np.dot(conc, stain_matrix))
+    return np.clip(out.reshape(img.shape), 0, 255).astype(np.uint8)

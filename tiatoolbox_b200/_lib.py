@@ -90,6 +90,7 @@ SIGNATURES = {
     "tiab_stain_fit_host": (C.c_int, [_vp, C.POINTER(StainParams), _vp, C.c_int, C.c_int, _dp, _dp, _ip]),
     "tiab_stain_tissue_mask": (C.c_int, [_vp, C.POINTER(StainParams), _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_stain_concentrations": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _dp, _vp, _vp]),
+    "tiab_stain_augment": (C.c_int, [_vp, _vp, _vp, C.c_longlong, _dp, _dp, _dp, _vp, _vp]),
     "tiab_reinhard_fit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _dp, _dp, _vp]),
     "tiab_reinhard_transform_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _vp, _vp, _vp]),
     "tiab_lab_convert": (C.c_int, [_vp, _vp, _vp, C.c_longlong, C.c_int, _vp]),
