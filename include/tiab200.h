@@ -247,7 +247,13 @@ int tiab_stitch_patches(tiab_handle_t h, const float* blocks_dev, int N, int bh,
 int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
                            int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id, int32_t* inst_box,
                            double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream);
+/* The same with HoVerNet._proc_np_hv's `scale_factor` (hovernet.py:506, 564-565): Sobel size int(20 * scale_factor + 1) and marker
+ * size threshold ceil(10 * scale_factor^2) - 1.  Supported: 1.0 (HoVer-Net) and 0.5 (HoVerNetPlus.postproc, hovernetplus.py:305). */
+int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
+                                  double scale_factor, int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id,
+                                  int32_t* inst_box, double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream);
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]);
+int tiab_dbg_sobel_kernels_k(int ksize, double* deriv, double* smooth);
 /* host-side test hooks of csrc/lab_math.cuh (no GPU): the device's per-pixel colour conversion and per-level Reinhard maps run on the CPU.
  * tiab_dbg_reinhard_maps returns 1 (and identity maps) when a channel is constant. */
 int tiab_dbg_lab_convert(const uint8_t* in_host, uint8_t* out_host, long long npix, int inverse);

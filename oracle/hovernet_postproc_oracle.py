@@ -66,8 +66,8 @@ def watershed(image: np.ndarray, markers: np.ndarray, mask: np.ndarray) -> np.nd
     return out
 
 
-def proc_np_hv(np_map: np.ndarray, hv_map: np.ndarray, *, debug: dict | None = None) -> np.ndarray:
-    """HoVerNet._proc_np_hv with scale_factor = 1 (hovernet.py:536-616)."""
+def proc_np_hv(np_map: np.ndarray, hv_map: np.ndarray, *, debug: dict | None = None, scale_factor: float = 1.0) -> np.ndarray:
+    """HoVerNet._proc_np_hv (hovernet.py:536-616); scale_factor 1 for HoVer-Net, 0.5 for HoVerNetPlus (hovernetplus.py:305)."""
     blb_raw = np_map[..., 0]
     h_dir_raw = hv_map[..., 0]
     v_dir_raw = hv_map[..., 1]
@@ -77,8 +77,8 @@ def proc_np_hv(np_map: np.ndarray, hv_map: np.ndarray, *, debug: dict | None = N
     blb[blb > 0] = 1
     h_dir = cv2.normalize(h_dir_raw, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
     v_dir = cv2.normalize(v_dir_raw, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
-    ksize = 21
-    obj_size = math.ceil(10 * 1.0)
+    ksize = int((20 * scale_factor) + 1)
+    obj_size = math.ceil(10 * (scale_factor**2))
     sobel_h = cv2.Sobel(h_dir, cv2.CV_64F, 1, 0, ksize=ksize)
     sobel_v = cv2.Sobel(v_dir, cv2.CV_64F, 0, 1, ksize=ksize)
     sobel_h = 1 - cv2.normalize(sobel_h, None, alpha=0, beta=1, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
@@ -146,6 +146,69 @@ def get_instance_info(pred_inst: np.ndarray, pred_type: np.ndarray | None = None
             rec["type"] = int(t)
             rec["prob"] = float(dict(order)[t] / (np.sum(m) + 1.0e-6))
     return info
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HoVerNetPlus (architecture/hovernetplus.py): layer-segmentation clean-up, layer contours, two-task postproc
+# ---------------------------------------------------------------------------------------------------------------------
+def remove_small_objects_bool(mask: np.ndarray, max_size: int) -> np.ndarray:
+    """skimage.morphology.remove_small_objects for a BOOLEAN array: connected components (1-connectivity, like ndimage.label's default)
+    of at most max_size pixels are cleared."""
+    lab = ndimage.label(mask)[0]
+    sizes = np.bincount(lab.ravel())
+    small = sizes <= max_size
+    small[0] = False
+    out = mask.copy()
+    out[small[lab]] = False
+    return out
+
+
+def proc_ls(ls_map: np.ndarray) -> np.ndarray:
+    """HoVerNetPlus._proc_ls (hovernetplus.py:135-194)."""
+    ls_map = np.around(np.squeeze(ls_map)).astype("uint8")
+    min_size, kernel_size = 20000, 20
+    epith_all = np.where(ls_map >= 2, 1, 0).astype("uint8") > 0
+    mask = np.where(ls_map >= 1, 1, 0).astype("uint8")
+    epith_mask = remove_small_objects_bool(epith_all, max_size=min_size - 1).astype("uint8")
+    epith_edited = (epith_mask * ls_map).astype("uint8")
+    epith_edited_open = np.zeros_like(epith_edited).astype("uint8")
+    k = np.ones((kernel_size, kernel_size))
+    for i in [3, 2, 4]:
+        tmp = np.where(epith_edited == i, 1, 0).astype("uint8")
+        ep_open = cv2.morphologyEx(cv2.morphologyEx(tmp, cv2.MORPH_CLOSE, k), cv2.MORPH_OPEN, k)
+        epith_edited_open[ep_open == 1] = i
+    mask_open = cv2.morphologyEx(cv2.morphologyEx(mask, cv2.MORPH_CLOSE, k), cv2.MORPH_OPEN, k).astype("uint8")
+    out = mask_open.copy()
+    for i in range(2, 5):
+        out[epith_edited_open == i] = i
+    return out.astype("uint8")
+
+
+def get_layer_info(pred_layer: np.ndarray, offset=(0, 0)) -> dict:
+    """HoVerNetPlus._get_layer_info (hovernetplus.py:197-264)."""
+    info, count = {}, 1
+    for type_class in [v for v in np.unique(pred_layer) if v != 0]:
+        layer = np.where(pred_layer == type_class, 1, 0).astype("uint8")
+        bounding_box = get_bounding_box(layer)
+        contours, _ = cv2.findContours(layer, cv2.RETR_TREE, cv2.CHAIN_APPROX_NONE)
+        for cont in contours:
+            sq = np.squeeze(cont)
+            if sq.shape[0] < 3 or len(sq.shape) != 2:
+                continue
+            box = bounding_box.copy()
+            box[:2] = box[:2] + offset
+            box[2:] = box[2:] + offset
+            info[count] = {"box": box, "contours": cont[:, 0, :] + offset, "type": type_class}
+            count += 1
+    return info
+
+
+def postproc_plus(np_map, hv_map, tp_map, ls_map, offset=(0, 0)):
+    """HoVerNetPlus.postproc (hovernetplus.py:267-410) -> (inst_map, nucleus info dict, layer map, layer info dict)."""
+    inst = proc_np_hv(np_map, hv_map, scale_factor=0.5)
+    layer = proc_ls(ls_map)
+    pred_type = np.around(tp_map).astype("uint8")
+    return inst, get_instance_info(inst, pred_type, offset), layer, get_layer_info(layer, offset)
 
 
 def postproc(np_map, hv_map, tp_map=None, offset=(0, 0)):

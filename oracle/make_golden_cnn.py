@@ -44,6 +44,72 @@ def make_hovernet() -> None:
     print("hovernet golden:", {k: v.shape for k, v in out.items()})
 
 
+def synthetic_layer_map(h: int = 400, w: int = 420, seed: int = 0) -> np.ndarray:
+    """A 5-class layer map (0 background, 1 other tissue, 2 basal, 3 core epithelium, 4 keratin) made of bands + islands + speckle, as the
+    float32 argmax head HoVerNetPlus.infer_batch returns (H, W, 1)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    m = np.zeros((h, w), np.uint8)
+    m[40:, :] = 1
+    wave = (30 * np.sin(xx / 40.0)).astype(int)
+    m[(yy > 120 + wave) & (yy < 330 + wave)] = 3
+    m[(yy > 120 + wave) & (yy < 150 + wave)] = 2
+    m[(yy > 290 + wave) & (yy < 330 + wave)] = 4
+    m[60:80, 30:60] = 3            # small epithelium island (< 20 000 px): removed
+    m[200:215, 100:118] = 1        # hole in the epithelium smaller than the 20x20 closing
+    speck = rng.random((h, w)) < 0.01
+    m[speck] = rng.integers(0, 5, int(speck.sum()))
+    return m.astype(np.float32)[..., None]
+
+
+def make_hovernetplus() -> None:
+    """HoVerNetPlus (hovernetplus-oed shape: 3 nucleus types, 5 layers): BN calibration, reference logits / heads, reference postproc."""
+    import importlib
+    import sys
+
+    from oracle import hovernet_postproc_oracle as po
+    from oracle import ref_shim
+    from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_spec
+    from tiatoolbox_b200.synthetic import he_tiles, hovernet_head_maps
+
+    ref_shim.load_models()
+    hp = importlib.import_module("tiatoolbox.models.architecture.hovernetplus")
+    nt, nl = 3, 5
+    sd = seeded_state_dict(hovernet_spec(3, nt, "fast", nl), seed=0)
+    xcal = torch.from_numpy(he_tiles(2, 256, 256, seed=100)).permute(0, 3, 1, 2).float()
+    stats = calibrate(sd, lambda s, x: hovernet_forward_reference(s, x, "fast", nt, num_layers=nl), xcal)
+    np.savez_compressed(GOLDEN / "hovernetplus_bn_calib.npz", **{k: v.numpy() for k, v in stats.items()})
+    net = hp.HoVerNetPlus(num_types=nt, num_layers=nl).eval()
+    net.load_state_dict(sd)
+    tiles = he_tiles(2, 256, 256, seed=0)
+    out = {}
+    with torch.inference_mode():
+        raw = net(torch.from_numpy(tiles).permute(0, 3, 1, 2).float())
+    heads = hp.HoVerNetPlus.infer_batch(net, torch.from_numpy(tiles), device="cpu")
+    for k, v in raw.items():
+        out[f"logits_{k}"] = _f16(v.permute(0, 2, 3, 1))[:, ::2, ::2]
+    for k, v in zip(("np", "hv", "tp", "ls"), heads):
+        out[f"head_{k}"] = np.asarray(v, dtype=np.float32)[:1]
+    # reference post-processing (two restated scikit-image functions injected) on synthetic head maps + a synthetic layer map
+    hn = ref_shim.load_models().hovernet
+    hn.remove_small_objects, hn.watershed = po.remove_small_objects, po.watershed
+    sys.modules["skimage.morphology"].remove_small_objects = po.remove_small_objects_bool
+    npm, hvm, tpm = hovernet_head_maps(1, 164, seed=4)
+    ls = synthetic_layer_map()
+    out["pp_ls_in"] = ls
+    out["pp_layer"] = hp.HoVerNetPlus._proc_ls(ls)
+    out["pp_inst"] = hp.HoVerNetPlus._proc_np_hv(npm[0], hvm[0], scale_factor=0.5)
+    linfo = hp.HoVerNetPlus._get_layer_info(out["pp_layer"], (3, 7))
+    out["pp_layer_types"] = np.array([int(r["type"]) for r in linfo.values()])
+    out["pp_layer_boxes"] = np.array([r["box"] for r in linfo.values()])
+    out["pp_layer_contour_lens"] = np.array([len(r["contours"]) for r in linfo.values()])
+    out["pp_layer_contour0"] = np.asarray(next(iter(linfo.values()))["contours"])
+    np.savez_compressed(GOLDEN / "hovernetplus_golden.npz", **out)
+    print("hovernetplus golden:", {k: v.shape for k, v in out.items()}, "layer classes", np.unique(out["pp_layer"]), "instances",
+          int(out["pp_inst"].max()))
+
+
 def make_cnn() -> None:
     GOLDEN.mkdir(parents=True, exist_ok=True)
     make_hovernet()

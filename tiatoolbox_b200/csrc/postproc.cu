@@ -70,8 +70,12 @@ struct PPWork {  // all arrays are [N * P] unless noted
   int* itype;          // [N*maxI*PP_MAX_TYPES]
 };
 
-__constant__ double c_sobel_d[21];
+__constant__ double c_sobel_d[21];     // ksize 21 (scale_factor 1)
 __constant__ double c_sobel_s[21];
+__constant__ double c_sobel_d11[11];   // ksize 11 (scale_factor 0.5: HoVerNet+, hovernetplus.py:305)
+__constant__ double c_sobel_s11[11];
+template <int K> __device__ __forceinline__ const double* sobel_d() { return K == 21 ? c_sobel_d : c_sobel_d11; }
+template <int K> __device__ __forceinline__ const double* sobel_s() { return K == 21 ? c_sobel_s : c_sobel_s11; }
 
 __device__ __forceinline__ int refl101(int i, int n) {
   if (i < 0) i = -i;
@@ -285,22 +289,25 @@ __global__ void pp_normalize_hv(const float* __restrict__ hv, int P, long long t
   }
 }
 // Sobel rows: rowh = deriv along x of h, rowv = smooth along x of v   (generic RowFilter: s = k[0]*S[0]; s += k[i]*S[i])
+template <int K>
 __global__ void pp_sobel_rows(const float* __restrict__ hn, const float* __restrict__ vn, int H, int W, long long total,
                               double* __restrict__ rowh, double* __restrict__ rowv) {
+  const double* kd = sobel_d<K>();
+  const double* ks = sobel_s<K>();
   PP_GRID_LOOP(i, total) {
     const int x = (int)(i % W);
     const long long rowbase = i - x;
     double sh = 0.0, sv = 0.0;
 #pragma unroll
-    for (int k = 0; k < 21; ++k) {
-      const int xx = refl101(x + k - 10, W);
+    for (int k = 0; k < K; ++k) {
+      const int xx = refl101(x + k - K / 2, W);
       const double a = (double)hn[rowbase + xx], b = (double)vn[rowbase + xx];
       if (k == 0) {
-        sh = __dmul_rn(c_sobel_d[0], a);
-        sv = __dmul_rn(c_sobel_s[0], b);
+        sh = __dmul_rn(kd[0], a);
+        sv = __dmul_rn(ks[0], b);
       } else {
-        sh = __dadd_rn(sh, __dmul_rn(c_sobel_d[k], a));
-        sv = __dadd_rn(sv, __dmul_rn(c_sobel_s[k], b));
+        sh = __dadd_rn(sh, __dmul_rn(kd[k], a));
+        sv = __dadd_rn(sv, __dmul_rn(ks[k], b));
       }
     }
     rowh[i] = sh;
@@ -308,22 +315,26 @@ __global__ void pp_sobel_rows(const float* __restrict__ hn, const float* __restr
   }
 }
 // Sobel columns: sobel_h = smooth along y of rowh (symmetric), sobel_v = deriv along y of rowv (anti-symmetric)
+template <int K>
 __global__ void pp_sobel_cols(const double* __restrict__ rowh, const double* __restrict__ rowv, int H, int W, long long total,
                               double* __restrict__ sobh, double* __restrict__ sobv) {
+  const double* kd = sobel_d<K>();
+  const double* ks = sobel_s<K>();
+  constexpr int C = K / 2;
   const int P = H * W;
   PP_GRID_LOOP(i, total) {
     const int p = (int)(i % P);
     const long long base = i - p;
     const int x = p % W, y = p / W;
-    double sh = __dmul_rn(c_sobel_s[10], rowh[i]);
+    double sh = __dmul_rn(ks[C], rowh[i]);
     double sv = 0.0;
 #pragma unroll
-    for (int k = 1; k <= 10; ++k) {
+    for (int k = 1; k <= C; ++k) {
       const int ya = refl101(y + k, H), yb = refl101(y - k, H);
       const double ha = rowh[base + (long long)ya * W + x], hb = rowh[base + (long long)yb * W + x];
       const double va = rowv[base + (long long)ya * W + x], vb = rowv[base + (long long)yb * W + x];
-      sh = __dadd_rn(sh, __dmul_rn(c_sobel_s[10 + k], __dadd_rn(ha, hb)));
-      sv = __dadd_rn(sv, __dmul_rn(c_sobel_d[10 + k], __dadd_rn(va, -vb)));
+      sh = __dadd_rn(sh, __dmul_rn(ks[C + k], __dadd_rn(ha, hb)));
+      sv = __dadd_rn(sv, __dmul_rn(kd[C + k], __dadd_rn(va, -vb)));
     }
     sobh[i] = sh;
     sobv[i] = sv;
@@ -620,17 +631,17 @@ __global__ void __launch_bounds__(PP_THREADS) pp_inst_finalize(int N, int maxI, 
 
 using namespace tiab;
 
-static void sobel_kernels(double d[21], double s[21]) {
-  // binomial smoothing (1+x)^20 and derivative (1+x)^19 * (x-1)  (cv2.getDerivKernels(1, 0, 21), un-normalised)
+static void sobel_kernels(double* d, double* s, int K = 21) {
+  // binomial smoothing (1+x)^(K-1) and derivative (1+x)^(K-2) * (x-1)  (cv2.getDerivKernels(1, 0, K), un-normalised), K <= 21
   long long a[22] = {0}, b[22] = {0};
   a[0] = 1;
-  for (int it = 0; it < 20; ++it)
+  for (int it = 0; it < K - 1; ++it)
     for (int k = it + 1; k >= 1; --k) a[k] += a[k - 1];
-  for (int k = 0; k < 21; ++k) s[k] = (double)a[k];
+  for (int k = 0; k < K; ++k) s[k] = (double)a[k];
   b[0] = 1;
-  for (int it = 0; it < 19; ++it)
+  for (int it = 0; it < K - 2; ++it)
     for (int k = it + 1; k >= 1; --k) b[k] += b[k - 1];
-  for (int k = 0; k < 21; ++k) d[k] = (double)((k >= 1 ? b[k - 1] : 0) - (k <= 19 ? b[k] : 0));
+  for (int k = 0; k < K; ++k) d[k] = (double)((k >= 1 ? b[k - 1] : 0) - (k <= K - 2 ? b[k] : 0));
 }
 
 struct PPAlloc {
@@ -665,6 +676,12 @@ int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]) {
   return TIAB_OK;
 }
 
+int tiab_dbg_sobel_kernels_k(int ksize, double* deriv, double* smooth) {
+  if (ksize < 3 || ksize > 21 || !(ksize & 1) || !deriv || !smooth) return TIAB_E_INVALID;
+  sobel_kernels(deriv, smooth, ksize);
+  return TIAB_OK;
+}
+
 // copy an intermediate of the LAST tiab_hovernet_postproc call to the host (tests only):
 // 0 blb u8, 1 h_dir f32, 2 v_dir f32, 3 sobel_h f64, 4 sobel_v f64, 5 dist f64, 6 marker i32, 7 opened seeds u8
 int tiab_dbg_postproc_fetch(tiab_handle_t h, int which, void* host_out, void* stream) {
@@ -678,10 +695,24 @@ int tiab_dbg_postproc_fetch(tiab_handle_t h, int which, void* host_out, void* st
 int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
                            int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id, int32_t* inst_box,
                            double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream) {
+  return tiab_hovernet_postproc_scaled(h, np_map, hv_map, tp_map, N, H, W, 1.0, inst_map, max_inst, inst_count, inst_id, inst_box,
+                                       inst_centroid, inst_type, inst_prob, stream);
+}
+
+int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
+                                  double scale_factor, int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id,
+                                  int32_t* inst_box, double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream) {
   if (!h) return TIAB_E_INVALID;
-  if (!np_map || !hv_map || !inst_map || N <= 0 || H < 11 || W < 11 || (long long)H * W > (1 << 24) || max_inst <= 0) {
+  if (!np_map || !hv_map || !inst_map || N <= 0 || H < 11 || W < 11 || (long long)H * W > (1 << 24) || max_inst <= 0 || !(scale_factor > 0)) {
     h->err = "tiab_hovernet_postproc: invalid argument";
     return TIAB_E_INVALID;
+  }
+  // hovernet.py:564-565: ksize = int(20 * scale_factor + 1), obj_size = ceil(10 * scale_factor^2)
+  const int ksize = (int)(20.0 * scale_factor + 1.0);
+  const int marker_max_size = (int)ceil(10.0 * scale_factor * scale_factor) - 1;
+  if (ksize != 21 && ksize != 11) {
+    h->err = "tiab_hovernet_postproc: scale_factor must give a Sobel size of 21 (1.0: HoVer-Net) or 11 (0.5: HoVerNet+)";
+    return TIAB_E_UNSUPPORTED;
   }
   const bool want_table = inst_count != nullptr;
   if (want_table && (!inst_id || !inst_box || !inst_centroid || !inst_type || !inst_prob)) {
@@ -692,9 +723,12 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
   cudaStream_t s = (cudaStream_t)stream;
   if (!h->pp_const_set) {
     double d[21], sm[21];
-    sobel_kernels(d, sm);
+    sobel_kernels(d, sm, 21);
     TIAB_CUDA_OK(h, cudaMemcpyToSymbol(c_sobel_d, d, sizeof(d)));
     TIAB_CUDA_OK(h, cudaMemcpyToSymbol(c_sobel_s, sm, sizeof(sm)));
+    sobel_kernels(d, sm, 11);
+    TIAB_CUDA_OK(h, cudaMemcpyToSymbol(c_sobel_d11, d, 11 * sizeof(double)));
+    TIAB_CUDA_OK(h, cudaMemcpyToSymbol(c_sobel_s11, sm, 11 * sizeof(double)));
     h->pp_const_set = 1;
   }
   const int P = H * W;
@@ -752,8 +786,13 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
   PP_LAUNCH(h, pp_mm_init, gN, PP_THREADS, N, w.mm, w.mm64);
   PP_LAUNCH(h, pp_minmax_hv, g2, PP_THREADS, hv_map, P, w.mm);
   PP_LAUNCH(h, pp_normalize_hv, g, PP_THREADS, hv_map, P, T, w.mm, w.hn, w.vn);
-  PP_LAUNCH(h, pp_sobel_rows, g, PP_THREADS, w.hn, w.vn, H, W, T, w.rowh, w.rowv);
-  PP_LAUNCH(h, pp_sobel_cols, g, PP_THREADS, w.rowh, w.rowv, H, W, T, w.sobh, w.sobv);
+  if (ksize == 21) {
+    PP_LAUNCH(h, pp_sobel_rows<21>, g, PP_THREADS, w.hn, w.vn, H, W, T, w.rowh, w.rowv);
+    PP_LAUNCH(h, pp_sobel_cols<21>, g, PP_THREADS, w.rowh, w.rowv, H, W, T, w.sobh, w.sobv);
+  } else {
+    PP_LAUNCH(h, pp_sobel_rows<11>, g, PP_THREADS, w.hn, w.vn, H, W, T, w.rowh, w.rowv);
+    PP_LAUNCH(h, pp_sobel_cols<11>, g, PP_THREADS, w.rowh, w.rowv, H, W, T, w.sobh, w.sobv);
+  }
   PP_LAUNCH(h, pp_minmax_sobel, g2, PP_THREADS, w.sobh, w.sobv, P, w.mm64);
   // 3. energy, distance, seeds (hovernet.py:592-603)
   PP_LAUNCH(h, pp_energy, g, PP_THREADS, w.sobh, w.sobv, w.mm64, w.blb, P, T, w.dist0, w.mk);
@@ -768,12 +807,12 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
   // 5. opening with the 5x5 ellipse (hovernet.py:605-606)
   PP_LAUNCH(h, pp_morph, g, PP_THREADS, w.tmp, H, W, T, 0, w.fg);
   PP_LAUNCH(h, pp_morph, g, PP_THREADS, w.fg, H, W, T, 1, w.mk);
-  // 6. label the seeds, drop <= 9 px, keep ids (hovernet.py:607-614)
+  // 6. label the seeds, drop <= obj_size - 1 px (9 at scale 1), keep ids (hovernet.py:607-614)
   PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.mk, P, T, lab2, size2, (int*)nullptr, w.border);
   PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.mk, H, W, T, lab2);
   PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, lab2, size2, (int*)nullptr, w.border);
   PP_LAUNCH(h, pp_rank_roots, N, 1024, lab2, P, w.cid, roots2, ncomp2);
-  PP_LAUNCH(h, pp_keep_large, g, PP_THREADS, lab2, size2, w.cid, P, T, 9, (uint8_t*)nullptr, w.marker);
+  PP_LAUNCH(h, pp_keep_large, g, PP_THREADS, lab2, size2, w.cid, P, T, marker_max_size, (uint8_t*)nullptr, w.marker);
   // 7. watershed (hovernet.py:616)
   TIAB_CUDA_OK(h, cudaMemsetAsync(inst_map, 0, (size_t)T * 4, s));
   PP_LAUNCH(h, pp_heap_offsets, N, PP_THREADS, w.roots, w.ncomp, w.size, P, N, w.heap_off);

@@ -1,5 +1,5 @@
 """Model registry for the hot-path models (mirrors tiatoolbox/models/architecture/__init__.py:70-178 and the
-three entries of tiatoolbox/data/pretrained_model.yaml:15-28, 572-592, 642-672).
+entries of tiatoolbox/data/pretrained_model.yaml:15-28, 572-592, 642-672, 758-794).
 
 The reference downloads weights from Hugging Face; there is no network here, so `weights=` takes a local
 `.pth` (a tiatoolbox checkpoint loads unchanged — the state-dict keys are identical) and, when it is
@@ -47,6 +47,13 @@ PRETRAINED_INFO = {
                                      5: "Non-Neoplastic Epithelial"}},
         "ioconfig": IOConfig((256, 256), (164, 164), [{"units": "mpp", "resolution": 0.25}], [{"units": "mpp", "resolution": 0.25}] * 3,
                              (164, 164), {"units": "mpp", "resolution": 0.25}, margin=128, tile_shape=(1024, 1024), ignore_index=0),
+    },
+    "hovernetplus-oed": {
+        "class": ("hovernetplus", "HoVerNetPlus"),
+        "kwargs": {"num_types": 3, "num_layers": 5, "nuc_type_dict": {0: "Background", 1: "Other", 2: "Epithelial"},
+                   "layer_type_dict": {0: "Background", 1: "Other Tissue", 2: "Basal Epithelium", 3: "(Core) Epithelium", 4: "Keratin"}},
+        "ioconfig": IOConfig((256, 256), (164, 164), [{"units": "mpp", "resolution": 0.5}], [{"units": "mpp", "resolution": 0.5}] * 4,
+                             (164, 164), {"units": "mpp", "resolution": 0.5}, margin=128, tile_shape=(2048, 2048), ignore_index=0),
     },
 }
 

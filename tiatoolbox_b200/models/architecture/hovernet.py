@@ -27,7 +27,21 @@ RES_CFG = (("d0", 64, (64, 64, 256), 3, 1), ("d1", 256, (128, 128, 512), 4, 2),
            ("d2", 512, (256, 256, 1024), 6, 2), ("d3", 1024, (512, 512, 2048), 3, 2))
 
 
-def hovernet_spec(num_input_channels: int = 3, num_types: int | None = None, mode: str = "original") -> ParamSpec:
+def branch_channels(num_types: int | None, num_layers: int | None = None) -> OrderedDict:
+    """Decoder branches in the reference's ModuleDict order with their output channels: [tp], np, hv (hovernet.py:381-403) and, for
+    HoVerNet+, ls (hovernetplus.py:107-131)."""
+    br = OrderedDict()
+    if num_types is not None:
+        br["tp"] = num_types
+    br["np"] = 2
+    br["hv"] = 2
+    if num_layers is not None:
+        br["ls"] = num_layers
+    return br
+
+
+def hovernet_spec(num_input_channels: int = 3, num_types: int | None = None, mode: str = "original",
+                  num_layers: int | None = None) -> ParamSpec:
     sp = ParamSpec()
     sp.conv("conv0./", 64, num_input_channels, 7)
     sp.bn("conv0.bn", 64)
@@ -48,9 +62,7 @@ def hovernet_spec(num_input_channels: int = 3, num_types: int | None = None, mod
         sp.bn(f"{name}.blk_bna.bn", c3)
     sp.conv("conv_bot", 1024, 2048, 1)
     k = 5 if mode == "original" else 3
-    branches = (["tp"] if num_types is not None else []) + ["np", "hv"]
-    for b in branches:
-        out_ch = num_types if b == "tp" else 2
+    for b, out_ch in branch_channels(num_types, num_layers).items():
         for lvl, cin, cmid, units in (("u3", 1024, 256, 8), ("u2", 512, 128, 4)):
             p = f"decoder.{b}.{lvl}"
             sp.conv(f"{p}.conva", cmid, cin, k)
@@ -124,8 +136,10 @@ def _dense_block(x, sd, name, units):
     return F.relu(_bn(prev, sd, f"{name}.blk_bna.bn"))
 
 
-def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: int | None, capture: dict | None = None) -> OrderedDict:
-    """fp32 PyTorch restatement of HoVerNet.forward (hovernet.py:405-454).  x in [0, 255]."""
+def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: int | None, capture: dict | None = None,
+                               num_layers: int | None = None) -> OrderedDict:
+    """fp32 PyTorch restatement of HoVerNet.forward (hovernet.py:405-454; with `num_layers` HoVerNetPlus, which only adds the `ls`
+    decoder branch: hovernetplus.py:87-133).  x in [0, 255]."""
     x = x_nchw / 255.0
     if mode == "fast":
         pb, pa = tf_same_pad(x.shape[2], 7, 1)
@@ -147,7 +161,7 @@ def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: i
     d1 = feats[1][:, :, c1 // 2: feats[1].shape[2] - c1 // 2, c1 // 2: feats[1].shape[3] - c1 // 2]
     k = 5 if mode == "original" else 3
     out = OrderedDict()
-    for b in (["tp"] if num_types is not None else []) + ["np", "hv"]:
+    for b in branch_channels(num_types, num_layers):
         p = f"decoder.{b}"
         u3 = _up2(feats[3]) + feats[2]
         if capture is not None:
@@ -184,6 +198,9 @@ def hovernet_heads_reference(out: OrderedDict) -> tuple[torch.Tensor, ...]:
     o["np"] = F.softmax(o["np"], dim=-1)[..., 1:]
     if "tp" in o:
         tp = torch.argmax(F.softmax(o["tp"], dim=-1), dim=-1, keepdim=True).type(torch.float32)
+        if "ls" in o:   # HoVerNetPlus.infer_batch (hovernetplus.py:444-459)
+            ls = torch.argmax(F.softmax(o["ls"], dim=-1), dim=-1, keepdim=True).type(torch.float32)
+            return o["np"], o["hv"], tp, ls
         return o["np"], o["hv"], tp
     return o["np"], o["hv"]
 

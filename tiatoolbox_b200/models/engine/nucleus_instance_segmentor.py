@@ -49,8 +49,10 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
     def infer_patches(self, patches: np.ndarray):
         """GPU: stain -> network -> post-processing per batch, all asynchronous.  Host: the instance dictionaries (contour tracing
         with cv2) of batch i are built while the GPU already works on batch i + 1 (results travel through pinned buffers)."""
-        insts, infos, heads = [], [], []
+        insts, infos, heads, layers = [], [], [], []
         pending = None
+        two_task = getattr(self.model, "num_layers", None) is not None      # HoVerNetPlus: nuclei (scale 0.5) + layer segmentation
+        scale = 0.5 if two_task else 1.0
 
         def finish(p):
             ev, inst_h, table_h = p
@@ -64,8 +66,10 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
             outs = type(self.model).infer_batch_device(self.model, x, device=self.device)
             np_map, hv_map = outs[0], outs[1]
             tp_map = outs[2] if len(outs) > 2 else None
-            inst, table = pp.proc_np_hv_batch(np_map, hv_map, tp_map)
+            inst, table = pp.proc_np_hv_batch(np_map, hv_map, tp_map, scale_factor=scale)
             insts.append(inst)
+            if two_task:   # the layer head is a class-index map; its clean-up is whole-map morphology on the host (hovernetplus.py:135-194)
+                layers.append(outs[3][..., 0].to(torch.uint8).cpu().numpy())
             slot = b & 1
             inst_h = self._to_host_async(("inst", slot), inst)
             table_h = {k: self._to_host_async(("tab", k, slot), v) for k, v in table.items()}
@@ -78,10 +82,12 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
             pending = (ev, inst_h, table_h)
         if pending is not None:
             finish(pending)
+        if two_task:
+            return insts, infos, heads, [type(self.model)._proc_ls(m) for batch in layers for m in batch]  # noqa: SLF001
         return insts, infos, heads
 
     def post_process_patches(self, raw, n_total: int) -> dict:
-        insts, infos, heads = raw
+        insts, infos, heads = raw[:3]
         dist, rank, world = self._dist()
         local = torch.cat(insts) if insts else torch.empty((0, 1, 1), dtype=torch.int32, device=self.device)
         inst_all = self._all_gather_rows(local, n_total).cpu().numpy()
@@ -98,9 +104,25 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
             for key in cols:
                 cols[key].append(packed[key])
         out.update(cols)
+        probabilities = None
         if self.return_probabilities and heads:
-            out["probabilities"] = [self._all_gather_rows(torch.cat([h[j] for h in heads]), n_total).cpu().numpy()
-                                    for j in range(len(heads[0]))]
+            probabilities = [self._all_gather_rows(torch.cat([h[j] for h in heads]), n_total).cpu().numpy() for j in range(len(heads[0]))]
+        if len(raw) > 3:   # two tasks: results nested under the task names (multi_task_segmentor.py:1631-1661)
+            layer_maps = raw[3]
+            local = torch.from_numpy(np.stack(layer_maps)) if layer_maps else torch.empty((0, 1, 1), dtype=torch.uint8)
+            layer_all = self._all_gather_rows(local.to(self.device), n_total).cpu().numpy()
+            linfo = {key: [] for key in ("box", "contours", "type")}
+            for m in layer_all:
+                info = type(self.model)._get_layer_info(m)  # noqa: SLF001
+                for key in linfo:
+                    col = np.empty(len(info), dtype=object)
+                    for i, rec in enumerate(info.values()):
+                        col[i] = rec[key]
+                    linfo[key].append(col if len(info) else np.empty(0))
+            tasks = self.model.tasks
+            out = {tasks[0]: out, tasks[1]: {"predictions": layer_all, **linfo}}
+        if probabilities is not None:
+            out["probabilities"] = probabilities
         return out
 
 

@@ -13,15 +13,15 @@ import torch
 
 from tiatoolbox_b200.models import ops
 from tiatoolbox_b200.models.architecture._params import bn_scale_shift
-from tiatoolbox_b200.models.architecture.hovernet import RES_CFG, tf_same_pad
+from tiatoolbox_b200.models.architecture.hovernet import RES_CFG, branch_channels, tf_same_pad
 from tiatoolbox_b200.models.plan import Plan
 
 
 class HoVerNetPlan(Plan):
     def __init__(self, sd, *, batch: int, device, mode: str = "fast", num_types: int | None = 6, in_size: int | None = None,
-                 precision: str = "fp16x3"):
+                 precision: str = "fp16x3", num_layers: int | None = None):
         super().__init__(device, batch, precision)
-        self.mode, self.num_types = mode, num_types
+        self.mode, self.num_types, self.num_layers = mode, num_types, num_layers
         S = in_size or (256 if mode == "fast" else 270)
         self.S = S
         B = batch
@@ -57,7 +57,8 @@ class HoVerNetPlan(Plan):
         self.add(lambda: ops.upsample_add(dbot, H3, H3, H3, H3, 0, 0, d2, H2, H2, 0, 0, B, 1024, None, None, False, u3in, G3, G3, 0, 0))
         crop0, crop1 = (184, 72) if mode == "original" else (92, 36)
         h = k // 2
-        branches = (["tp"] if num_types is not None else []) + ["np", "hv"]
+        br_ch = branch_channels(num_types, num_layers)   # [tp], np, hv, [ls (HoVerNet+)]
+        branches = list(br_ch)
         # The branches have identical shapes, so every decoder layer is ONE grouped launch over R*B images (group r = branch
         # r with its own weight rows): three times the tiles per launch, a third of the launches.
         R = len(branches)
@@ -109,7 +110,7 @@ class HoVerNetPlan(Plan):
             self.add(lambda r=r: ops.upsample_add(u2out.images(r * B, B), W2, W2, G2, G2, lo2, lo2, d0, H0, H0, crop0 // 2, crop0 // 2, B,
                                                   256, None, None, False, u1in.images(r * B, B), G1, G1, pu[0], pu[0]))
         # u1 conv with u0 (BN + ReLU + 1x1 conv + bias -> fp32 logits) fused into its epilogue: the 64-channel tensor is never stored
-        out_chs = [num_types if b == "tp" else 2 for b in branches]
+        out_chs = [br_ch[b] for b in branches]
         logits = {b: self.buf(f"logits_{b}", (B, So, So, oc), torch.float32) for b, oc in zip(branches, out_chs)}
         w_u1 = self.weight_groups([sd[f"{p}.u1.conva.weight"] for p in pre])
         if max(out_chs) <= 8:
@@ -141,6 +142,9 @@ class HoVerNetPlan(Plan):
         self.tp_out = self.buf("tp_out", (B, So, So, 1), torch.float32) if num_types is not None else None
         self.add(lambda: ops.hovernet_heads(logits["np"], logits["hv"], logits.get("tp"), num_types or 0, B * So * So, self.np_out,
                                             self.hv_out, self.tp_out))
+        # HoVerNet+: the layer head is argmax(softmax(ls)) as float32 (hovernetplus.py:455-458) — 27k x num_layers values per image,
+        # formed with two torch calls after the plan has run (see forward)
+        self.ls_out = self.buf("ls_out", (B, So, So, 1), torch.float32) if num_layers is not None else None
 
     # ------------------------------------------------------------------------------------------
     def _res_block(self, sd, name, x_act, H, cin, c1, c2, c3, units, stride, cat=None):
@@ -229,6 +233,10 @@ class HoVerNetPlan(Plan):
         assert x_u8.shape == self.inp.shape and x_u8.dtype == torch.uint8, (x_u8.shape, self.inp.shape)
         self.inp.copy_(x_u8, non_blocking=True)
         self.run()
+        if self.ls_out is not None:
+            probs = torch.softmax(self.logits["ls"], dim=-1)
+            self.ls_out.copy_(torch.argmax(probs, dim=-1, keepdim=True))
+            return self.np_out, self.hv_out, self.tp_out, self.ls_out
         if self.tp_out is not None:
             return self.np_out, self.hv_out, self.tp_out
         return self.np_out, self.hv_out

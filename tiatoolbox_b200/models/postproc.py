@@ -16,7 +16,7 @@ from tiatoolbox_b200 import _lib
 
 
 def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.Tensor | None = None, max_inst: int | None = None,
-                     want_table: bool = True):
+                     want_table: bool = True, scale_factor: float = 1.0):
     """np_map (N,H,W,1), hv_map (N,H,W,2), tp_map (N,H,W,1) float32 CUDA tensors ->
     inst_map (N,H,W) int32 CUDA tensor and (optionally) the per-image instance table as CUDA tensors."""
     assert np_map.is_cuda and np_map.dtype == torch.float32
@@ -26,7 +26,8 @@ def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.T
     tp_map = None if tp_map is None else tp_map.contiguous()
     inst = torch.empty((n, h_, w_), dtype=torch.int32, device=dev)
     if max_inst is None:
-        max_inst = max(16, (h_ * w_) // 10 + 1)  # every kept marker has >= 10 pixels
+        # every kept marker has >= ceil(10 * scale_factor^2) pixels (hovernet.py:565, 613)
+        max_inst = max(16, (h_ * w_) // max(int(np.ceil(10 * scale_factor * scale_factor)), 1) + 1)
     table = None
     if want_table:
         table = {
@@ -38,8 +39,9 @@ def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.T
             "prob": torch.empty((n, max_inst), dtype=torch.float64, device=dev),
         }
     hd = _lib.handle(dev.index or 0)
-    rc = _lib.lib().tiab_hovernet_postproc(
-        hd, np_map.data_ptr(), hv_map.data_ptr(), None if tp_map is None else tp_map.data_ptr(), n, h_, w_, inst.data_ptr(), max_inst,
+    rc = _lib.lib().tiab_hovernet_postproc_scaled(
+        hd, np_map.data_ptr(), hv_map.data_ptr(), None if tp_map is None else tp_map.data_ptr(), n, h_, w_, float(scale_factor),
+        inst.data_ptr(), max_inst,
         None if table is None else table["count"].data_ptr(), None if table is None else table["id"].data_ptr(),
         None if table is None else table["box"].data_ptr(), None if table is None else table["centroid"].data_ptr(),
         None if table is None else table["type"].data_ptr(), None if table is None else table["prob"].data_ptr(),
