@@ -128,3 +128,24 @@ def test_wsi_mode_hovernet_vahadane_end_to_end(built_lib):
         assert np.array_equal(out["box"][i], rec["box"]) and np.array_equal(out["contours"][i], rec["contours"])
         assert out["type"][i] == rec["type"]
     assert np.array_equal(out["predictions"], wsi_pred)
+
+
+def test_patch_predictor_wsi_mode(built_lib):
+    """PatchPredictor on an in-memory region: the coordinate grid and 255 padding of the reference's WSI dataset, results == patch mode."""
+    from tests.cnn_common import resnet18_test_weights
+    from tiatoolbox_b200.models.engine import PatchPredictor
+    from tiatoolbox_b200.synthetic import he_tiles
+    from tiatoolbox_b200.tools.patchextraction import PatchExtractor
+
+    eng = PatchPredictor("resnet18-kather100k", batch_size=4, device="cuda")
+    eng.model.load_state_dict(resnet18_test_weights())
+    t = he_tiles(6, 256, 256, seed=13)
+    region = np.concatenate([np.concatenate(list(t[:3]), axis=1), np.concatenate(list(t[3:]), axis=1)], axis=0)[:500, :700].copy()
+    out = eng.run(region, patch_mode=False, return_probabilities=True)
+    coords = PatchExtractor.get_coordinates(image_shape=(700, 500), patch_input_shape=(224, 224), stride_shape=(224, 224))
+    assert np.array_equal(out["coordinates"], coords) and len(coords) == 4 * 3
+    padded = np.full((672, 896, 3), 255, np.uint8)
+    padded[:500, :700] = region
+    patches = np.stack([padded[y0:y1, x0:x1] for x0, y0, x1, y1 in coords])
+    ref = eng.run(patches, return_probabilities=True)
+    assert np.array_equal(out["probabilities"], ref["probabilities"]) and np.array_equal(out["predictions"], ref["predictions"])
