@@ -252,8 +252,18 @@ int tiab_hovernet_postproc(tiab_handle_t h, const float* np_map, const float* hv
 int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const float* hv_map, const float* tp_map, int N, int H, int W,
                                   double scale_factor, int32_t* inst_map, int max_inst, int* inst_count, int32_t* inst_id,
                                   int32_t* inst_box, double* inst_centroid, int32_t* inst_type, double* inst_prob, void* stream);
+/* The contour part of get_instance_info (hovernet.py:685-693: cv2.findContours(crop, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0]) for every
+ * row of the instance table written by tiab_hovernet_postproc: cont_xy N*capacity*2 int32 (x, y in image coordinates), the vertices of
+ * table row (n, k) at [cont_off[n*max_inst+k], +cont_len[...]) of image n's slice; cont_total[n] = vertices image n needs (a slice that
+ * would pass `capacity` is counted but not written).  All pointers are device pointers; asynchronous on `stream`. */
+int tiab_hovernet_contours(tiab_handle_t h, const int32_t* inst_map, int N, int H, int W, int max_inst, const int* inst_count,
+                           const int32_t* inst_id, const int32_t* inst_box, int capacity, int32_t* cont_off, int32_t* cont_len,
+                           int32_t* cont_total, int32_t* cont_xy, void* stream);
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]);
 int tiab_dbg_sobel_kernels_k(int ksize, double* deriv, double* smooth);
+/* host-side test hook of csrc/contour_math.cuh: the CHAIN_APPROX_SIMPLE outer border of label `id` (its component that contains the
+ * label's first pixel in raster order) in an H*W int32 host image; returns the number of points (at most `cap` are written). */
+int tiab_dbg_trace_contour(const int32_t* map_host, int H, int W, int32_t id, int* out_xy, int cap);
 /* host-side test hooks of csrc/lab_math.cuh (no GPU): the device's per-pixel colour conversion and per-level Reinhard maps run on the CPU.
  * tiab_dbg_reinhard_maps returns 1 (and identity maps) when a channel is constant. */
 int tiab_dbg_lab_convert(const uint8_t* in_host, uint8_t* out_host, long long npix, int inverse);

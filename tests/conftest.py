@@ -17,7 +17,7 @@ def pytest_configure(config):
 
 # GPU test modules written after round 1's GPU budget was spent (not yet run on a B200): they are collected AFTER the modules that have
 # been, so that with `-x` a first-run failure in new code cannot hide the results of the established hot-path tests.
-_NEWEST_GPU_MODULES = ("test_reinhard_gpu", "test_augment_gpu", "test_wsi_gpu", "test_hovernetplus_gpu")
+_NEWEST_GPU_MODULES = ("test_reinhard_gpu", "test_augment_gpu", "test_contours_gpu", "test_wsi_gpu", "test_hovernetplus_gpu")
 
 
 def pytest_collection_modifyitems(config, items):  # noqa: ARG001

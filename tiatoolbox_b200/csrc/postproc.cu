@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/tiab200.h"
+#include "contour_math.cuh"
 #include "ctx.h"
 
 namespace tiab {
@@ -627,6 +628,34 @@ __global__ void __launch_bounds__(PP_THREADS) pp_inst_finalize(int N, int maxI, 
   }
 }
 
+// Contours of the tabulated instances (hovernet.py:685-693): one thread per table row walks the instance's outer border twice — once to
+// count the CHAIN_APPROX_SIMPLE vertices, once to write them into a slice reserved with one atomicAdd on the image's vertex counter.
+__global__ void __launch_bounds__(128) pp_contours(const int32_t* __restrict__ inst_map, int N, int H, int W, int max_inst,
+                                                   const int* __restrict__ inst_count, const int32_t* __restrict__ inst_id,
+                                                   const int32_t* __restrict__ inst_box, int capacity, int32_t* __restrict__ cont_off,
+                                                   int32_t* __restrict__ cont_len, int32_t* __restrict__ cont_total,
+                                                   int32_t* __restrict__ cont_xy) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * max_inst) return;
+  const int n = (int)(t / max_inst), k = (int)(t - (long long)n * max_inst);
+  if (k >= inst_count[n]) return;
+  const LabelView v{inst_map + (long long)n * H * W, H, W, inst_id[t]};
+  const int32_t* box = inst_box + t * 4;   // [x0, y0, x1, y1): the first pixel in raster order lies on row y0
+  int x0 = box[0];
+  const int y0 = box[1];
+  while (x0 < box[2] && !v.fg(x0, y0)) ++x0;
+  if (x0 >= box[2]) {   // cannot happen for a consistent table
+    cont_off[t] = 0;
+    cont_len[t] = 0;
+    return;
+  }
+  const int len = trace_outer_contour(v, x0, y0, nullptr, 0);
+  const int off = atomicAdd(&cont_total[n], len);
+  cont_off[t] = off;
+  cont_len[t] = len;
+  if (off + len <= capacity) trace_outer_contour(v, x0, y0, cont_xy + ((long long)n * capacity + off) * 2, len);
+}
+
 }  // namespace tiab
 
 using namespace tiab;
@@ -674,6 +703,15 @@ extern "C" {
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]) {
   sobel_kernels(deriv, smooth);
   return TIAB_OK;
+}
+
+int tiab_dbg_trace_contour(const int32_t* map_host, int H, int W, int32_t id, int* out_xy, int cap) {
+  if (!map_host || H <= 0 || W <= 0 || cap < 0 || (cap && !out_xy)) return TIAB_E_INVALID;
+  const LabelView v{map_host, H, W, id};
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x)
+      if (v.fg(x, y)) return trace_outer_contour(v, x, y, out_xy, cap);
+  return 0;
 }
 
 int tiab_dbg_sobel_kernels_k(int ksize, double* deriv, double* smooth) {
@@ -831,6 +869,25 @@ int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const fl
     PP_LAUNCH(h, pp_inst_finalize, N, PP_THREADS, N, max_inst, tp_map ? 1 : 0, w.iarea, w.ibox, w.isx, w.isy, w.itype, inst_count, inst_id,
               inst_box, inst_centroid, inst_type, inst_prob);
   }
+  return TIAB_OK;
+}
+
+int tiab_hovernet_contours(tiab_handle_t h, const int32_t* inst_map, int N, int H, int W, int max_inst, const int* inst_count,
+                           const int32_t* inst_id, const int32_t* inst_box, int capacity, int32_t* cont_off, int32_t* cont_len,
+                           int32_t* cont_total, int32_t* cont_xy, void* stream) {
+  if (!h) return TIAB_E_INVALID;
+  if (!inst_map || N <= 0 || H <= 0 || W <= 0 || max_inst <= 0 || !inst_count || !inst_id || !inst_box || capacity <= 0 || !cont_off ||
+      !cont_len || !cont_total || !cont_xy) {
+    h->err = "tiab_hovernet_contours: invalid argument";
+    return TIAB_E_INVALID;
+  }
+  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TIAB_CUDA_OK(h, cudaMemsetAsync(cont_total, 0, (size_t)N * sizeof(int32_t), s));
+  const long long threads = (long long)N * max_inst;
+  h->last_launches = 0;
+  PP_LAUNCH(h, pp_contours, (unsigned)((threads + 127) / 128), 128, inst_map, N, H, W, max_inst, inst_count, inst_id, inst_box, capacity,
+            cont_off, cont_len, cont_total, cont_xy);
   return TIAB_OK;
 }
 

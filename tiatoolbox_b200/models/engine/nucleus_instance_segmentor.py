@@ -20,6 +20,9 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
      ["probabilities": [np, hv, tp]]}."""
 
     with_contours = True
+    #: trace the instance contours on the device (csrc/contour_math.cuh, equal to cv2.findContours on fuzzed masks) instead of calling
+    #: cv2.findContours per nucleus on the host.  Opt-in until its GPU tests have run on a B200 (written after round 1's GPU budget).
+    device_contours = False
 
     def run(self, images, *, patch_mode: bool = True, ioconfig=None, return_predictions=None, **kwargs):
         """Patch mode: EngineABC.run.  `patch_mode=False` with in-memory slides — one (H, W, 3) uint8 array or a list of them — runs the
@@ -67,6 +70,8 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
             np_map, hv_map = outs[0], outs[1]
             tp_map = outs[2] if len(outs) > 2 else None
             inst, table = pp.proc_np_hv_batch(np_map, hv_map, tp_map, scale_factor=scale)
+            if self.device_contours and self.with_contours:
+                pp.trace_contours(inst, table)
             insts.append(inst)
             if two_task:   # the layer head is a class-index map; its clean-up is whole-map morphology on the host (hovernetplus.py:135-194)
                 layers.append(outs[3][..., 0].to(torch.uint8).cpu().numpy())

@@ -2,8 +2,8 @@
 
 `proc_np_hv_batch` = HoVerNet._proc_np_hv for a batch (hovernet.py:502-616) entirely on the GPU;
 `instance_info` assembles get_instance_info's dictionary (hovernet.py:618-748): box / centroid /
-type / prob come from the device table, contours from cv2.findContours on the host (SURVEY §8f item 2
-keeps contour tracing as the next step to move on-device).
+type / prob come from the device table; contours from `trace_contours` (device border following, csrc/contour_math.cuh) when the
+table carries them, else from cv2.findContours on the host.
 """
 from __future__ import annotations
 
@@ -50,6 +50,26 @@ def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.T
     return inst, table
 
 
+def trace_contours(inst: torch.Tensor, table: dict, capacity: int | None = None) -> dict:
+    """Contours of every tabulated instance on the device (the `cv2.findContours(..., RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0]` of
+    hovernet.py:685-693): adds `cont_off`, `cont_len` (N, max_inst), `cont_total` (N,) and `cont_xy` (N, capacity, 2) int32 tensors to
+    `table` (vertices in image coordinates) and returns it.  `capacity` = vertices per image (default H*W // 2)."""
+    n, h_, w_ = inst.shape
+    dev = inst.device
+    max_inst = table["id"].shape[1]
+    capacity = int(capacity) if capacity is not None else max(64, (h_ * w_) // 2)
+    table["cont_off"] = torch.empty((n, max_inst), dtype=torch.int32, device=dev)
+    table["cont_len"] = torch.empty((n, max_inst), dtype=torch.int32, device=dev)
+    table["cont_total"] = torch.empty((n,), dtype=torch.int32, device=dev)
+    table["cont_xy"] = torch.empty((n, capacity, 2), dtype=torch.int32, device=dev)
+    hd = _lib.handle(dev.index or 0)
+    _lib.check(hd, _lib.lib().tiab_hovernet_contours(
+        hd, inst.data_ptr(), n, h_, w_, max_inst, table["count"].data_ptr(), table["id"].data_ptr(), table["box"].data_ptr(), capacity,
+        table["cont_off"].data_ptr(), table["cont_len"].data_ptr(), table["cont_total"].data_ptr(), table["cont_xy"].data_ptr(),
+        torch.cuda.current_stream(dev).cuda_stream))
+    return table
+
+
 def fetch_debug(which: int, shape, dtype, device=0) -> np.ndarray:
     out = np.empty(shape, dtype)
     hd = _lib.handle(device)
@@ -63,11 +83,19 @@ def instance_info(inst_map: np.ndarray, table_row: dict, offset=(0, 0), with_con
 
     offset = np.asarray(offset)
     info = {}
+    device_contours = with_contours and "cont_xy" in table_row
+    if device_contours and int(table_row["cont_total"]) > len(table_row["cont_xy"]):
+        device_contours = False   # the image needed more vertices than the device buffer holds: trace on the host instead
     for k in range(int(table_row["count"])):
         inst_id = int(table_row["id"][k])
         box = table_row["box"][k].astype(np.int64).copy()
         rec = {"box": None, "centroid": None, "contours": None, "prob": None, "type": None}
-        if with_contours:
+        if device_contours:
+            n_pts, off = int(table_row["cont_len"][k]), int(table_row["cont_off"][k])
+            if n_pts < 3:  # hovernet.py:696-701 (a squeezed 1- or 2-point contour has shape[0] < 3)  # noqa: PLR2004
+                continue
+            rec["contours"] = (table_row["cont_xy"][off: off + n_pts] + offset[None]).astype(np.int32)
+        elif with_contours:
             crop = (inst_map[box[1]:box[3], box[0]:box[2]] == inst_id).astype(np.uint8)
             contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].astype(np.int32)
             contour = np.squeeze(contour)
