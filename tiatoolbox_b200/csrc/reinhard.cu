@@ -25,7 +25,7 @@
 
 namespace tiab {
 
-struct LabTablesDev {   // device copies of lab_tables.h (one per process and device, built on first use)
+struct __align__(16) LabTablesDev {   // device copies of lab_tables.h (one per process and device, built on first use); read as uint4
   uint16_t gamma[256];
   uint16_t cbrt[2048 + 8];   // 2041 used
   uint16_t yf[512];
@@ -34,7 +34,7 @@ struct LabTablesDev {   // device copies of lab_tables.h (one per process and de
 
 __device__ LabTablesDev g_lab_tables;
 
-struct LabShared {
+struct __align__(16) LabShared {
   uint16_t gamma[256];
   uint16_t cbrt[2048 + 8];
   uint16_t yf[512];
