@@ -380,6 +380,8 @@ def main():
         r = e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if combined:   # bytes the engine actually copied device -> host in one call: instance maps + instance tables + contour vertices
+        d2h = int(getattr(eng, "d2h_bytes", d2h))
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -30,10 +30,14 @@ def _decoder_engine(batch_size: int = 7):
 
         def _wsi_forward(self, x):
             assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()
-            c = x[:, 12:52, 12:52]
-            f = c.float()
-            npm = f[..., 0:1] / 255.0
-            hv = f[..., 1:3] / 127.5 - 1.0
+            c = x[:, 12:52, 12:52].long()
+            # per-level tables computed by numpy (torch's CUDA division by a constant is a multiplication by its reciprocal, 1 ulp off)
+            lv = np.arange(256, dtype=np.uint8)[:, None].repeat(3, 1)
+            t_np, t_hv, _ = decode_heads(lv)
+            lut_np = torch.from_numpy(np.ascontiguousarray(t_np[:, 0])).to(x.device)
+            lut_hv = torch.from_numpy(np.ascontiguousarray(t_hv[:, 0])).to(x.device)
+            npm = lut_np[c[..., 0:1]]
+            hv = lut_hv[c[..., 1:3]]
             tp = torch.where(npm > 0.5, 1.0 + ((c[..., 1:2] // 16) % 5).float(), torch.zeros_like(npm))
             return [npm.contiguous(), hv.contiguous(), tp.contiguous()]
 

@@ -203,4 +203,5 @@ class EngineABC:
         """Start a device -> pinned-host copy on the current stream; the caller synchronises on an event before reading."""
         buf = self._pinned(key, (max(self.batch_size, t.shape[0]), *t.shape[1:]), t.dtype)[: t.shape[0]]
         buf.copy_(t, non_blocking=True)
+        self.__dict__["d2h_bytes"] = self.__dict__.get("d2h_bytes", 0) + buf.numel() * buf.element_size()   # what actually crosses the bus
         return buf

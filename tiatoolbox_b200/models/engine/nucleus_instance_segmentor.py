@@ -20,9 +20,9 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
      ["probabilities": [np, hv, tp]]}."""
 
     with_contours = True
-    #: trace the instance contours on the device (csrc/contour_math.cuh, equal to cv2.findContours on fuzzed masks) instead of calling
-    #: cv2.findContours per nucleus on the host.  Opt-in until its GPU tests have run on a B200 (written after round 1's GPU budget).
-    device_contours = False
+    #: trace the instance contours on the device (csrc/contour_math.cuh: equal to cv2.findContours on fuzzed masks on the CPU and on
+    #: the B200, profiles/r1h_gpu_tests_contours.log); False = cv2.findContours per nucleus on the host (the r1g behaviour)
+    device_contours = True
 
     def run(self, images, *, patch_mode: bool = True, ioconfig=None, return_predictions=None, **kwargs):
         """Patch mode: EngineABC.run.  `patch_mode=False` with in-memory slides — one (H, W, 3) uint8 array or a list of them — runs the
@@ -49,19 +49,32 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
 
     predict = run
 
+    #: rows of the instance table / contour vertices copied to the host per image in the common case (a 164-px HoVer-Net map holds a few
+    #: dozen nuclei); an image that needs more is fetched in full when its batch is finished
+    table_rows_fast = 512
+    contour_vertices_fast = 4096
+
     def infer_patches(self, patches: np.ndarray):
-        """GPU: stain -> network -> post-processing per batch, all asynchronous.  Host: the instance dictionaries (contour tracing
-        with cv2) of batch i are built while the GPU already works on batch i + 1 (results travel through pinned buffers)."""
-        insts, infos, heads, layers = [], [], [], []
+        """GPU: stain -> network -> post-processing (+ contour tracing) per batch, all asynchronous.  Host: the instance dictionaries of
+        batch i are assembled while the GPU already works on batch i + 1 (results travel through pinned buffers; with
+        `device_contours=False` the host also traces the contours with cv2 there)."""
+        insts, infos, heads, layers, inst_host = [], [], [], [], []
         pending = None
         two_task = getattr(self.model, "num_layers", None) is not None      # HoVerNetPlus: nuclei (scale 0.5) + layer segmentation
         scale = 0.5 if two_task else 1.0
+        self.d2h_bytes = 0
 
         def finish(p):
-            ev, inst_h, table_h = p
+            ev, inst_h, table_h, table_d = p
             ev.synchronize()
-            inst_np = inst_h.numpy()
+            inst_np = inst_h.numpy().copy()           # the pinned buffer is reused two batches later
+            inst_host.append(inst_np)
             t = {k: v.numpy() for k, v in table_h.items()}
+            need_rows = int(t["count"].max()) if len(t["count"]) else 0
+            need_xy = int(t["cont_total"].max()) if "cont_total" in t and len(t["cont_total"]) else 0
+            if need_rows > t["id"].shape[1] or ("cont_xy" in t and need_xy > t["cont_xy"].shape[1]):
+                t = {k: v.cpu().numpy() for k, v in table_d.items()}      # rare: an unusually crowded image, fetch the whole table
+                self.d2h_bytes += sum(v.numel() * v.element_size() for v in table_d.values())
             for i in range(len(t["count"])):
                 infos.append(pp.instance_info(inst_np[i], {key: v[i] for key, v in t.items()}, with_contours=self.with_contours))
 
@@ -77,16 +90,20 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
                 layers.append(outs[3][..., 0].to(torch.uint8).cpu().numpy())
             slot = b & 1
             inst_h = self._to_host_async(("inst", slot), inst)
-            table_h = {k: self._to_host_async(("tab", k, slot), v) for k, v in table.items()}
+            table_h = {}
+            for k, v in table.items():
+                cap = self.contour_vertices_fast if k == "cont_xy" else (self.table_rows_fast if v.dim() > 1 else None)
+                table_h[k] = self._to_host_async(("tab", k, slot), v if cap is None or v.shape[1] <= cap else v[:, :cap])
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             if self.return_probabilities:
                 heads.append([o.clone() for o in outs])
             if pending is not None:
                 finish(pending)
-            pending = (ev, inst_h, table_h)
+            pending = (ev, inst_h, table_h, table)
         if pending is not None:
             finish(pending)
+        self._inst_host = inst_host
         if two_task:
             return insts, infos, heads, [type(self.model)._proc_ls(m) for batch in layers for m in batch]  # noqa: SLF001
         return insts, infos, heads
@@ -94,8 +111,12 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
     def post_process_patches(self, raw, n_total: int) -> dict:
         insts, infos, heads = raw[:3]
         dist, rank, world = self._dist()
-        local = torch.cat(insts) if insts else torch.empty((0, 1, 1), dtype=torch.int32, device=self.device)
-        inst_all = self._all_gather_rows(local, n_total).cpu().numpy()
+        if dist is None and insts:   # single rank: the instance maps already came back through the pinned buffers
+            inst_all = np.concatenate(self._inst_host)
+        else:
+            local = torch.cat(insts) if insts else torch.empty((0, 1, 1), dtype=torch.int32, device=self.device)
+            inst_all = self._all_gather_rows(local, n_total).cpu().numpy()
+            self.d2h_bytes += inst_all.nbytes
         if dist is not None:
             gathered = [None] * world
             dist.all_gather_object(gathered, infos)

@@ -181,6 +181,8 @@ class WsiTileModeMixin:
                 pad = (0, 0, 0, max(self.min_tile - tw, 0), 0, max(self.min_tile - th, 0))
                 stacks = [torch.nn.functional.pad(s, pad).contiguous() for s in stacks]
             inst, table = self._wsi_postproc(stacks[0], stacks[1], stacks[2] if has_tp else None)
+            if getattr(self, "device_contours", False) and inst.is_cuda:
+                pp.trace_contours(inst.contiguous(), table)     # vertices in tile coordinates, before any sliver crop (pad is background)
             inst = inst[:, :th, :tw]
             inst_h = inst.cpu().numpy()
             tab = {k: v.cpu().numpy() for k, v in table.items()}
