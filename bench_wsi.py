@@ -8,7 +8,8 @@ public call — `NucleusInstanceSegmentor.run(slide, patch_mode=False, return_pr
 `preproc_func` — on a virtual slide generated tile-wise from a seed: host slide in, merged instance table + int32
 instance map out, i.e. everything (upload, patches, stain, network, stitching, tile post-processing, contours, gather, merge replay) is inside
 the timed region.  Wall clock around a barrier + synchronize on both sides, max over ranks; prints one JSON line on rank 0.
-Status: written after round 1's GPU budget was spent — not yet measured."""
+Status: the data flow is parity-green on the B200 at small size (tests/test_wsi_gpu.py); this harness itself has not been run yet (round 1's GPU
+budget was spent before it was written)."""
 from __future__ import annotations
 
 import argparse

@@ -15,8 +15,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
-# GPU test modules written after round 1's GPU budget was spent (not yet run on a B200): they are collected AFTER the modules that have
-# been, so that with `-x` a first-run failure in new code cannot hide the results of the established hot-path tests.
+# GPU test modules added last in round 1 (each has passed on a B200 once: profiles/r1h_gpu_tests_*.log): they are collected AFTER the
+# long-established modules, so that with `-x` a failure in the newest code cannot hide the results of the hot-path tests.
 _NEWEST_GPU_MODULES = ("test_reinhard_gpu", "test_augment_gpu", "test_contours_gpu", "test_wsi_gpu", "test_hovernetplus_gpu")
 
 
