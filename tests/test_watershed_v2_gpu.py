@@ -1,0 +1,58 @@
+"""The opt-in version-2 flood (8-ary heap, one warp per component) on the device: bit-exact against the oracle and the default flood,
+on 164-px maps, a 512-px tile and both scale factors; prints both timings (`-s`) for the round-2 decision to make it the default."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import hovernet_postproc_oracle as po
+from tiatoolbox_b200.synthetic import hovernet_head_maps
+
+pytestmark = pytest.mark.gpu
+
+
+def test_v2_flood_bit_exact_and_timed(built_lib):
+    import torch
+
+    from tiatoolbox_b200.models import postproc as pp
+
+    def run(maps, scale=1.0):
+        inst, table = pp.proc_np_hv_batch(*[torch.from_numpy(a).cuda() for a in maps], scale_factor=scale)
+        return inst.cpu().numpy(), {k: v.cpu().numpy() for k, v in table.items()}
+
+    def timed(maps):
+        d = [torch.from_numpy(a).cuda() for a in maps]
+        for _ in range(2):
+            pp.proc_np_hv_batch(*d)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            pp.proc_np_hv_batch(*d)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 5
+
+    small = hovernet_head_maps(16, 164, seed=0)
+    big = hovernet_head_maps(1, 512, seed=3)
+    try:
+        pp.set_watershed_impl(1)
+        ref_small, tab1 = run(small)
+        ref_big, _ = run(big)
+        ref_half, _ = run(small, 0.5)
+        t1 = timed(small)
+        pp.set_watershed_impl(2)
+        got_small, tab2 = run(small)
+        got_big, _ = run(big)
+        got_half, _ = run(small, 0.5)
+        t2 = timed(small)
+    finally:
+        pp.set_watershed_impl(1)
+    for i in range(16):
+        assert np.array_equal(got_small[i], po.proc_np_hv(small[0][i], small[1][i])), i
+        assert np.array_equal(got_half[i], ref_half[i]), i
+    assert np.array_equal(got_small, ref_small) and np.array_equal(got_big, ref_big)
+    assert np.array_equal(got_big[0], po.proc_np_hv(big[0][0], big[1][0]))
+    for k in tab1:
+        assert np.array_equal(tab1[k], tab2[k]), k
+    print(f"\npost-processing of 16 maps (164 px, ~40 nuclei): flood v1 {t1:.2f} ms, flood v2 {t2:.2f} ms")

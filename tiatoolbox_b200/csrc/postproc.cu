@@ -26,6 +26,7 @@
 #include "../../include/tiab200.h"
 #include "contour_math.cuh"
 #include "ctx.h"
+#include "watershed_math.cuh"
 
 namespace tiab {
 
@@ -628,6 +629,27 @@ __global__ void __launch_bounds__(PP_THREADS) pp_inst_finalize(int N, int maxI, 
   }
 }
 
+// Version 2 of the flood: one WARP per component (lane 0 walks, so components never wait on each other inside a divergent warp) over the
+// 8-ary heap of watershed_math.cuh, total order (value, age, index).  Selected with tiab_hovernet_set_watershed(h, 2).
+__global__ void __launch_bounds__(128) pp_watershed_v2(const int* __restrict__ roots, const int* __restrict__ ncomp, const int* __restrict__ lab,
+                                                       const int* __restrict__ size, const int* __restrict__ bbox, const int* __restrict__ heap_off,
+                                                       const uint8_t* __restrict__ blb, const int* __restrict__ marker,
+                                                       const double* __restrict__ dist, int H, int W, int N, int maxcomp,
+                                                       HeapItem* __restrict__ heap, int* __restrict__ inst) {
+  if (threadIdx.x & 31) return;
+  const int P = H * W;
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n = (int)(t / maxcomp), c = (int)(t % maxcomp);
+  if (n >= N || c >= ncomp[n]) return;
+  const long long base = (long long)n * P;
+  const int r = roots[base + c];
+  if (size[base + r] <= 9) return;
+  const int* bb = bbox + 4 * (base + r);
+  static_assert(sizeof(HeapItem) == sizeof(WsItem), "the heap arena is shared between the two flood versions");
+  ws_flood<8>(lab + base, r, bb[0], bb[1], bb[2], bb[3], blb + base, marker + base, dist + base, H, W,
+              reinterpret_cast<WsItem*>(heap + base + heap_off[base + r]), inst + base);
+}
+
 // Contours of the tabulated instances (hovernet.py:685-693): one thread per table row walks the instance's outer border twice — once to
 // count the CHAIN_APPROX_SIMPLE vertices, once to write them into a slice reserved with one atomicAdd on the image's vertex counter.
 __global__ void __launch_bounds__(128) pp_contours(const int32_t* __restrict__ inst_map, int N, int H, int W, int max_inst,
@@ -702,6 +724,22 @@ extern "C" {
 
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]) {
   sobel_kernels(deriv, smooth);
+  return TIAB_OK;
+}
+
+int tiab_hovernet_set_watershed(tiab_handle_t h, int impl) {
+  if (!h || (impl != 1 && impl != 2)) return TIAB_E_INVALID;
+  h->pp_watershed_impl = impl;
+  return TIAB_OK;
+}
+
+int tiab_dbg_watershed(const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W, int32_t* out_host) {
+  if (!dist_host || !markers_host || !mask_host || !out_host || H <= 0 || W <= 0) return TIAB_E_INVALID;
+  const long long P = (long long)H * W;
+  std::vector<WsItem> heap((size_t)P);
+  std::vector<int> marker((size_t)P);
+  for (long long p = 0; p < P; ++p) marker[p] = mask_host[p] ? markers_host[p] : 0, out_host[p] = 0;   // out = markers * mask
+  ws_flood<8>(nullptr, 0, 0, 0, W - 1, H - 1, mask_host, marker.data(), dist_host, H, W, heap.data(), out_host);
   return TIAB_OK;
 }
 
@@ -858,8 +896,14 @@ int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const fl
     // one thread per possible component rank (ranks >= ncomp[n] and removed small components exit immediately)
     const int mc = P;
     const long long nthreads = (long long)N * mc;
-    PP_LAUNCH(h, pp_watershed, (unsigned)((nthreads + 63) / 64), 64, w.roots, w.ncomp, w.lab, w.size, w.bbox, w.heap_off, w.blb, w.marker,
-              w.dist, H, W, N, mc, w.heap, inst_map);
+    if (h->pp_watershed_impl == 2) {
+      // only ranks below the largest component count can be live: bound the grid by min(P, a generous per-image cap) warps per image
+      PP_LAUNCH(h, pp_watershed_v2, (unsigned)((nthreads * 32 + 127) / 128), 128, w.roots, w.ncomp, w.lab, w.size, w.bbox, w.heap_off, w.blb,
+                w.marker, w.dist, H, W, N, mc, w.heap, inst_map);
+    } else {
+      PP_LAUNCH(h, pp_watershed, (unsigned)((nthreads + 63) / 64), 64, w.roots, w.ncomp, w.lab, w.size, w.bbox, w.heap_off, w.blb, w.marker,
+                w.dist, H, W, N, mc, w.heap, inst_map);
+    }
   }
   // 8. instance table (hovernet.py:670-748, without contours)
   if (want_table) {

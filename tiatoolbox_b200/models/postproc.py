@@ -50,6 +50,14 @@ def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.T
     return inst, table
 
 
+def set_watershed_impl(impl: int, device: int = 0) -> None:
+    """Flood implementation used by `proc_np_hv_batch` on this thread's handle of `device`: 1 = binary heap, one thread per foreground
+    component (the round-1 default); 2 = 8-ary heap with the total order (value, age, index), one warp per component
+    (csrc/watershed_math.cuh — host-compiled and equal to the oracle on the CPU; to become the default once measured on the B200)."""
+    hd = _lib.handle(device)
+    _lib.check(hd, _lib.lib().tiab_hovernet_set_watershed(hd, int(impl)))
+
+
 def trace_contours(inst: torch.Tensor, table: dict, capacity: int | None = None) -> dict:
     """Contours of every tabulated instance on the device (the `cv2.findContours(..., RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0]` of
     hovernet.py:685-693): adds `cont_off`, `cont_len` (N, max_inst), `cont_total` (N,) and `cont_xy` (N, capacity, 2) int32 tensors to
