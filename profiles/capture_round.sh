@@ -20,7 +20,11 @@ step watershed_v2 120 python -m pytest tests/test_watershed_v2_gpu.py -q -m gpu 
 step ncu_launches 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
      python bench.py --steps 2 --warmup 1 --no-cpu-baseline
 # 5. full captures of the kernels that matter (3 launches each)
-for pat in conv_gemm_kernel stain_fused_kernel reinhard_apply_kernel reinhard_hist_kernel pp_watershed; do
+for pat in conv_gemm_kernel stain_fused_kernel; do      # launched by the headline bench
+  step ncu_$pat 400 ncu --set full --clock-control none --import-source on -k regex:$pat -s 4 -c 3 -o $out/${tag}_$pat \
+       python bench.py --steps 1 --warmup 1 --no-cpu-baseline
+done
+for pat in reinhard_apply_kernel reinhard_hist_kernel pp_watershed pp_contours; do      # launched by the new-kernel timing script
   step ncu_$pat 300 ncu --set full --clock-control none --import-source on -k regex:$pat -s 4 -c 3 -o $out/${tag}_$pat \
        python profiles/measure_new_kernels.py
 done
