@@ -361,9 +361,12 @@ def main():
                         conv_launches=sum(1 for op in plan.ops if hasattr(op, "desc")))
 
     # ---- e2e leg: numpy host buffers through the public API ----
-    host_tiles = np.ascontiguousarray(x[:min(Be, B)].cpu().numpy())
-    if len(host_tiles) < Be:
-        host_tiles = np.concatenate([host_tiles] * (-(-Be // len(host_tiles))))[:Be]
+    # combined workload under torchrun: every rank hands the SAME tile list to eng.run, which shards it — so the list holds Be tiles per
+    # rank (weak scaling, like the device-resident leg)
+    Be_total = Be * world if combined else Be
+    host_tiles = np.ascontiguousarray(x[:min(Be_total, B)].cpu().numpy())
+    if len(host_tiles) < Be_total:
+        host_tiles = np.concatenate([host_tiles] * (-(-Be_total // len(host_tiles))))[:Be_total]
     if combined:
         eng = NucleusInstanceSegmentor(model, batch_size=B, device=str(dev))
         model.preproc_func = norm.transform
@@ -371,7 +374,7 @@ def main():
         d2h = Be * 164 * 164 * 4
     else:
         e2e_call = lambda: norm.transform_batch(host_tiles, raise_on_error=False)  # noqa: E731
-        d2h = Be * PATCH * PATCH * 3 + Be * 68
+        d2h = world * (Be * PATCH * PATCH * 3 + Be * 68)
     for _ in range(2):
         r = e2e_call()
     if world > 1:
@@ -387,8 +390,8 @@ def main():
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    # under torchrun eng.run shards host_tiles across ranks itself (strong over Be): total work = Be per step
-    e2e_units = Be if (combined and world > 1) else world * Be
+    # total tiles per step over all ranks: eng.run shards the Be_total list itself; the stain-only call runs Be tiles on every rank
+    e2e_units = Be_total if combined else world * Be
     e2e_value = e2e_units * args.steps / float(te.item())
 
     if rank == 0:
@@ -404,8 +407,8 @@ def main():
                        "l2_policy": ("activations %.1f GB per step >> 126 MB L2" % (plan.bytes_allocated() / 1e9)) if combined else
                                     f"inputs+outputs {2 * B * PATCH * PATCH * 3 / 1e6:.0f} MB per step > 126 MB L2",
                        "parallelism": f"patch-shard x{world}, all-gather of the result map"},
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": Be * PATCH * PATCH * 3, "d2h_bytes_per_step": d2h,
-                    "tiles_per_step": Be, "api": "NucleusInstanceSegmentor.run(numpy tiles), preproc_func = MacenkoNormalizer.transform"
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": e2e_units * PATCH * PATCH * 3, "d2h_bytes_per_step": d2h,
+                    "tiles_per_step": e2e_units, "api": "NucleusInstanceSegmentor.run(numpy tiles), preproc_func = MacenkoNormalizer.transform"
                     if combined else "StainNormalizer.transform_batch(numpy)"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
