@@ -270,6 +270,9 @@ class WsiTileModeMixin:
         if image.ndim != 3 or image.shape[2] != 3 or image.dtype != np.uint8:  # noqa: PLR2004
             msg = "WSI mode expects an in-memory (H, W, 3) uint8 array (slide files are read by WSIReader, outside the B200 path)"
             raise ValueError(msg)
+        if getattr(self.model, "num_layers", None) is not None:
+            msg = "WSI mode of two-task models (HoVerNetPlus: nuclei + layer map) is not built yet; use patch mode"
+            raise NotImplementedError(msg)
         io = ioconfig or self.ioconfig
         if io is None or io.patch_output_shape is None:
             msg = "an ioconfig with patch_input_shape / patch_output_shape / stride_shape is required for WSI mode"
