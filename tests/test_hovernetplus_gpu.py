@@ -73,3 +73,23 @@ def test_two_task_engine_contract(built_lib):
     res = eng.model.postproc([np_m[0], hv_m[0], tp_m[0], ls_m[0]])
     assert [r["task_type"] for r in res] == ["nuclei_segmentation", "layer_segmentation"] and res[1]["seg_type"] == "semantic"
     assert np.array_equal(res[0]["predictions"], nuc["predictions"][0]) and np.array_equal(res[1]["predictions"], lay["predictions"][0])
+
+
+def test_two_task_wsi_mode_region(built_lib):
+    """HoVerNetPlus on an in-memory region (fits one 2048-px tile: the un-tiled branch): nested two-task output == the oracle post-processing
+    of the stitched head maps."""
+    from tiatoolbox_b200.models.engine import NucleusInstanceSegmentor
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    eng = NucleusInstanceSegmentor("hovernetplus-oed", batch_size=4, device="cuda")
+    eng.model.load_state_dict(hovernetplus_test_weights())
+    t = he_tiles(6, 256, 256, seed=3)
+    region = np.concatenate([np.concatenate(list(t[:3]), axis=1), np.concatenate(list(t[3:]), axis=1)], axis=0)[:420, :600].copy()
+    out = eng.run(region, patch_mode=False, return_predictions=True, return_probabilities=True)
+    assert set(out) >= {"nuclei_segmentation", "layer_segmentation", "coordinates", "probabilities"}
+    heads = out["probabilities"]
+    assert len(heads) == 4 and heads[3].shape == (420, 600, 1)
+    inst, info, layer, linfo = po.postproc_plus(*heads)
+    nuc, lay = out["nuclei_segmentation"], out["layer_segmentation"]
+    assert np.array_equal(nuc["predictions"], inst) and len(nuc.get("box", [])) == len(info)
+    assert np.array_equal(lay["predictions"], layer) and len(lay.get("box", [])) == len(linfo)

@@ -97,12 +97,12 @@ class StubEngine(NucleusInstanceSegmentor):
         res = stitch_oracle.stitch(blocks.numpy(), locs, canvas_width=width, output_shape=(out.shape[0], out.shape[1]))
         out.copy_(torch.from_numpy(res))
 
-    def _wsi_postproc(self, np_map, hv_map, tp_map):
+    def _wsi_postproc(self, np_map, hv_map, tp_map, scale_factor=1.0):
         n, h, w = np_map.shape[:3]
-        max_inst = max(16, (h * w) // 10 + 1)
+        max_inst = max(16, (h * w) // 3 + 1)
         insts, rows = [], []
         for i in range(n):
-            inst = ppo.proc_np_hv(np_map[i].numpy(), hv_map[i].numpy())
+            inst = ppo.proc_np_hv(np_map[i].numpy(), hv_map[i].numpy(), scale_factor=scale_factor)
             insts.append(inst.astype(np.int32))
             rows.append(table_from_inst(inst, tp_map[i].numpy(), max_inst))
         table = {k: torch.from_numpy(np.stack([r[k] for r in rows])) for k in rows[0]}
@@ -206,3 +206,53 @@ def test_wsi_mode_world2_equals_world1():
     assert calls[1] == 2 * 3 and 0 < calls[0] <= 30
     for _, _, out in res:                               # every rank returns the full result
         check(out, kept, wsi_pred)
+
+
+# ---- two-task model (HoVerNetPlus): nuclei at scale 0.5 + layer map, both merged tile by tile -----------------------------------------
+def decode_heads4(rgb: np.ndarray) -> list[np.ndarray]:
+    """The three heads of `decode_heads` plus a pixel-wise 5-class layer head: the tissue background decodes to one class (large regions that
+    pass `_proc_ls`'s 20 000-pixel filter inside a grid tile but not inside a strip), nuclei interiors to speckles of the others."""
+    npm, hv, tp = decode_heads(rgb)
+    ls = (((rgb[..., 0:1] > 128).astype(np.int64) + rgb[..., 1:2] // 64 + rgb[..., 2:3] // 64) % 5).astype(np.float32)
+    return [npm, hv, tp, ls]
+
+
+class StubEnginePlus(StubEngine):
+    def __init__(self, batch_size: int = 5) -> None:  # noqa: D107
+        super().__init__(batch_size)
+        from tiatoolbox_b200.models.architecture.hovernetplus import HoVerNetPlus
+
+        self.model = SimpleNamespace(_plan_batch=None, num_layers=5, tasks=["nuclei_segmentation", "layer_segmentation"],
+                                     _proc_ls=HoVerNetPlus._proc_ls, _get_layer_info=HoVerNetPlus._get_layer_info)
+
+    def _wsi_forward(self, x):
+        self.forward_calls += 1
+        return [torch.from_numpy(np.ascontiguousarray(h)) for h in decode_heads4(x.numpy()[:, 12:52, 12:52])]
+
+
+def expected_result_plus(image: np.ndarray, io: IOConfig):
+    heads = decode_heads4(image)
+    h, w = image.shape[:2]
+    nuc_tiles, lay_tiles = [], []
+    wsi_pred, wsi_layer, mx = np.zeros((h, w), np.int32), np.zeros((h, w), np.uint8), None
+    for bounds, flag, mode in wo.build_tile_tasks(wo.get_tile_info((w, h), io.tile_shape, io.patch_output_shape, io.margin)):
+        x0, y0, x1, y1 = (int(v) for v in bounds)
+        inst, info, layer, linfo = ppo.postproc_plus(*[hd[max(y0, 0):y1, max(x0, 0):x1] for hd in heads])
+        mx = wo.paste_instance_tile(wsi_pred, inst, bounds, mx)
+        wsi_layer[y0:min(y1, h), x0:min(x1, w)] = layer[: min(y1, h) - y0, : min(x1, w) - x0]
+        nuc_tiles.append((bounds, flag, mode, list(info.values())))
+        lay_tiles.append((bounds, flag, mode, list(linfo.values())))
+    return wo.replay_merge(nuc_tiles, io.margin), wo.replay_merge(lay_tiles, io.margin), wsi_pred, wsi_layer
+
+
+def test_two_task_wsi_mode_matches_the_oracle_flow():
+    image = synthetic_slide(390, 450, seed=7)
+    nuc, lay, wsi_pred, wsi_layer = expected_result_plus(image, IO_SMALL)
+    out = StubEnginePlus().run(image, patch_mode=False, return_predictions=True)
+    assert set(out) == {"nuclei_segmentation", "layer_segmentation", "coordinates"}
+    check(out["nuclei_segmentation"], nuc, wsi_pred)
+    got = out["layer_segmentation"]
+    assert len(lay) > 3 and len(got["box"]) == len(lay) and len(np.unique(wsi_layer)) >= 2
+    for i, rec in enumerate(lay):
+        assert np.array_equal(got["box"][i], rec["box"]) and np.array_equal(got["contours"][i], rec["contours"]) and got["type"][i] == rec["type"]
+    assert got["predictions"].dtype == np.uint8 and np.array_equal(got["predictions"], wsi_layer)

@@ -106,9 +106,9 @@ class WsiTileModeMixin:
 
         stitch_patches(blocks, locs, canvas_width=width, output_shape=(out.shape[0], out.shape[1]), out=out)
 
-    def _wsi_postproc(self, np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.Tensor | None):
+    def _wsi_postproc(self, np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.Tensor | None, scale_factor: float = 1.0):
         """(n, h, w, C) head tiles -> (inst (n, h, w) int32, instance table) on the device (csrc/postproc.cu)."""
-        return pp.proc_np_hv_batch(np_map, hv_map, tp_map)
+        return pp.proc_np_hv_batch(np_map, hv_map, tp_map, scale_factor=scale_factor)
 
     # ---- stages ------------------------------------------------------------------------------------------------------------
     def _wsi_upload(self, image: np.ndarray, plan: WsiTilePlan) -> torch.Tensor:
@@ -154,11 +154,14 @@ class WsiTileModeMixin:
         return canvases or []
 
     def _wsi_postproc_tiles(self, canvases: list[torch.Tensor], plan: WsiTilePlan, *, keep_maps: bool):
-        """This rank's tiles -> [(task index, tile instance dict, tile inst map (device int32) | None)] in task order."""
+        """This rank's tiles -> [(task index, tile instance dict, tile inst map (device int32) | None, extra)] in task order; `extra` is
+        None for HoVer-Net and (layer region dict, layer map uint8 | None) for the two-task HoVerNetPlus (hovernetplus.py:267-410 per tile)."""
         results = []
         if not canvases:
             return results
         has_tp = len(canvases) > 2
+        two_task = getattr(self.model, "num_layers", None) is not None
+        scale = 0.5 if two_task else 1.0
 
         def clipped(i):
             x0, y0, x1, y1 = (int(v) for v in plan.tasks[i][0])
@@ -180,15 +183,20 @@ class WsiTileModeMixin:
                 # sliver is extended with background (all heads 0) and the instance map cropped back
                 pad = (0, 0, 0, max(self.min_tile - tw, 0), 0, max(self.min_tile - th, 0))
                 stacks = [torch.nn.functional.pad(s, pad).contiguous() for s in stacks]
-            inst, table = self._wsi_postproc(stacks[0], stacks[1], stacks[2] if has_tp else None)
+            inst, table = self._wsi_postproc(stacks[0], stacks[1], stacks[2] if has_tp else None, scale_factor=scale)
             if getattr(self, "device_contours", False) and inst.is_cuda:
                 pp.trace_contours(inst.contiguous(), table)     # vertices in tile coordinates, before any sliver crop (pad is background)
             inst = inst[:, :th, :tw]
             inst_h = inst.cpu().numpy()
             tab = {k: v.cpu().numpy() for k, v in table.items()}
+            layers = stacks[3][:, :th, :tw, 0].cpu().numpy() if two_task else None
             for j, i in enumerate(group):
                 info = pp.instance_info(inst_h[j], {k: v[j] for k, v in tab.items()}, with_contours=True)
-                results.append((i, {k + 1: rec for k, rec in enumerate(info.values())}, inst[j] if keep_maps else None))
+                extra = None
+                if two_task:   # the layer task of this tile: whole-tile morphology + region contours on the host (OpenCV, like the reference)
+                    layer = self.model._proc_ls(layers[j])  # noqa: SLF001
+                    extra = (self.model._get_layer_info(layer), layer if keep_maps else None)  # noqa: SLF001
+                results.append((i, {k + 1: rec for k, rec in enumerate(info.values())}, inst[j] if keep_maps else None, extra))
             group.clear()
 
         shape = None
@@ -196,7 +204,7 @@ class WsiTileModeMixin:
             x0, y0, x1, y1 = clipped(i)
             s = (y1 - y0, x1 - x0)
             if s[0] <= 0 or s[1] <= 0:
-                results.append((i, {}, None))
+                results.append((i, {}, None, ({}, None) if two_task else None))
                 continue
             if s != shape or len(group) >= self.tile_batch:
                 flush()
@@ -207,19 +215,19 @@ class WsiTileModeMixin:
         return results
 
     def _wsi_gather(self, results, plan: WsiTilePlan, *, keep_maps: bool):
-        """Exchange the per-tile results: object all-gather of the instance records, ONE tensor all-gather of the flattened instance
-        maps.  Returns {task index: (inst_dict, inst_map numpy | None)} on every rank."""
+        """Exchange the per-tile results: object all-gather of the instance records (and of the two-task model's layer results), ONE tensor
+        all-gather of the flattened instance maps.  Returns {task index: (inst_dict, inst_map numpy | None, extra)} on every rank."""
         dist, rank, world = self._dist()
         merged = {}
         if dist is None:
-            for i, d, m in results:
-                merged[i] = (d, None if m is None else m.cpu().numpy())
+            for i, d, m, extra in results:
+                merged[i] = (d, None if m is None else m.cpu().numpy(), extra)
             return merged
         gathered = [None] * world
-        dist.all_gather_object(gathered, [(i, d, None if m is None else tuple(m.shape)) for i, d, m in results])
+        dist.all_gather_object(gathered, [(i, d, None if m is None else tuple(m.shape), extra) for i, d, m, extra in results])
         maps_by_rank = [None] * world
         if keep_maps:
-            flat = [m.reshape(-1) for _, _, m in results if m is not None]
+            flat = [m.reshape(-1) for _, _, m, _ in results if m is not None]
             mine = torch.cat(flat) if flat else torch.empty(0, dtype=torch.int32, device=self.device)
             n = torch.tensor([mine.numel()], dtype=torch.long, device=self.device)
             sizes = [torch.zeros_like(n) for _ in range(world)]
@@ -233,46 +241,62 @@ class WsiTileModeMixin:
             maps_by_rank = [out[r, : int(sizes[r].item())] for r in range(world)]
         for r, part in enumerate(gathered):
             off = 0
-            for i, d, shp in part:
+            for i, d, shp, extra in part:
                 m = None
                 if shp is not None and keep_maps:
                     cnt = int(shp[0]) * int(shp[1])
                     m = maps_by_rank[r][off: off + cnt].reshape(shp)
                     off += cnt
-                merged[i] = (d, m)
+                merged[i] = (d, m, extra)
         return merged
 
     def _wsi_replay(self, merged: dict, plan: WsiTilePlan, *, return_predictions: bool) -> dict:
-        """`_process_tile_mode`'s merge loop (:1230-1279) over all tiles in task order -> the task's output entries."""
+        """`_process_tile_mode`'s merge loop (:1230-1279) over all tiles in task order -> the output entries of the task (one task), or
+        {task name: entries} for the two-task model: its layer regions go through the same margin logic keyed on their boxes, and its
+        semantic tile maps are pasted in order (later tiles overwrite, `_update_tile_based_predictions_array` :3160-3212)."""
         store = wm.WsiInstanceStore()
+        two_task = any(v[2] is not None for v in merged.values())
+        layer_store = wm.WsiInstanceStore() if two_task else None
         wsi_pred = np.zeros((plan.H, plan.W), dtype=np.int32) if return_predictions else None
+        wsi_layer = np.zeros((plan.H, plan.W), dtype=np.uint8) if (return_predictions and two_task) else None
         max_inst = None
         for i, (bounds, flag, mode) in enumerate(plan.tasks):
-            inst_dict, inst_map = merged.get(i, ({}, None))
+            inst_dict, inst_map, extra = merged.get(i, ({}, None, None))
             if wsi_pred is not None and inst_map is not None:
                 max_inst = wm.update_tile_based_predictions_array(inst_map, wsi_pred, bounds, (0, 0), max_inst)
+            if extra is not None and wsi_layer is not None and extra[1] is not None:
+                wm.update_tile_based_predictions_array(extra[1], wsi_layer, bounds, (0, 0), seg_type="semantic")
             if plan.tile_mode:
                 store.merge_tile(inst_dict, tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin)
+                if extra is not None:
+                    layer_store.merge_tile(extra[0], tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin)
             else:   # `_process_full_wsi` :999-1076: one postproc call over the whole map, nothing to merge
                 for rec in inst_dict.values():
                     store._append(rec)  # noqa: SLF001
+                for rec in (extra[0].values() if extra is not None else ()):
+                    layer_store._append(rec)  # noqa: SLF001
         out = dict(store.to_info_dict())
         if wsi_pred is not None:
             out["predictions"] = wsi_pred
-        return out
+        if not two_task:
+            return out
+        layer_out = dict(layer_store.to_info_dict())
+        if wsi_layer is not None:
+            layer_out["predictions"] = wsi_layer
+        tasks = self.model.tasks
+        return {tasks[0]: out, tasks[1]: layer_out}
 
     # ---- entry ---------------------------------------------------------------------------------------------------------------
     def run_wsi(self, image: np.ndarray, *, ioconfig=None, return_predictions: bool = False, return_probabilities: bool = False) -> dict:
         """One in-memory slide / region (H, W, 3) uint8 -> {"box", "centroid", "contours", "prob", "type": object arrays over the merged
         instances in WSI coordinates (absent when nothing was found, like the reference), "coordinates": (N, 4) patch input boxes,
-        ["predictions": (H, W) int32 instance map], ["probabilities": [np, hv, tp] WSI head maps (single-rank runs only)]}."""
+        ["predictions": (H, W) int32 instance map], ["probabilities": [np, hv, tp] WSI head maps (single-rank runs only)]}.  A two-task
+        model (HoVerNetPlus) nests the entries under its task names and adds the layer task's "box" / "contours" / "type"
+        [/ "predictions": (H, W) uint8 layer map]."""
         image = np.ascontiguousarray(image)
         if image.ndim != 3 or image.shape[2] != 3 or image.dtype != np.uint8:  # noqa: PLR2004
             msg = "WSI mode expects an in-memory (H, W, 3) uint8 array (slide files are read by WSIReader, outside the B200 path)"
             raise ValueError(msg)
-        if getattr(self.model, "num_layers", None) is not None:
-            msg = "WSI mode of two-task models (HoVerNetPlus: nuclei + layer map) is not built yet; use patch mode"
-            raise NotImplementedError(msg)
         io = ioconfig or self.ioconfig
         if io is None or io.patch_output_shape is None:
             msg = "an ioconfig with patch_input_shape / patch_output_shape / stride_shape is required for WSI mode"
