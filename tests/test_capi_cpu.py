@@ -27,6 +27,20 @@ def test_header_symbols_exported(built_lib):
     assert built_lib.tiab_version() == b"0.1"
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/tiab200.h must compile as C99 (no torch / C++ types in the signatures) and as C++."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = str(ROOT / "include" / "tiab200.h")
+    for args in (["-std=c99", "-x", "c"], ["-std=c++17", "-x", "c++"]):
+        r = subprocess.run([gcc, *args, "-fsyntax-only", "-Wall", "-Werror", hdr], capture_output=True, text=True, check=False)
+        assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 

@@ -121,3 +121,53 @@ def test_patch_pipeline_on_cpu_stand_ins(built_lib, monkeypatch, rows_fast, xy_f
         assert eng.d2h_bytes > 5 * full_rows * 16          # at least the full box columns came across
     else:
         assert eng.d2h_bytes < 5 * (164 * 164 * 4 + 512 * 64 + 4096 * 8 + 4096)
+
+
+# ---- world_size 2 (gloo): contiguous patch shards, all-gather of the instance maps + object gather of the records ----------------------
+def _worker(rank: int, world: int, port: int, q):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tiatoolbox_b200 import _lib
+
+    heads = hovernet_head_maps(5, 164, seed=33)
+    pp.proc_np_hv_batch = _cpu_postproc
+    pp.trace_contours = _cpu_trace_contours(_lib.lib())
+    torch.cuda.Event = _Event
+    torch.cuda.current_stream = lambda *_a, **_k: SimpleNamespace(cuda_stream=0)
+    lo, hi = NucleusInstanceSegmentor.shard_bounds(5, rank, world)
+    eng = _CpuEngine(tuple(h[lo:hi] for h in heads), batch_size=2)      # the stand-in network serves this rank's shard in order
+    eng.labels = None
+    out = eng.run(np.zeros((5, 256, 256, 3), np.uint8))
+    q.put((rank, lo, hi, out["predictions"], [[np.asarray(b) for b in boxes] for boxes in out["box"]], int(eng.d2h_bytes)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_patch_pipeline_world2(built_lib):
+    import os
+
+    import torch.multiprocessing as mp
+
+    heads = hovernet_head_maps(5, 164, seed=33)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted((r[1], r[2]) for r in res) == [(0, 3), (3, 5)]
+    for _, _, _, preds, boxes, d2h in res:            # every rank returns the complete result
+        assert preds.shape == (5, 164, 164) and d2h > 0
+        for i in range(5):
+            ref_inst, ref_info = po.postproc(heads[0][i], heads[1][i], heads[2][i])
+            assert np.array_equal(preds[i], ref_inst) and len(boxes[i]) == len(ref_info)
+            assert all(np.array_equal(a, r["box"]) for a, r in zip(boxes[i], ref_info.values()))
