@@ -85,6 +85,7 @@ class StubEngine(NucleusInstanceSegmentor):
         self.model = SimpleNamespace(_plan_batch=None)
         self.return_probabilities = False
         self.forward_calls = 0
+        self.cpu_contours = False
 
     def _wsi_forward(self, x):
         assert x.dtype == torch.uint8 and x.is_contiguous() and x.shape[1:] == (64, 64, 3) and x.shape[0] <= self.batch_size
@@ -106,7 +107,13 @@ class StubEngine(NucleusInstanceSegmentor):
             insts.append(inst.astype(np.int32))
             rows.append(table_from_inst(inst, tp_map[i].numpy(), max_inst))
         table = {k: torch.from_numpy(np.stack([r[k] for r in rows])) for k in rows[0]}
-        return torch.from_numpy(np.stack(insts)), table
+        inst_t = torch.from_numpy(np.stack(insts))
+        if self.cpu_contours:   # the device contour buffers, filled by the host-compiled tracer: exercises the vertex slicing of the tile loop
+            from tests.test_instance_engine_cpu import _cpu_trace_contours
+            from tiatoolbox_b200 import _lib
+
+            _cpu_trace_contours(_lib.lib())(inst_t, table)
+        return inst_t, table
 
 
 def expected_result(image: np.ndarray, io: IOConfig):
@@ -160,6 +167,9 @@ def test_wsi_mode_single_rank_matches_the_oracle_flow():
     eng.return_probabilities = True
     out = eng.run(image, patch_mode=False, return_predictions=(True,))
     check(out, kept, wsi_pred)
+    eng2 = StubEngine()
+    eng2.cpu_contours = True                                  # contours from the (host-compiled) device tracer instead of cv2
+    check(eng2.run(image, patch_mode=False, return_predictions=True), kept, wsi_pred)
     for got, want in zip(out["probabilities"], heads):     # the stitched head canvases equal the pixel-wise decode of the slide
         assert np.array_equal(got, want)
     assert out["coordinates"].shape == (10 * 12, 4) and eng.forward_calls == 10 * 3   # 12 patches per row in batches of 5

@@ -188,6 +188,9 @@ class WsiTileModeMixin:
                 pp.trace_contours(inst.contiguous(), table)     # vertices in tile coordinates, before any sliver crop (pad is background)
             inst = inst[:, :th, :tw]
             inst_h = inst.cpu().numpy()
+            if "cont_xy" in table:   # only the vertices that were written travel (the buffer is sized for the worst case)
+                used = min(int(table["cont_total"].max().item()), table["cont_xy"].shape[1]) if table["cont_total"].numel() else 0
+                table = {**table, "cont_xy": table["cont_xy"][:, : max(used, 1)]}
             tab = {k: v.cpu().numpy() for k, v in table.items()}
             layers = stacks[3][:, :th, :tw, 0].cpu().numpy() if two_task else None
             for j, i in enumerate(group):
