@@ -8,7 +8,11 @@ import pytest
 from oracle import hovernet_postproc_oracle as po
 from tiatoolbox_b200.synthetic import hovernet_head_maps
 
-pytestmark = pytest.mark.gpu
+import os
+
+# Opt-in code paths that have not run on a B200 yet: excluded from the default `-m gpu` run (set TIAB_EXPERIMENTAL=1, as
+# profiles/capture_round.sh does) so that the established suite's verdict cannot depend on them.
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("TIAB_EXPERIMENTAL") != "1", reason="experimental flood: set TIAB_EXPERIMENTAL=1")]
 
 
 def test_v2_flood_bit_exact_and_timed(built_lib):
