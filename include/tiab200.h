@@ -260,11 +260,14 @@ int tiab_hovernet_contours(tiab_handle_t h, const int32_t* inst_map, int N, int 
                            const int32_t* inst_id, const int32_t* inst_box, int capacity, int32_t* cont_off, int32_t* cont_len,
                            int32_t* cont_total, int32_t* cont_xy, void* stream);
 /* Flood implementation of tiab_hovernet_postproc on this handle: 1 = binary heap, one thread per foreground component (default);
- * 2 = 8-ary heap with the total order (value, age, pixel index), one warp per component (csrc/watershed_math.cuh). */
+ * 2 = 8-ary heap with the total order (value, age, pixel index), one warp per component (csrc/watershed_math.cuh);
+ * 3 = the same flood with the component's bounding box and heap staged in shared memory, persistent blocks over a work list. */
 int tiab_hovernet_set_watershed(tiab_handle_t h, int impl);
 /* host-side test hook of csrc/watershed_math.cuh: skimage.segmentation.watershed(dist, markers, mask=mask) on H*W host arrays (float64
  * image, int32 markers, uint8 mask) through the version-2 flood code. */
 int tiab_dbg_watershed(const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W, int32_t* out_host);
+/* the same through version 3's data flow (per-component box-local copies, local raveled indices) */
+int tiab_dbg_watershed_local(const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W, int32_t* out_host);
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]);
 int tiab_dbg_sobel_kernels_k(int ksize, double* deriv, double* smooth);
 /* host-side test hook of csrc/contour_math.cuh: the CHAIN_APPROX_SIMPLE outer border of label `id` (its component that contains the

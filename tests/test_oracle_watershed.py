@@ -10,11 +10,15 @@ from tiatoolbox_b200.synthetic import hovernet_head_maps
 
 
 def _flood(lib, dist: np.ndarray, markers: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """Both host-compiled data flows must agree: the whole-image flood (version 2's code) and the per-component box-local flood (version 3's)."""
     d = np.ascontiguousarray(dist, dtype=np.float64)
     m = np.ascontiguousarray(markers, dtype=np.int32)
     k = np.ascontiguousarray(mask, dtype=np.uint8)
     out = np.empty(d.shape, np.int32)
     assert lib.tiab_dbg_watershed(d.ctypes.data, m.ctypes.data, k.ctypes.data, d.shape[0], d.shape[1], out.ctypes.data) == 0
+    local = np.empty(d.shape, np.int32)
+    assert lib.tiab_dbg_watershed_local(d.ctypes.data, m.ctypes.data, k.ctypes.data, d.shape[0], d.shape[1], local.ctypes.data) == 0
+    assert np.array_equal(out, local)
     return out
 
 

@@ -50,8 +50,16 @@ def test_v2_flood_bit_exact_and_timed(built_lib):
         got_big, _ = run(big)
         got_half, _ = run(small, 0.5)
         t2 = timed(small)
+        pp.set_watershed_impl(3)
+        v3_small, tab3 = run(small)
+        v3_big, _ = run(big)
+        v3_half, _ = run(small, 0.5)
+        t3 = timed(small)
     finally:
         pp.set_watershed_impl(1)
+    assert np.array_equal(v3_small, ref_small) and np.array_equal(v3_big, ref_big) and np.array_equal(v3_half, ref_half)
+    for k in tab1:
+        assert np.array_equal(tab1[k], tab3[k]), k
     for i in range(16):
         assert np.array_equal(got_small[i], po.proc_np_hv(small[0][i], small[1][i])), i
         assert np.array_equal(got_half[i], ref_half[i]), i
@@ -59,4 +67,4 @@ def test_v2_flood_bit_exact_and_timed(built_lib):
     assert np.array_equal(got_big[0], po.proc_np_hv(big[0][0], big[1][0]))
     for k in tab1:
         assert np.array_equal(tab1[k], tab2[k]), k
-    print(f"\npost-processing of 16 maps (164 px, ~40 nuclei): flood v1 {t1:.2f} ms, flood v2 {t2:.2f} ms")
+    print(f"\npost-processing of 16 maps (164 px, ~40 nuclei): flood v1 {t1:.2f} ms, v2 {t2:.2f} ms, v3 {t3:.2f} ms")
