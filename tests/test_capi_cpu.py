@@ -27,6 +27,32 @@ def test_header_symbols_exported(built_lib):
     assert built_lib.tiab_version() == b"0.1"
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and pointer-vs-scalar kind of every ctypes signature against the C prototype (a mismatch would only show as a crash on the GPU)."""
+    import ctypes
+
+    from tiatoolbox_b200 import _lib
+
+    header = (ROOT / "include" / "tiab200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|void|const char\s*\*)\s*(tiab_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        res, args = _lib.SIGNATURES[name]
+        assert len(args) == len(plist), (name, len(args), plist)
+        for a, q in zip(args, plist):
+            is_ptr = "*" in q or "[" in q or q.startswith("tiab_handle_t")
+            ct_ptr = a in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(a, "_type_") and isinstance(a._type_, type)
+            assert is_ptr == bool(ct_ptr), (name, q, a)
+            if not is_ptr:
+                want = {"int": ctypes.c_int, "int32_t": ctypes.c_int, "long long": ctypes.c_longlong, "double": ctypes.c_double,
+                        "float": ctypes.c_float, "unsigned": ctypes.c_uint}
+                base = re.sub(r"\bconst\b", "", q).strip().rsplit(" ", 1)[0].strip()
+                assert a is want[base], (name, q, a)
+
+
 def test_header_is_plain_c():
     """The boundary is a C ABI: include/tiab200.h must compile as C99 (no torch / C++ types in the signatures) and as C++."""
     import shutil
