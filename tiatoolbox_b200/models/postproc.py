@@ -88,36 +88,46 @@ def fetch_debug(which: int, shape, dtype, device=0) -> np.ndarray:
 
 def instance_info(inst_map: np.ndarray, table_row: dict, offset=(0, 0), with_contours: bool = True) -> dict:
     """get_instance_info's dict for ONE image from the device table (numpy views of one image's rows)."""
-    import cv2
-
     offset = np.asarray(offset)
+    count = int(table_row["count"])
     info = {}
+    if count == 0:
+        return info
     device_contours = with_contours and "cont_xy" in table_row
     if device_contours and int(table_row["cont_total"]) > len(table_row["cont_xy"]):
         device_contours = False   # the image needed more vertices than the device buffer holds: trace on the host instead
-    for k in range(int(table_row["count"])):
-        inst_id = int(table_row["id"][k])
-        box = table_row["box"][k].astype(np.int64).copy()
+    # column-wise work first (one numpy call per column instead of one per nucleus), then the per-nucleus records
+    ids = table_row["id"][:count].tolist()
+    raw_boxes = table_row["box"][:count].astype(np.int64)
+    boxes = raw_boxes + np.concatenate([offset, offset])[None]
+    centroids = table_row["centroid"][:count] + offset[None]
+    types = table_row["type"][:count].tolist()
+    probs = table_row["prob"][:count].tolist()
+    if device_contours:
+        lens = table_row["cont_len"][:count].tolist()
+        offs = table_row["cont_off"][:count].tolist()
+        shifted = (table_row["cont_xy"][: int(table_row["cont_total"])] + offset[None]).astype(np.int32)
+    elif with_contours:
+        import cv2
+    for k in range(count):
+        inst_id = ids[k]
         rec = {"box": None, "centroid": None, "contours": None, "prob": None, "type": None}
         if device_contours:
-            n_pts, off = int(table_row["cont_len"][k]), int(table_row["cont_off"][k])
-            if n_pts < 3:  # hovernet.py:696-701 (a squeezed 1- or 2-point contour has shape[0] < 3)  # noqa: PLR2004
+            if lens[k] < 3:  # hovernet.py:696-701 (a squeezed 1- or 2-point contour has shape[0] < 3)  # noqa: PLR2004
                 continue
-            rec["contours"] = (table_row["cont_xy"][off: off + n_pts] + offset[None]).astype(np.int32)
+            rec["contours"] = shifted[offs[k]: offs[k] + lens[k]]
         elif with_contours:
-            crop = (inst_map[box[1]:box[3], box[0]:box[2]] == inst_id).astype(np.uint8)
+            b = raw_boxes[k]
+            crop = (inst_map[b[1]:b[3], b[0]:b[2]] == inst_id).astype(np.uint8)
             contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)[0][0].astype(np.int32)
             contour = np.squeeze(contour)
-            if contour.shape[0] < 3 or len(contour.shape) != 2:  # hovernet.py:696-701
+            if contour.shape[0] < 3 or len(contour.shape) != 2:  # hovernet.py:696-701  # noqa: PLR2004
                 continue
-            rec["contours"] = (contour + (box[:2] + offset)[None]).astype(np.int32)   # hovernet.py:705 adds in place: stays int32
-        rec["centroid"] = table_row["centroid"][k] + offset
-        box[:2] += offset
-        box[2:] += offset
-        rec["box"] = box
-        t = int(table_row["type"][k])
-        if t >= 0:
-            rec["type"] = t
-            rec["prob"] = float(table_row["prob"][k])
+            rec["contours"] = (contour + (b[:2] + offset)[None]).astype(np.int32)   # hovernet.py:705 adds in place: stays int32
+        rec["centroid"] = centroids[k]
+        rec["box"] = boxes[k]
+        if types[k] >= 0:
+            rec["type"] = types[k]
+            rec["prob"] = probs[k]
         info[inst_id] = rec
     return info
