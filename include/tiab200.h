@@ -116,6 +116,9 @@ int tiab_reinhard_fit(tiab_handle_t h, const uint8_t* target_dev, int H, int W, 
  * image is constant (the reference raises ZeroDivisionError at stainnorm.py:277-283); such an image is copied through unchanged. */
 int tiab_reinhard_transform_batch(tiab_handle_t h, const uint8_t* in_dev, uint8_t* out_dev, int N, int H, int W, const double target_means[3],
                                   const double target_stds[3], double* src_stats_dev, int* status_dev, void* stream);
+/* Path of tiab_reinhard_transform_batch on this handle: 0 = three launches (default); 1 = experimental fused kernel, one CTA per image,
+ * for images of at most 196 608 bytes whose size is a multiple of 16 bytes (e.g. 256 x 256 x 3); other sizes keep path 0. */
+int tiab_reinhard_set_path(tiab_handle_t h, int path);
 /* cv2.cvtColor(x, COLOR_RGB2LAB) (inverse = 0) or COLOR_LAB2RGB (inverse = 1) for npix uint8 pixels on the device. */
 int tiab_lab_convert(tiab_handle_t h, const uint8_t* in_dev, uint8_t* out_dev, long long npix, int inverse, void* stream);
 

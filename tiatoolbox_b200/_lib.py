@@ -93,6 +93,7 @@ SIGNATURES = {
     "tiab_stain_augment": (C.c_int, [_vp, _vp, _vp, C.c_longlong, _dp, _dp, _dp, _vp, _vp]),
     "tiab_reinhard_fit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _dp, _dp, _vp]),
     "tiab_reinhard_transform_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _vp, _vp, _vp]),
+    "tiab_reinhard_set_path": (C.c_int, [_vp, C.c_int]),
     "tiab_lab_convert": (C.c_int, [_vp, _vp, _vp, C.c_longlong, C.c_int, _vp]),
     "tiab_dbg_lab_convert": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int]),
     "tiab_dbg_reinhard_maps": (C.c_int, [_vp, C.c_double, _dp, _dp, _dp, _vp]),

@@ -204,6 +204,92 @@ __global__ void __launch_bounds__(RH_THREADS) lab_convert_kernel(const uint8_t* 
   }
 }
 
+// ---- experimental: the three passes fused, one CTA per image (opt-in: tiab_reinhard_set_path(h, 1)) ---------------------------------------
+// For images of at most 192 KB (256 x 256 x 3): the image is read ONCE into shared memory, converted to Lab8 in place while the three
+// histograms are built, the level maps are formed by the same finalise code, and the second pass reads Lab from shared memory — one
+// forward conversion instead of two and 2 x H x W x 3 bytes of HBM traffic instead of 3 x.  Persistent CTAs (one per SM) loop over images.
+constexpr int RF_THREADS = 1024;
+constexpr int RF_MAX_BYTES = 196608;
+
+__global__ void __launch_bounds__(RF_THREADS) reinhard_fused_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int N,
+                                                                    int npix, const double* __restrict__ tgt, double* __restrict__ stats,
+                                                                    int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  LabShared& tabs = *reinterpret_cast<LabShared*>(rf_smem);
+  unsigned* h = reinterpret_cast<unsigned*>(rf_smem + sizeof(LabShared));            // [768]
+  uint8_t* m = reinterpret_cast<uint8_t*>(h + 768);                                  // [768]
+  double* s_stats = reinterpret_cast<double*>(m + 768);                              // [6] (+ flag)
+  uint8_t* img = reinterpret_cast<uint8_t*>(s_stats + 8);                            // [npix * 3], 16-byte aligned
+  const int nbytes = npix * 3, nvec = nbytes >> 4, nquad = npix >> 2;                // the caller guarantees nbytes % 16 == 0
+  stage_tables(tabs, true, true);
+  const LabTables t{tabs.gamma, tabs.cbrt, tabs.yf, tabs.inv_gamma};
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + (long long)n * nbytes);
+    uint4* dst = reinterpret_cast<uint4*>(out + (long long)n * nbytes);
+    for (int i = threadIdx.x; i < nvec; i += RF_THREADS) reinterpret_cast<uint4*>(img)[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < 768; i += RF_THREADS) h[i] = 0u;
+    __syncthreads();
+    // pass 1: RGB -> Lab8 in place (4 pixels = three 32-bit words per thread and step) + histograms
+    for (int q = threadIdx.x; q < nquad; q += RF_THREADS) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(img) + 3 * q;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      const int c[12] = {(int)(w0 & 255), (int)((w0 >> 8) & 255), (int)((w0 >> 16) & 255), (int)(w0 >> 24),
+                         (int)(w1 & 255), (int)((w1 >> 8) & 255), (int)((w1 >> 16) & 255), (int)(w1 >> 24),
+                         (int)(w2 & 255), (int)((w2 >> 8) & 255), (int)((w2 >> 16) & 255), (int)(w2 >> 24)};
+      int o[12];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        rgb_to_lab_u8(t, c[3 * k], c[3 * k + 1], c[3 * k + 2], o[3 * k], o[3 * k + 1], o[3 * k + 2]);
+        atomicAdd(&h[o[3 * k]], 1u);
+        atomicAdd(&h[256 + o[3 * k + 1]], 1u);
+        atomicAdd(&h[512 + o[3 * k + 2]], 1u);
+      }
+      w[0] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+      w[1] = (uint32_t)o[4] | ((uint32_t)o[5] << 8) | ((uint32_t)o[6] << 16) | ((uint32_t)o[7] << 24);
+      w[2] = (uint32_t)o[8] | ((uint32_t)o[9] << 8) | ((uint32_t)o[10] << 16) | ((uint32_t)o[11] << 24);
+    }
+    __syncthreads();
+    // statistics + level maps (the code of reinhard_finalize_kernel)
+    if (threadIdx.x < 3) {
+      double mean, sd;
+      reinhard_stats(threadIdx.x, h + 256 * threadIdx.x, (double)npix, mean, sd);
+      s_stats[threadIdx.x] = mean;
+      s_stats[3 + threadIdx.x] = sd;
+    }
+    __syncthreads();
+    const bool bad = !(s_stats[3] > 0.0) || !(s_stats[4] > 0.0) || !(s_stats[5] > 0.0);
+    if (threadIdx.x < 6) stats[(long long)n * 6 + threadIdx.x] = s_stats[threadIdx.x];
+    if (threadIdx.x == 0) status[n] = bad ? 1 : 0;
+    if (bad) {   // constant channel: the image passes through unchanged (block-uniform branch)
+      for (int i = threadIdx.x; i < nvec; i += RF_THREADS) dst[i] = __ldg(src + i);
+      __syncthreads();
+      continue;
+    }
+    if (threadIdx.x < 256)
+      for (int c = 0; c < 3; ++c)
+        m[256 * c + threadIdx.x] = (uint8_t)reinhard_level(c, threadIdx.x, s_stats[c], s_stats[3 + c], tgt[c], tgt[3 + c]);
+    __syncthreads();
+    // pass 2: Lab8 -> level maps -> RGB in place, then coalesced 16-byte stores
+    for (int q = threadIdx.x; q < nquad; q += RF_THREADS) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(img) + 3 * q;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      const int c[12] = {(int)(w0 & 255), (int)((w0 >> 8) & 255), (int)((w0 >> 16) & 255), (int)(w0 >> 24),
+                         (int)(w1 & 255), (int)((w1 >> 8) & 255), (int)((w1 >> 16) & 255), (int)(w1 >> 24),
+                         (int)(w2 & 255), (int)((w2 >> 8) & 255), (int)((w2 >> 16) & 255), (int)(w2 >> 24)};
+      int o[12];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        lab_to_rgb_u8(t, m[c[3 * k]], m[256 + c[3 * k + 1]], m[512 + c[3 * k + 2]], o[3 * k], o[3 * k + 1], o[3 * k + 2]);
+      w[0] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+      w[1] = (uint32_t)o[4] | ((uint32_t)o[5] << 8) | ((uint32_t)o[6] << 16) | ((uint32_t)o[7] << 24);
+      w[2] = (uint32_t)o[8] | ((uint32_t)o[9] << 8) | ((uint32_t)o[10] << 16) | ((uint32_t)o[11] << 24);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nvec; i += RF_THREADS) dst[i] = reinterpret_cast<const uint4*>(img)[i];
+    __syncthreads();
+  }
+}
+
 static int ensure_tables(tiab_ctx* h, cudaStream_t s) {
   if (h->lab_tables_set) return TIAB_OK;
   static LabTablesDev host;   // zero-initialised padding
@@ -297,8 +383,19 @@ int tiab_reinhard_transform_batch(tiab_handle_t h, const uint8_t* in_dev, uint8_
   double tgt_host[6] = {target_means[0], target_means[1], target_means[2], target_stds[0], target_stds[1], target_stds[2]};
   TIAB_CUDA_OK(h, cudaMemcpyAsync(tgt, tgt_host, sizeof(tgt_host), cudaMemcpyHostToDevice, s));
   TIAB_CUDA_OK(h, cudaStreamSynchronize(s));   // tgt_host lives on this stack frame
-  int rc = reinhard_stats_dev(h, in_dev, N, npix, tgt, hist, stats, status, lut, s);
-  if (rc == TIAB_OK) {
+  const bool fused_ok = h->reinhard_path == 1 && npix * 3 <= RF_MAX_BYTES && (npix * 3) % 16 == 0 && npix % 4 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(in_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15) == 0;
+  int rc = TIAB_OK;
+  if (fused_ok) {
+    const size_t smem = sizeof(LabShared) + 768 * sizeof(unsigned) + 768 + 8 * sizeof(double) + (size_t)npix * 3;
+    TIAB_CUDA_OK(h, cudaFuncSetAttribute(reinhard_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reinhard_fused_kernel<<<std::min(N, h->sm_count), RF_THREADS, smem, s>>>(in_dev, out_dev, N, (int)npix, tgt, stats, status);
+    h->last_launches++;
+    rc = launch_ok(h, "reinhard_fused_kernel");
+  } else {
+    rc = reinhard_stats_dev(h, in_dev, N, npix, tgt, hist, stats, status, lut, s);
+  }
+  if (rc == TIAB_OK && !fused_ok) {
     const int chunks = (int)((npix + RH_PIX_PER_BLOCK - 1) / RH_PIX_PER_BLOCK);
     reinhard_apply_kernel<<<dim3(chunks, N), RH_THREADS, 0, s>>>(in_dev, out_dev, npix, lut, status);
     h->last_launches++;
@@ -309,6 +406,12 @@ int tiab_reinhard_transform_batch(tiab_handle_t h, const uint8_t* in_dev, uint8_
   if (rc == TIAB_OK && status_dev) TIAB_CUDA_OK(h, cudaMemcpyAsync(status_dev, status, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, s));
   cudaFreeAsync(work, s);
   return rc;
+}
+
+int tiab_reinhard_set_path(tiab_handle_t h, int path) {
+  if (!h || (path != 0 && path != 1)) return TIAB_E_INVALID;
+  h->reinhard_path = path;
+  return TIAB_OK;
 }
 
 int tiab_lab_convert(tiab_handle_t h, const uint8_t* in_dev, uint8_t* out_dev, long long npix, int inverse, void* stream) {

@@ -341,6 +341,13 @@ class ReinhardNormalizer(StainNormalizer):
         return res
 
 
+def set_reinhard_path(path: int, device: int = 0) -> None:
+    """Kernel path of `ReinhardNormalizer.transform_batch` on this thread's handle of `device`: 0 = histogram + finalise + apply launches
+    (default); 1 = experimental fused kernel (one CTA per image, the image resident in shared memory; images up to 256 x 256 x 3)."""
+    h = _lib.handle(device)
+    _lib.check(h, _lib.lib().tiab_reinhard_set_path(h, int(path)))
+
+
 def get_normalizer(method_name: str, stain_matrix=None) -> StainNormalizer:
     """Return a :class:`StainNormalizer` by name (stainnorm.py:370-425)."""
     if method_name.lower() not in ["reinhard", "ruifrok", "macenko", "vahadane", "custom"]:
