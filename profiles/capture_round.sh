@@ -10,7 +10,7 @@ step() { name=$1; lim=$2; shift 2; echo "== $name"; ( timeout $lim "$@" ) > $out
 # 1. parity: the whole GPU suite (established modules first, newest last: tests/conftest.py)
 step tests 600 python -m pytest tests -q -m gpu -x --durations=8
 # 2. the opt-in code paths (floods v2 / v3, fused Reinhard): bit-exactness against the defaults + timings
-step experimental 240 env TIAB_EXPERIMENTAL=1 python -m pytest tests/test_watershed_v2_gpu.py tests/test_reinhard_fused_gpu.py -q -m gpu -s
+step experimental 240 env TIAB_EXPERIMENTAL=1 python -m pytest tests/test_watershed_v2_gpu.py tests/test_reinhard_fused_gpu.py tests/test_hovernetplus_gpu.py::test_two_task_wsi_mode_region -q -m gpu -s
 # 3. benches (clock sampling is inside bench.py)
 ( timeout 400 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err ); tail -c 400 $out/${tag}_bench_n1.json
 ( timeout 200 python bench.py --workload macenko --steps 10 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_macenko.json 2>> $out/${tag}_bench_n1.err )
