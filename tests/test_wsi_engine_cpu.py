@@ -266,3 +266,34 @@ def test_two_task_wsi_mode_matches_the_oracle_flow():
     for i, rec in enumerate(lay):
         assert np.array_equal(got["box"][i], rec["box"]) and np.array_equal(got["contours"][i], rec["contours"]) and got["type"][i] == rec["type"]
     assert got["predictions"].dtype == np.uint8 and np.array_equal(got["predictions"], wsi_layer)
+
+
+def test_plan_properties_over_random_slides():
+    """For random slide sizes / world sizes: every tile has exactly one owner, and a rank's patch set contains every patch whose output
+    box meets one of its tiles (so its canvases hold everything its tiles read); the bands are contiguous runs of whole patch rows."""
+    from tiatoolbox_b200.models.architecture import PRETRAINED_INFO
+
+    rng = np.random.default_rng(11)
+    configs = [IO_SMALL, PRETRAINED_INFO["hovernet_fast-pannuke"]["ioconfig"]]
+    for trial in range(40):
+        io = configs[trial % 2]
+        scale = 40 if io is IO_SMALL else 164
+        w, h = int(rng.integers(1, 40) * scale + rng.integers(0, scale)), int(rng.integers(1, 40) * scale + rng.integers(0, scale))
+        world = int(rng.choice([1, 2, 3, 4, 8]))
+        owned = []
+        for r in range(world):
+            p = WsiTilePlan((w, h), io, r, world)
+            owned += p.my_tasks
+            mine = set(p.my_patches.tolist())
+            for i in p.my_tasks:
+                x0, y0, x1, y1 = (int(v) for v in p.tasks[i][0])
+                x0, y0, x1, y1 = max(x0, 0), max(y0, 0), min(x1, w), min(y1, h)
+                if x1 <= x0 or y1 <= y0:
+                    continue
+                ob = p.out_boxes
+                need = np.nonzero((ob[:, 2] > x0) & (ob[:, 0] < x1) & (ob[:, 3] > y0) & (ob[:, 1] < y1))[0]
+                assert set(need.tolist()) <= mine, (w, h, world, r, i)
+                assert p.canvas_y0 <= y0 and y1 <= p.canvas_y1
+            if len(p.my_patches):
+                assert np.array_equal(p.my_patches, np.arange(p.my_patches[0], p.my_patches[-1] + 1))
+        assert sorted(owned) == list(range(len(p.tasks))), (w, h, world)
