@@ -149,7 +149,7 @@ def cpu_pipeline(workload: str, sample: int, procs: int, threads: int):
     t_net = t_post = 0.0
     if workload == "macenko_hovernet":
         from oracle import hovernet_postproc_oracle as po
-        from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_heads_reference
+        from oracle.torch_reference import hovernet_forward_reference, hovernet_heads_reference
 
         torch.set_num_threads(threads)
         sd = _hovernet_weights()
@@ -173,7 +173,7 @@ def _best_torch_threads(cores: int) -> int:
     """oneDNN convs on these boxes slow down badly when every hyper-thread is used: give the CPU arm its best setting."""
     import torch
 
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference
+    from oracle.torch_reference import hovernet_forward_reference
 
     sd = _hovernet_weights()
     x = torch.from_numpy(_tiles(1, seed=5)).permute(0, 3, 1, 2).float()

@@ -264,12 +264,19 @@ int tiab_hovernet_contours(tiab_handle_t h, const int32_t* inst_map, int N, int 
                            int32_t* cont_total, int32_t* cont_xy, void* stream);
 /* Flood implementation of tiab_hovernet_postproc on this handle: 1 = binary heap, one thread per foreground component (default);
  * 2 = 8-ary heap with the total order (value, age, pixel index), one warp per component (csrc/watershed_math.cuh);
- * 3 = the same flood with the component's bounding box and heap staged in shared memory, persistent blocks over a work list. */
+ * 3 = the same flood with the component's bounding box and heap staged in shared memory, persistent blocks over a work list;
+ * 4 = work list + shared memory like 3, but the whole warp drives a 32-ary heap (children compared with redux.sync), the four neighbour
+ *     tests run on four lanes. */
 int tiab_hovernet_set_watershed(tiab_handle_t h, int impl);
+int tiab_hovernet_get_watershed(tiab_handle_t h);   /* the implementation in use (1..4), negative on error */
 /* host-side test hook of csrc/watershed_math.cuh: skimage.segmentation.watershed(dist, markers, mask=mask) on H*W host arrays (float64
  * image, int32 markers, uint8 mask) through the version-2 flood code. */
 int tiab_dbg_watershed(const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W, int32_t* out_host);
-/* the same through version 3's data flow (per-component box-local copies, local raveled indices) */
+/* the work-list floods (impl 3: lane-0 8-ary heap in shared memory, 4: warp-cooperative 32-ary heap) on the DEVICE for arbitrary host
+ * inputs (tests: adversarial tie cases on the GPU); whole mask = one work item */
+int tiab_dbg_watershed_device(tiab_handle_t h, const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W,
+                              int impl, int32_t* out_host);
+/* tiab_dbg_watershed through version 3's data flow on the host (per-component box-local copies, local raveled indices) */
 int tiab_dbg_watershed_local(const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W, int32_t* out_host);
 int tiab_dbg_sobel_kernels(double deriv[21], double smooth[21]);
 int tiab_dbg_sobel_kernels_k(int ksize, double* deriv, double* smooth);

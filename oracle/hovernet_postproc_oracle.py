@@ -66,6 +66,52 @@ def watershed(image: np.ndarray, markers: np.ndarray, mask: np.ndarray) -> np.nd
     return out
 
 
+# ---- the same two functions in plain C (oracle/csrc/postproc_oracle.c, built by __graft_entry__.build() with gcc into oracle/_build/) ----
+_CLIB = None
+
+
+def build_c(force: bool = False):
+    """Compile oracle/csrc/postproc_oracle.c with gcc (a second, independently written restatement + compiled speed for the CPU arm)."""
+    import subprocess
+    from pathlib import Path
+
+    here = Path(__file__).resolve().parent
+    src, out = here / "csrc" / "postproc_oracle.c", here / "_build" / "libtiab_oracle.so"
+    if force or not out.exists() or out.stat().st_mtime < src.stat().st_mtime:
+        out.parent.mkdir(exist_ok=True)
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", str(out), str(src)], check=True)
+    return out
+
+
+def _clib():
+    global _CLIB  # noqa: PLW0603
+    if _CLIB is None:
+        import ctypes as C
+
+        lib = C.CDLL(str(build_c()))
+        lib.tiab_oracle_watershed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.tiab_oracle_remove_small_objects.argtypes = [C.c_void_p, C.c_long, C.c_int]
+        _CLIB = lib
+    return _CLIB
+
+
+def watershed_c(image: np.ndarray, markers: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """`watershed` through the C restatement (same semantics, same tie rule)."""
+    img = np.ascontiguousarray(image, dtype=np.float64)
+    mk = np.ascontiguousarray(markers, dtype=np.int32)
+    msk = np.ascontiguousarray(np.asarray(mask).astype(bool).astype(np.uint8))
+    out = np.empty(img.shape, np.int32)
+    rc = _clib().tiab_oracle_watershed(img.ctypes.data, mk.ctypes.data, msk.ctypes.data, img.shape[0], img.shape[1], out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def remove_small_objects_c(label_img: np.ndarray, max_size: int) -> np.ndarray:
+    out = np.ascontiguousarray(label_img, dtype=np.int32).copy()
+    assert _clib().tiab_oracle_remove_small_objects(out.ctypes.data, out.size, int(max_size)) == 0
+    return out.astype(label_img.dtype, copy=False)
+
+
 def proc_np_hv(np_map: np.ndarray, hv_map: np.ndarray, *, debug: dict | None = None, scale_factor: float = 1.0) -> np.ndarray:
     """HoVerNet._proc_np_hv (hovernet.py:536-616); scale_factor 1 for HoVer-Net, 0.5 for HoVerNetPlus (hovernetplus.py:305)."""
     blb_raw = np_map[..., 0]

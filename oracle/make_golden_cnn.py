@@ -20,7 +20,8 @@ def _f16(a: torch.Tensor) -> np.ndarray:
 def make_hovernet() -> None:
     from oracle import ref_shim
     from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_spec
+    from oracle.torch_reference import hovernet_forward_reference
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
     from tiatoolbox_b200.synthetic import he_tiles
 
     m = ref_shim.load_models()
@@ -70,7 +71,8 @@ def make_hovernetplus() -> None:
     from oracle import hovernet_postproc_oracle as po
     from oracle import ref_shim
     from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_spec
+    from oracle.torch_reference import hovernet_forward_reference
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
     from tiatoolbox_b200.synthetic import he_tiles, hovernet_head_maps
 
     ref_shim.load_models()
@@ -124,7 +126,8 @@ def make_postproc() -> None:
 def make_resnet18() -> None:
     from oracle import ref_shim
     from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
-    from tiatoolbox_b200.models.architecture.vanilla import cnn_forward_reference, cnn_spec
+    from oracle.torch_reference import cnn_forward_reference
+    from tiatoolbox_b200.models.architecture.vanilla import cnn_spec
     from tiatoolbox_b200.synthetic import he_tiles
 
     m = ref_shim.load_models()
@@ -144,7 +147,8 @@ def make_resnet18() -> None:
 def make_unet() -> None:
     from oracle import ref_shim
     from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
-    from tiatoolbox_b200.models.architecture.unet import unet_forward_reference, unet_spec
+    from oracle.torch_reference import unet_forward_reference
+    from tiatoolbox_b200.models.architecture.unet import unet_spec
     from tiatoolbox_b200.synthetic import he_tiles
 
     m = ref_shim.load_models()

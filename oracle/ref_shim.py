@@ -1,7 +1,7 @@
-"""Load the UNMODIFIED reference sources from /root/reference through stub modules.
+"""Load the UNMODIFIED reference sources through stub modules.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Works only in the build
-container (``/root/reference`` does not exist on the GPU box).  Used by
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  The sources are read from ``/root/reference`` (build
+container) or from ``oracle/_ref`` (the vendored copy that travels to the GPU box: oracle/vendor_ref.py).  Used by
 ``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/`` and by the
 ``-m "not gpu"`` tests that pin the numpy/C restatements against the real reference.
 
@@ -28,7 +28,10 @@ from pathlib import Path
 
 import numpy as np
 
-REF_ROOT = Path("/root/reference")
+# /root/reference in the build container; on the GPU box the byte-for-byte copy of the hot-path files that oracle/vendor_ref.py
+# places under oracle/_ref/ (git-ignored, travels with the snapshot like the built .so)
+_CANDIDATES = (Path("/root/reference"), Path(__file__).resolve().parent / "_ref")
+REF_ROOT = next((c for c in _CANDIDATES if (c / "tiatoolbox" / "tools" / "stainnorm.py").exists()), _CANDIDATES[0])
 REF_PKG = REF_ROOT / "tiatoolbox"
 
 

@@ -4,7 +4,7 @@ import sys, time
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch, torch.nn.functional as F
 from tests.cnn_common import hovernet_test_weights, rel_l2
-from tiatoolbox_b200.models.architecture import hovernet as hn
+import oracle.torch_reference as hn
 from tiatoolbox_b200.synthetic import he_tiles
 
 real_conv = F.conv2d

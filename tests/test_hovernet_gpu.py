@@ -40,7 +40,7 @@ def hv(built_lib):
 def test_logits_match_fp32_reference_and_golden(hv):
     import torch
 
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference
+    from oracle.torch_reference import hovernet_forward_reference
 
     sd, plan, tiles = hv
     x = torch.from_numpy(tiles).cuda()
@@ -103,7 +103,7 @@ def test_cuda_graph_replay_is_bit_identical_and_fast(hv):
 def test_single_pass_fp16_mode_shallow_layers(built_lib):
     import torch
 
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference
+    from oracle.torch_reference import hovernet_forward_reference
     from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan
     from tiatoolbox_b200.synthetic import he_tiles
 
@@ -128,7 +128,8 @@ def test_original_mode_270_matches_fp32_reference(built_lib):
     import torch
 
     from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_spec
+    from oracle.torch_reference import hovernet_forward_reference
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
     from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan
     from tiatoolbox_b200.synthetic import he_tiles
 

@@ -24,7 +24,7 @@ def hovernetplus_test_weights():
 
 
 def test_reference_forward_restatement_matches_reference_module():
-    from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_heads_reference
+    from oracle.torch_reference import hovernet_forward_reference, hovernet_heads_reference
     from tiatoolbox_b200.synthetic import he_tiles
 
     sd = hovernetplus_test_weights()

@@ -7,6 +7,7 @@ import sys
 
 import numpy as np
 import pytest
+from scipy import ndimage
 
 from oracle import hovernet_postproc_oracle as po
 from tiatoolbox_b200.synthetic import hovernet_head_maps
@@ -75,3 +76,42 @@ def test_pipeline_equals_reference_code_path(have_reference):
         for k in a:
             assert np.array_equal(a[k]["box"], b[k]["box"]) and np.array_equal(a[k]["contours"], b[k]["contours"])
             assert np.allclose(a[k]["centroid"], b[k]["centroid"], atol=0) and a[k]["type"] == b[k]["type"] and a[k]["prob"] == b[k]["prob"]
+
+
+def test_c_restatement_equals_python_restatement_on_adversarial_floods():
+    """oracle/csrc/postproc_oracle.c (independently written binary-heap flood) == the Python heapq restatement on plateaus, equal-valued
+    markers, single-pixel bridges and random quantised landscapes (many (value) ties), and on the pipeline's own intermediates."""
+    rng = np.random.default_rng(7)
+    cases = []
+    h, w = 24, 31
+    flat = np.zeros((h, w))                                   # one big plateau, two markers: pure (age, index) ordering
+    mk = np.zeros((h, w), np.int32)
+    mk[3, 4], mk[20, 25] = 1, 2
+    cases.append((flat, mk, np.ones((h, w), bool)))
+    mk2 = np.zeros((h, w), np.int32)                          # equal-valued marker blobs next to each other
+    mk2[5:8, 5:8], mk2[5:8, 9:12], mk2[15:18, 20:23] = 1, 2, 3
+    cases.append((np.round(rng.random((h, w)) * 3) / 3, mk2, np.ones((h, w), bool)))
+    bridge = np.zeros((h, w), bool)                           # two rooms joined by a one-pixel corridor
+    bridge[2:12, 2:12] = bridge[2:12, 16:28] = True
+    bridge[6, 12:16] = True
+    mk3 = np.zeros((h, w), np.int32)
+    mk3[4, 4], mk3[9, 25] = 5, 9
+    cases.append((rng.random((h, w)), mk3, bridge))
+    for _ in range(40):                                       # random quantised landscapes: ties everywhere
+        hh, ww = int(rng.integers(5, 40)), int(rng.integers(5, 40))
+        img = np.round(rng.normal(size=(hh, ww)) * rng.integers(1, 4)) / 2
+        msk = rng.random((hh, ww)) < 0.8
+        m = np.zeros((hh, ww), np.int32)
+        for lab in range(1, int(rng.integers(2, 7))):
+            y, x = int(rng.integers(0, hh)), int(rng.integers(0, ww))
+            m[max(0, y - 1): y + 2, max(0, x - 1): x + 2] = lab
+        cases.append((img, m, msk))
+    for img, m, msk in cases:
+        assert np.array_equal(po.watershed_c(img, m, msk), po.watershed(img, m, msk))
+    npm, hvm, _ = hovernet_head_maps(3, 164, seed=11)
+    for i in range(3):
+        dbg = {}
+        out = po.proc_np_hv(npm[i], hvm[i], debug=dbg)
+        assert np.array_equal(po.watershed_c(dbg["dist"], dbg["marker"], dbg["blb"]), out)
+        lab = ndimage.label(npm[i][..., 0] >= 0.5)[0]
+        assert np.array_equal(po.remove_small_objects_c(lab, 9), po.remove_small_objects(lab, 9))

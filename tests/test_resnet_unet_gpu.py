@@ -21,7 +21,7 @@ def _no_tf32():
 def test_resnet18_probabilities(built_lib):
     import torch
 
-    from tiatoolbox_b200.models.architecture.vanilla import cnn_forward_reference
+    from oracle.torch_reference import cnn_forward_reference
     from tiatoolbox_b200.models.resnet_plan import CNNPlan
     from tiatoolbox_b200.synthetic import he_tiles
 
@@ -49,7 +49,7 @@ def test_resnet18_probabilities(built_lib):
 def test_unet_probabilities(built_lib):
     import torch
 
-    from tiatoolbox_b200.models.architecture.unet import unet_forward_reference, unet_infer_tail_reference
+    from oracle.torch_reference import unet_forward_reference, unet_infer_tail_reference
     from tiatoolbox_b200.models.resnet_plan import UNetPlan
     from tiatoolbox_b200.synthetic import he_tiles
 

@@ -116,8 +116,10 @@ SIGNATURES = {
                                                 _vp, _vp, _vp, _vp]),
     "tiab_hovernet_contours": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "tiab_hovernet_set_watershed": (C.c_int, [_vp, C.c_int]),
+    "tiab_hovernet_get_watershed": (C.c_int, [_vp]),
     "tiab_dbg_watershed": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "tiab_dbg_watershed_local": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "tiab_dbg_watershed_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "tiab_dbg_sobel_kernels": (C.c_int, [_vp, _vp]),
     "tiab_dbg_sobel_kernels_k": (C.c_int, [C.c_int, _vp, _vp]),
     "tiab_dbg_trace_contour": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int]),

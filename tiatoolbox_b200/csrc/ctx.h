@@ -30,7 +30,7 @@ struct tiab_ctx {
   void* pp_work = nullptr;
   size_t pp_bytes = 0;
   int pp_const_set = 0;
-  int pp_watershed_impl = 1;  // 1: binary heap, one thread per component (r1c); 2: 8-ary heap, one warp per component (watershed_math.cuh)
+  int pp_watershed_impl = 4;  // 1: binary heap, one thread per component (r1c); 2: 8-ary heap, one warp per component; 3: work list + shared memory, lane 0; 4 (default since r2c): work list + shared memory, warp-cooperative 32-ary heap
   int reinhard_path = 0;      // 0: hist + finalise + apply (default); 1: experimental one-CTA-per-image fused kernel when the image fits
   int lab_tables_set = 0;   // csrc/reinhard.cu: __device__ copy of lab_tables.h uploaded
   size_t pp_dbg_off[8] = {0};

@@ -1,4 +1,4 @@
-"""HoVer-Net (Graham et al. 2019) for the B200 — architecture definition + fp32 reference forward.
+"""HoVer-Net (Graham et al. 2019) for the B200 — architecture definition (parameter names / shapes) and the model class.
 
 Mirrors tiatoolbox/models/architecture/hovernet.py: same constructor arguments, same state_dict
 keys (so `hovernet_fast-pannuke` / `hovernet_original-*` checkpoints load unchanged), same
@@ -19,7 +19,6 @@ from collections import OrderedDict
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from tiatoolbox_b200.models.architecture._params import ParamSpec, seeded_state_dict
 
@@ -89,122 +88,6 @@ def tf_same_pad(size: int, ksize: int, stride: int) -> tuple[int, int]:
     return pad // 2, pad - pad // 2
 
 
-def _bn(x, sd, name):
-    if sd.get("__calibrate__", False):  # test-weight calibration: adopt the batch statistics (see _params.calibrate)
-        sd[name + ".running_mean"] = x.mean(dim=(0, 2, 3)).detach()
-        sd[name + ".running_var"] = x.var(dim=(0, 2, 3), unbiased=False).detach() + 1e-3
-    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
-                        sd[name + ".bias"], False, 0.0, 1e-5)
-
-
-def _crop_to(x, ref):
-    dh, dw = x.shape[2] - ref.shape[2], x.shape[3] - ref.shape[3]
-    return x[:, :, dh // 2: x.shape[2] - (dh - dh // 2), dw // 2: x.shape[3] - (dw - dw // 2)]
-
-
-def _up2(x):
-    return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-
-
-def _residual_block(x, sd, name, units, stride):
-    shortcut = F.conv2d(x, sd[f"{name}.shortcut.weight"], stride=stride) if f"{name}.shortcut.weight" in sd else x
-    prev = x
-    for i in range(units):
-        u = f"{name}.units.{i}"
-        y = prev
-        if i > 0:
-            y = F.relu(_bn(y, sd, f"{u}.preact/bn"))
-        y = F.relu(_bn(F.conv2d(y, sd[f"{u}.conv1.weight"]), sd, f"{u}.conv1/bn"))
-        s = stride if i == 0 else 1
-        pb, pa = tf_same_pad(y.shape[2], 3, s)
-        y = F.pad(y, (pb, pa, pb, pa))
-        y = F.relu(_bn(F.conv2d(y, sd[f"{u}.conv2.weight"], stride=s), sd, f"{u}.conv2/bn"))
-        y = F.conv2d(y, sd[f"{u}.conv3.weight"])
-        prev = y + shortcut
-        shortcut = prev
-    return F.relu(_bn(prev, sd, f"{name}.blk_bna.bn"))
-
-
-def _dense_block(x, sd, name, units):
-    prev = x
-    for i in range(units):
-        u = f"{name}.units.{i}"
-        y = F.relu(_bn(prev, sd, f"{u}.preact_bna/bn"))
-        y = F.relu(_bn(F.conv2d(y, sd[f"{u}.conv1.weight"]), sd, f"{u}.conv1/bn"))
-        y = F.conv2d(y, sd[f"{u}.conv2.weight"], groups=4)
-        prev = torch.cat([_crop_to(prev, y), y], dim=1)
-    return F.relu(_bn(prev, sd, f"{name}.blk_bna.bn"))
-
-
-def hovernet_forward_reference(sd, x_nchw: torch.Tensor, mode: str, num_types: int | None, capture: dict | None = None,
-                               num_layers: int | None = None) -> OrderedDict:
-    """fp32 PyTorch restatement of HoVerNet.forward (hovernet.py:405-454; with `num_layers` HoVerNetPlus, which only adds the `ls`
-    decoder branch: hovernetplus.py:87-133).  x in [0, 255]."""
-    x = x_nchw / 255.0
-    if mode == "fast":
-        pb, pa = tf_same_pad(x.shape[2], 7, 1)
-        x = F.pad(x, (pb, pa, pb, pa))
-    d = F.relu(_bn(F.conv2d(x, sd["conv0./.weight"]), sd, "conv0.bn"))
-    if capture is not None:
-        capture["x0"] = d
-    feats = []
-    for name, _, _, units, stride in RES_CFG:
-        d = _residual_block(d, sd, name, units, stride)
-        feats.append(d)
-        if capture is not None:
-            capture[name] = d
-    feats[3] = F.conv2d(feats[3], sd["conv_bot.weight"])
-    if capture is not None:
-        capture["dbot"] = feats[3]
-    c0, c1 = (184, 72) if mode == "original" else (92, 36)
-    d0 = feats[0][:, :, c0 // 2: feats[0].shape[2] - c0 // 2, c0 // 2: feats[0].shape[3] - c0 // 2]
-    d1 = feats[1][:, :, c1 // 2: feats[1].shape[2] - c1 // 2, c1 // 2: feats[1].shape[3] - c1 // 2]
-    k = 5 if mode == "original" else 3
-    out = OrderedDict()
-    for b in branch_channels(num_types, num_layers):
-        p = f"decoder.{b}"
-        u3 = _up2(feats[3]) + feats[2]
-        if capture is not None:
-            capture["u3in"] = u3
-        u3 = F.conv2d(u3, sd[f"{p}.u3.conva.weight"])
-        if capture is not None:
-            capture[f"{b}.u3.conva"] = u3
-        u3 = F.conv2d(_dense_block(u3, sd, f"{p}.u3.dense", 8), sd[f"{p}.u3.convf.weight"])
-        if capture is not None:
-            capture[f"{b}.u3out"] = u3
-        u2 = _up2(u3) + d1
-        if capture is not None:
-            capture[f"{b}.u2in"] = u2
-        u2 = F.conv2d(u2, sd[f"{p}.u2.conva.weight"])
-        u2 = F.conv2d(_dense_block(u2, sd, f"{p}.u2.dense", 4), sd[f"{p}.u2.convf.weight"])
-        if capture is not None:
-            capture[f"{b}.u2out"] = u2
-        u1 = _up2(u2) + d0
-        if capture is not None:
-            capture[f"{b}.u1in"] = u1
-        pb, pa = tf_same_pad(u1.shape[2], k, 1)
-        u1 = F.conv2d(F.pad(u1, (pb, pa, pb, pa)), sd[f"{p}.u1.conva.weight"])
-        if capture is not None:
-            capture[f"{b}.u1"] = u1
-        u0 = F.relu(_bn(u1, sd, f"{p}.u0.bn"))
-        out[b] = F.conv2d(u0, sd[f"{p}.u0.conv.weight"], sd[f"{p}.u0.conv.bias"])
-    return out
-
-
-def hovernet_heads_reference(out: OrderedDict) -> tuple[torch.Tensor, ...]:
-    """Head activations of HoVerNet.infer_batch (hovernet.py:897-909): NHWC, np = softmax[..., 1:],
-    tp = argmax as float32, hv raw.  Returns (np, hv[, tp])."""
-    o = {k: v.permute(0, 2, 3, 1).contiguous() for k, v in out.items()}
-    o["np"] = F.softmax(o["np"], dim=-1)[..., 1:]
-    if "tp" in o:
-        tp = torch.argmax(F.softmax(o["tp"], dim=-1), dim=-1, keepdim=True).type(torch.float32)
-        if "ls" in o:   # HoVerNetPlus.infer_batch (hovernetplus.py:444-459)
-            ls = torch.argmax(F.softmax(o["ls"], dim=-1), dim=-1, keepdim=True).type(torch.float32)
-            return o["np"], o["hv"], tp, ls
-        return o["np"], o["hv"], tp
-    return o["np"], o["hv"]
-
-
 # =================================================================================================
 # Model class (API mirror of tiatoolbox/models/architecture/hovernet.py:264-910)
 # =================================================================================================
@@ -229,9 +112,12 @@ class HoVerNet(ModelABC):
         self._sd = seeded_state_dict(hovernet_spec(num_input_channels, num_types, mode), seed=0)
 
     def forward(self, input_tensor: torch.Tensor) -> OrderedDict:
-        """fp32 PyTorch forward (NCHW in [0, 255]) — the parity reference, not the hot path."""
-        sd = {k: v.to(input_tensor.device) for k, v in self._sd.items()}
-        return hovernet_forward_reference(sd, input_tensor, self.mode, self.num_types)
+        """hovernet.py:405-454 on the device plan: NCHW input holding uint8 pixel values in [0, 255] -> OrderedDict of NCHW fp32 logits
+        per decoder branch.  There is no PyTorch-eager forward in the product (the fp32 restatement is test infrastructure: oracle/)."""
+        x = ModelABC._nchw_to_u8_nhwc(input_tensor, self._device)
+        plan = self.plan_for(x.shape[0], self._device, x.shape[1:3])
+        plan.forward(x)
+        return OrderedDict((b, plan.logits[b].permute(0, 3, 1, 2).clone()) for b in plan.logits)
 
     def _build_plan(self, batch, device, shape):
         from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan

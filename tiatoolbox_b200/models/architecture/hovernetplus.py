@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from tiatoolbox_b200.models.architecture._params import seeded_state_dict
-from tiatoolbox_b200.models.architecture.hovernet import HoVerNet, hovernet_forward_reference, hovernet_spec, pack_instance_result
+from tiatoolbox_b200.models.architecture.hovernet import HoVerNet, hovernet_spec, pack_instance_result
 from tiatoolbox_b200.models.models_abc import ModelABC
 
 
@@ -45,10 +45,6 @@ class HoVerNetPlus(HoVerNet):
         self.class_dict = {self.tasks[0]: nuc_type_dict, self.tasks[1]: layer_type_dict}
         self._sd = seeded_state_dict(hovernet_spec(num_input_channels, num_types, "fast", num_layers), seed=0)
 
-    def forward(self, input_tensor: torch.Tensor):
-        """fp32 PyTorch forward (NCHW in [0, 255]) — the parity reference, not the hot path."""
-        sd = {k: v.to(input_tensor.device) for k, v in self._sd.items()}
-        return hovernet_forward_reference(sd, input_tensor, "fast", self.num_types, num_layers=self.num_layers)
 
     def _build_plan(self, batch, device, shape):
         from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan

@@ -7,10 +7,9 @@ same state_dict keys (`backbone.*` incl. the unused `backbone.fc`, `conv1x1`, `u
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from tiatoolbox_b200.models.architecture._params import ParamSpec
-from tiatoolbox_b200.models.architecture.resnet_common import _bn, resnet_features, resnet_spec
+from tiatoolbox_b200.models.architecture.resnet_common import resnet_spec
 
 
 def unet_spec(num_input_channels: int = 3, num_output_channels: int = 2, decoder_block=(3,)) -> ParamSpec:
@@ -31,32 +30,6 @@ def unet_spec(num_input_channels: int = 3, num_output_channels: int = 2, decoder
     sp.conv("clf", num_output_channels, nxt, 1, bias=True)
     sp["upsample2x.unpool_mat"] = ((2, 2), "ones")
     return sp
-
-
-def unet_forward_reference(sd, x_nchw: torch.Tensor, decoder_block=(3,)) -> torch.Tensor:
-    """fp32 restatement of UNetModel.forward (unet.py:374-418): logits N x C x H/2 x W/2.  x in [0, 255]."""
-    en = resnet_features(sd, x_nchw / 255.0, "backbone.", "resnet50")
-    x = F.conv2d(en[-1], sd["conv1x1.weight"])
-    en = en[:-1]
-    for idx in range(1, len(en) + 1):
-        y = en[-idx]
-        x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3) + y
-        li = 0
-        for ks in decoder_block:
-            x = F.relu(_bn(x, sd, f"uplist.{idx - 1}.{li}"))
-            x = F.conv2d(x, sd[f"uplist.{idx - 1}.{li + 2}.weight"], padding=(ks - 1) // 2)
-            li += 3
-    return F.conv2d(x, sd["clf.weight"], sd["clf.bias"])
-
-
-def unet_infer_tail_reference(logits: torch.Tensor) -> torch.Tensor:
-    """UNetModel.infer_batch after the forward (unet.py:458-465): NHWC probabilities of the centre crop."""
-    _, _, h, w = logits.shape
-    probs = F.softmax(logits, 1)
-    probs = F.interpolate(probs, scale_factor=2, mode="bilinear", align_corners=False)
-    ch, cw = (2 * h) // 2, (2 * w) // 2  # crop_shape = [H_in // 2, W_in // 2] with H_in = 2h
-    t, l_ = (2 * h - ch) // 2, (2 * w - cw) // 2
-    return probs[:, :, t:t + ch, l_:l_ + cw].permute(0, 2, 3, 1).contiguous()
 
 
 # =================================================================================================
@@ -89,8 +62,11 @@ class UNetModel(ModelABC):
         self._sd = seeded_state_dict(unet_spec(num_input_channels, num_output_channels, self.decoder_block), seed=0)
 
     def forward(self, imgs: torch.Tensor, *args, **kwargs) -> torch.Tensor:  # noqa: ARG002
-        sd = {k: v.to(imgs.device) for k, v in self._sd.items()}
-        return unet_forward_reference(sd, imgs, self.decoder_block)
+        """unet.py:374-418 on the device plan: NCHW input holding uint8 pixel values in [0, 255] -> logits (N, C, H/2, W/2)."""
+        x = ModelABC._nchw_to_u8_nhwc(imgs, self._device)
+        plan = self.plan_for(x.shape[0], self._device, x.shape[1:3])
+        plan.forward(x)
+        return plan.logits.permute(0, 3, 1, 2).clone()
 
     def _build_plan(self, batch, device, shape):
         from tiatoolbox_b200.models.resnet_plan import UNetPlan

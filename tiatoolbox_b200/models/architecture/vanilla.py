@@ -6,10 +6,9 @@ Mirrors tiatoolbox/models/architecture/vanilla.py:256-359: same constructor, sta
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from tiatoolbox_b200.models.architecture._params import ParamSpec
-from tiatoolbox_b200.models.architecture.resnet_common import BASIC, BOTTLENECK, resnet_features, resnet_spec
+from tiatoolbox_b200.models.architecture.resnet_common import BASIC, BOTTLENECK, resnet_spec
 
 # nn.Sequential(*list(model.children())[:-2]) -> indices of the torchvision ResNet children
 _LAYERS = ("4", "5", "6", "7")
@@ -24,13 +23,6 @@ def cnn_spec(backbone: str, num_classes: int) -> ParamSpec:
     c = resnet_spec(sp, "feat_extract.", backbone, 3, _LAYERS, _STEM)
     sp.linear("classifier", num_classes, c)
     return sp
-
-
-def cnn_forward_reference(sd, x_nchw: torch.Tensor, backbone: str) -> torch.Tensor:
-    """fp32 restatement of CNNModel.forward (vanilla.py:300-316); x is what the dataset feeds (e.g. [0,1])."""
-    feat = resnet_features(sd, x_nchw, "feat_extract.", backbone, _LAYERS, _STEM)[-1]
-    gap = feat.mean(dim=(2, 3))
-    return torch.softmax(F.linear(gap, sd["classifier.weight"], sd["classifier.bias"]), -1)
 
 
 # =================================================================================================
@@ -55,8 +47,10 @@ class CNNModel(ModelABC):
         self._sd = seeded_state_dict(cnn_spec(backbone, num_classes), seed=0)
 
     def forward(self, imgs: torch.Tensor) -> torch.Tensor:
-        sd = {k: v.to(imgs.device) for k, v in self._sd.items()}
-        return cnn_forward_reference(sd, imgs, self.backbone)
+        """vanilla.py:300-316 on the device plan: NCHW input as the dataset feeds it (ToTensor: uint8 / 255) -> softmax probabilities."""
+        x = ModelABC._nchw_to_u8_nhwc(imgs / self.u8_scale, self._device)
+        plan = self.plan_for(x.shape[0], self._device, x.shape[1:3])
+        return plan.forward(x).clone()
 
     def _build_plan(self, batch, device, shape):
         from tiatoolbox_b200.models.resnet_plan import CNNPlan

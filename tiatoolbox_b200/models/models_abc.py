@@ -113,6 +113,22 @@ class ModelABC(torch.nn.Module):
         return self._plans[key]
 
     @staticmethod
+    def _nchw_to_u8_nhwc(x: torch.Tensor, device) -> torch.Tensor:
+        """`forward()` input (NCHW, pixel values 0..255 as the reference's forward expects) -> the plans' uint8 NHWC batch.  Non-integer
+        values cannot come out of the reference's uint8 data path and are rejected rather than silently rounded."""
+        x = torch.as_tensor(x)
+        if x.dim() != 4:  # noqa: PLR2004
+            msg = f"expected an NCHW batch, got shape {tuple(x.shape)}"
+            raise ValueError(msg)
+        if x.dtype != torch.uint8:
+            r = x.round()
+            if float((x - r).abs().max()) > 1e-3 or float(r.min()) < 0 or float(r.max()) > 255:  # noqa: PLR2004
+                msg = "the B200 forward takes uint8 pixel values (0..255): there is no PyTorch-eager forward for arbitrary float inputs"
+                raise ValueError(msg)
+            x = r.to(torch.uint8)
+        return x.permute(0, 2, 3, 1).contiguous().to(device)
+
+    @staticmethod
     def _as_device_u8(batch_data, device) -> torch.Tensor:
         """uint8 NHWC batch on the device (float inputs in [0, 255] are rounded like the reference's
         DataLoader output would be cast by the kernels)."""

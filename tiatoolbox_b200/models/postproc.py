@@ -53,10 +53,15 @@ def proc_np_hv_batch(np_map: torch.Tensor, hv_map: torch.Tensor, tp_map: torch.T
 def set_watershed_impl(impl: int, device: int = 0) -> None:
     """Flood implementation used by `proc_np_hv_batch` on this thread's handle of `device`: 1 = binary heap, one thread per foreground
     component (the round-1 default); 2 = 8-ary heap with the total order (value, age, index), one warp per component; 3 = the same
-    flood with each component's bounding box and heap staged in shared memory, persistent blocks over a work list
-    (csrc/watershed_math.cuh — host-compiled and equal to the oracle on the CPU; the fastest one becomes the default once measured)."""
+    flood with each component's bounding box and heap staged in shared memory, persistent blocks over a work list; 4 = work list +
+    shared memory with the whole warp driving a 32-ary heap (csrc/postproc.cu: pp_watershed_v4).  All four give identical labels
+    (tests/test_watershed_v2_gpu.py)."""
     hd = _lib.handle(device)
     _lib.check(hd, _lib.lib().tiab_hovernet_set_watershed(hd, int(impl)))
+
+
+def get_watershed_impl(device: int = 0) -> int:
+    return int(_lib.lib().tiab_hovernet_get_watershed(_lib.handle(device)))
 
 
 def trace_contours(inst: torch.Tensor, table: dict, capacity: int | None = None) -> dict:

@@ -1,5 +1,5 @@
 """Layer-by-layer comparison of the HoVer-Net device plan with the fp32 torch reference (debug aid,
-run on the GPU box:  PYTHONPATH=. python tests/debug_hovernet.py [fp16x3|fp16] [fast|original])."""
+run on the GPU box:  PYTHONPATH=. python tools/debug_hovernet.py [fp16x3|fp16] [fast|original])."""
 import sys
 
 import numpy as np
@@ -7,7 +7,8 @@ import torch
 
 from tests.cnn_common import hovernet_test_weights, rel_l2
 from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
-from tiatoolbox_b200.models.architecture.hovernet import hovernet_forward_reference, hovernet_spec
+from oracle.torch_reference import hovernet_forward_reference
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
 from tiatoolbox_b200.models.hovernet_plan import HoVerNetPlan
 from tiatoolbox_b200.synthetic import he_tiles
 

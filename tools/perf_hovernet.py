@@ -1,4 +1,4 @@
-"""Manual perf probe (GPU box): python -m tests.perf_hovernet [batch] [precision]"""
+"""Manual perf probe (GPU box): python -m tools.perf_hovernet [batch] [precision]"""
 import sys
 import time
 
