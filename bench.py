@@ -1,22 +1,32 @@
 #!/usr/bin/env python
 """bench.py — the driver's benchmark contract for the stain + patch-CNN hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload macenko_hovernet|macenko]
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+                    [--workload macenko_hovernet|macenko|resnet18|fcn_tissue_mask|wsi]
 
-Metric (BASELINE.json): patches/sec on 256x256x3 tiles for Macenko stain normalisation + HoVer-Net
-(hovernet_fast-pannuke architecture, seeded weights) incl. the on-device watershed post-processing.
-One "step" = one pass of that path over one batch of synthetic tiles per GPU (SURVEY.md §8d generator).
-At N>1 the driver launches this file under torchrun, one rank per GPU; tiles are sharded across ranks
-(weak scaling: per-GPU batch fixed), no data-path collective except the all-gather of the final instance
-maps.  Rank 0 prints ONE JSON line.
+Headline metric (BASELINE.json, default workload `macenko_hovernet`): patches/sec on 256x256x3 tiles for Macenko stain
+normalisation + HoVer-Net (hovernet_fast-pannuke architecture) incl. the on-device watershed post-processing, instance
+table and contours.  One "step" = one pass of that path over one batch of synthetic tiles per GPU.
+The other workloads are BASELINE.json's configs 1, 2, 3 and 5 (`--workload ...`), one JSON line each.
 
-`value`        device-timed whole-job patches/s, inputs resident in HBM (CUDA events, max over ranks)
-`e2e`          same metric through the public engine API (NucleusInstanceSegmentor.run with the stain
-               normaliser installed as preproc_func) with HOST numpy buffers: H2D + kernels + D2H + host tail
-`roofline`     the dominant kernel (conv_gemm_kernel, tensor-bound): algorithmic FLOPs / its summed launch
-               durations (CUDA events per launch, measured live) vs MEASURED_PEAKS.json
-`roofline_stain` the fused stain kernel (HBM-bound) measured the same way
-`cpu_baseline` the CPU port of the reference path (numpy oracle + fp32 torch forward + post-proc oracle)
+Head maps.  Pretrained checkpoints are remote, and the heads of a random-weight HoVer-Net contain almost no nuclei, which
+would make the post-processing a no-op.  Following SURVEY.md §8d config 4 the network's forward runs in full on every tile
+and the post-processing (watershed, instance table, contours, D2H, host assembly) is fed SURVEY's synthetic head maps
+(K ~ U{20..60} nuclei per 164-px map) instead of the network's own: `BenchHoVerNet.infer_batch_device` below.  This holds
+for `value`, for `e2e` and for the reference arm alike, and is stated in `config.heads`.
+
+At N>1 the driver launches this file under torchrun, one rank per GPU; tiles are sharded across ranks (weak scaling:
+per-GPU batch fixed), no data-path collective except the all-gather of the final instance maps.  Rank 0 prints ONE JSON line.
+
+`value`             device-timed whole-job patches/s, inputs resident in HBM (CUDA events, max over ranks)
+`e2e`               the same metric through the public engine API (NucleusInstanceSegmentor.run with the stain normaliser installed
+                    as preproc_func) with HOST numpy buffers: H2D + kernels + D2H + host assembly of the result dict
+`roofline`          the dominant kernel (conv_gemm_kernel, tensor-bound): ALGORITHMIC FLOPs (297.87 GFLOP per
+                    patch) / its summed launch durations (CUDA events per launch, measured live) vs MEASURED_PEAKS.json;
+                    `by_class` splits the launches into tensor-bound and HBM-bound ones, each against its own roof
+`roofline_stain`    the fused stain kernel (HBM-bound) measured the same way on a 16 384-tile launch
+`library_baseline`  the reference's OWN CUDA path (its unmodified nn.Module, eager cuDNN, TF32 on / off) on the same GPU and tiles
+`cpu_baseline`      the unmodified reference's CPU path on the box's host cores on a bounded sample
 """
 from __future__ import annotations
 
@@ -37,11 +47,34 @@ sys.path.insert(0, str(ROOT))
 
 PATCH = 256
 STAIN_BYTES_PER_PATCH = 2 * PATCH * PATCH * 3      # read u8 once + write u8 once
-HOVERNET_GFLOP_PER_PATCH = 297.87                    # SURVEY.md Appendix C (2*MAC of all convs)
+GFLOP = {"hovernet_fast": 297.87, "resnet18": 3.627, "fcn_tissue_mask": 291.15}   # SURVEY.md Appendix C (2*MAC of all convs / linear)
 METRICS = {
     "macenko_hovernet": "patches/sec (256x256x3) Macenko + HoVer-Net (hovernet_fast) incl. on-device post-processing",
     "macenko": "patches/sec (256x256x3) Macenko stain-normalisation transform",
+    "resnet18": "patches/sec (224x224x3) PatchPredictor resnet18-kather100k",
+    "fcn_tissue_mask": "tiles/sec (1024x1024x3) SemanticSegmentor fcn-tissue_mask",
+    "wsi": "patches/sec (256x256x3) Vahadane stain-norm + HoVer-Net end to end on a synthetic 20k-patch WSI",
 }
+UNITS = {"fcn_tissue_mask": "tiles/s"}
+
+
+def common_config(workload: str) -> dict:
+    """The part of `config` both arms share (the driver compares it)."""
+    cfg = {
+        "macenko_hovernet": {"workload": "macenko_hovernet", "tile": [PATCH, PATCH, 3], "stain": "macenko, fit on a synthetic 256x256 target",
+                             "model": "hovernet_fast (num_types=6), seeded + BN-calibrated random weights (residual-branch gain 0.2-0.25)",
+                             "heads": "network forward runs in full; post-processing input = SURVEY 8d config-4 synthetic head maps "
+                                      "(K~U{20..60} nuclei per 164x164 map), because random-weight heads contain no nuclei"},
+        "macenko": {"workload": "macenko", "tile": [PATCH, PATCH, 3], "stain": "macenko, fit on a synthetic 256x256 target"},
+        "resnet18": {"workload": "resnet18", "tile": [224, 224, 3], "model": "resnet18-kather100k architecture (9 classes), seeded + calibrated weights"},
+        "fcn_tissue_mask": {"workload": "fcn_tissue_mask", "tile": [1024, 1024, 3],
+                            "model": "fcn-tissue_mask architecture (UNet, ResNet-50 encoder), seeded + calibrated weights"},
+        "wsi": {"workload": "wsi", "tile": [PATCH, PATCH, 3], "stain": "vahadane, fit on a synthetic 256x256 target",
+                "model": "hovernet_fast (num_types=6), seeded + BN-calibrated random weights",
+                "heads": "synthetic config-4 head maps per patch (as in macenko_hovernet)",
+                "slide": "virtual slide, 141 x 142 output patches of 164 px (SURVEY 8d config 5)"},
+    }
+    return dict(cfg[workload])
 
 
 def _peaks():
@@ -104,118 +137,342 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _tiles(n_unique: int, seed: int = 0) -> np.ndarray:
+# ---------------------------------------------------------------------------------------------------
+# synthetic inputs and seeded weights (shared by both arms)
+# ---------------------------------------------------------------------------------------------------
+def _tiles(n_unique: int, seed: int = 0, size: int = PATCH) -> np.ndarray:
     from tiatoolbox_b200.synthetic import he_tiles
 
-    return he_tiles(n_unique, PATCH, PATCH, seed=seed)
+    return he_tiles(n_unique, size, size, seed=seed)
+
+
+def _calibrated(spec, fname):
+    from tiatoolbox_b200.models.architecture._params import seeded_state_dict, with_calibration
+
+    return with_calibration(seeded_state_dict(spec, seed=0), ROOT / "tests" / "golden" / fname)
 
 
 def _hovernet_weights():
-    from tiatoolbox_b200.models.architecture._params import seeded_state_dict, with_calibration
     from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
 
-    return with_calibration(seeded_state_dict(hovernet_spec(3, 6, "fast"), seed=0), ROOT / "tests" / "golden" / "hovernet_fast_bn_calib.npz")
+    return _calibrated(hovernet_spec(3, 6, "fast"), "hovernet_fast_bn_calib.npz")
 
 
-# ---------------------------------------------------------------------------------------------------
-# CPU arm: a port of the reference's CPU path (the Python reference cannot travel to the GPU box)
-# ---------------------------------------------------------------------------------------------------
-def _cpu_stain_worker(args):
-    from oracle import stain_oracle as so
+def _resnet18_weights():
+    from tiatoolbox_b200.models.architecture.vanilla import cnn_spec
 
-    tiles, mt, mc = args
-    return np.stack([so.transform("macenko", t.copy(), mt, mc) for t in tiles])
+    return _calibrated(cnn_spec("resnet18", 9), "resnet18_bn_calib.npz")
 
 
-def cpu_pipeline(workload: str, sample: int, procs: int, threads: int):
-    """Macenko (numpy oracle, `procs` processes) [+ HoVer-Net fp32 torch forward (`threads` threads) + post-proc oracle]."""
+def _unet_weights():
+    from tiatoolbox_b200.models.architecture.unet import unet_spec
+
+    return _calibrated(unet_spec(3, 2, (3,)), "unet_bn_calib.npz")
+
+
+def _head_pool(n: int, seed: int = 0):
+    from tiatoolbox_b200.synthetic import hovernet_head_maps
+
+    return hovernet_head_maps(n, 164, seed=seed)
+
+
+def synthetic_slide(n_patches: int, seed: int = 0) -> np.ndarray:
+    """H&E-like slide whose 164-px output grid has about `n_patches` cells (141 x 142 for 20 000), built from seeded 256-px tiles."""
+    import math
+
+    nx = max(1, int(math.floor(math.sqrt(n_patches))))
+    ny = max(1, int(math.ceil(n_patches / nx)))
+    h, w = ny * 164, nx * 164
+    base = _tiles(16, seed=seed)
+    rng = np.random.default_rng(seed)
+    slide = np.empty((h, w, 3), np.uint8)
+    for y in range(0, h, 256):
+        for x in range(0, w, 256):
+            t = base[int(rng.integers(0, len(base)))]
+            slide[y:y + 256, x:x + 256] = t[: min(256, h - y), : min(256, w - x)]
+    return slide
+
+
+def make_bench_hovernet(pool_maps: int, device):
+    """HoVerNet subclass for the bench: the REAL plan runs on every tile; the head maps handed to the post-processing are the synthetic
+    config-4 maps (rotating through a device-resident pool), because the random-weight heads hold no nuclei (module docstring)."""
     import torch
 
-    from oracle import stain_oracle as so
+    from tiatoolbox_b200.models.architecture.hovernet import HoVerNet
+
+    class BenchHoVerNet(HoVerNet):
+        _pool = None
+        _cursor = 0
+
+        @staticmethod
+        def infer_batch_device(model, batch_data, *, device):
+            real = HoVerNet.infer_batch_device(model, batch_data, device=device)     # full forward, heads included
+            n = real[0].shape[0]
+            pool, m = BenchHoVerNet._pool, BenchHoVerNet._pool[0].shape[0]
+            idx = (torch.arange(n, device=pool[0].device) + BenchHoVerNet._cursor) % m
+            BenchHoVerNet._cursor = (BenchHoVerNet._cursor + n) % m
+            return tuple(p.index_select(0, idx) for p in pool)
+
+    model = BenchHoVerNet(num_types=6, mode="fast")
+    model.load_state_dict(_hovernet_weights())
+    BenchHoVerNet._pool = [torch.from_numpy(a).to(device) for a in _head_pool(pool_maps, seed=0)]
+    return model
+
+
+# ---------------------------------------------------------------------------------------------------
+# Reference arm: the UNMODIFIED reference on the host cores (oracle/reference_runner.py -> oracle/ref_shim.py -> /root/reference or oracle/_ref)
+# ---------------------------------------------------------------------------------------------------
+def reference_pipeline(workload: str, sample: int, cores: int):
+    """Returns (step_fn() -> seconds split dict, cpu_baseline description, pool owner).  One call of step_fn processes `sample` units."""
+    import torch
+
+    from oracle import reference_runner as rr
     from tiatoolbox_b200.synthetic import he_target
 
-    tiles = _tiles(sample, seed=0)
-    mt, mc = so.fit("macenko", he_target(PATCH, PATCH))
-    t0 = time.perf_counter()
-    if procs <= 1:
-        norm = _cpu_stain_worker((tiles, mt, mc))
-    else:
-        import multiprocessing as mp
+    if not rr.reference_available():
+        raise RuntimeError("reference sources not found (neither /root/reference nor oracle/_ref)")
+    torch.set_grad_enabled(False)
+    procs = min(cores, sample)
+    if workload in ("macenko_hovernet", "wsi"):
+        method = "macenko" if workload == "macenko_hovernet" else "vahadane"
+        pipe = rr.CpuPipeline(method, he_target(PATCH, PATCH), procs)
+        net, cls = rr.hovernet(_hovernet_weights())
+        rr.set_postproc_model(net)
+        pipe.start_pool()                                   # fork before torch spins up its threads
+        tiles = _tiles(sample, seed=0)
+        heads = _head_pool(sample, seed=0)
+        x1 = torch.from_numpy(tiles[:1])
+        threads = rr.best_torch_threads(lambda: cls.infer_batch(net, x1, device="cpu"), cores)
 
-        chunks = [c for c in np.array_split(tiles, procs) if len(c)]
-        with mp.get_context("fork").Pool(len(chunks)) as pool:
-            norm = np.concatenate(pool.map(_cpu_stain_worker, [(c, mt, mc) for c in chunks]))
-    t_stain = time.perf_counter() - t0
-    t_net = t_post = 0.0
-    if workload == "macenko_hovernet":
-        from oracle import hovernet_postproc_oracle as po
-        from oracle.torch_reference import hovernet_forward_reference, hovernet_heads_reference
+        def step():
+            t0 = time.perf_counter()
+            normed = pipe.stain(tiles)
+            t1 = time.perf_counter()
+            for i in range(0, sample, 4):                   # HoVerNet.infer_batch(model, batch, device="cpu") (hovernet.py:862-910)
+                cls.infer_batch(net, torch.from_numpy(normed[i:i + 4]), device="cpu")
+            t2 = time.perf_counter()
+            res = pipe.postproc(heads)                      # HoVerNet.postproc per patch (hovernet.py:751-859) on the synthetic head maps
+            t3 = time.perf_counter()
+            assert sum(r[1] for r in res) > 10 * sample
+            return {"stain_s": t1 - t0, "forward_s": t2 - t1, "postproc_s": t3 - t2}
 
-        torch.set_num_threads(threads)
-        sd = _hovernet_weights()
-        t0 = time.perf_counter()
-        with torch.inference_mode():
-            outs = []
-            for i in range(0, sample, 4):
-                x = torch.from_numpy(norm[i:i + 4]).permute(0, 3, 1, 2).float()
-                outs.append([o.numpy() for o in hovernet_heads_reference(hovernet_forward_reference(sd, x, "fast", 6))])
-        t_net = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        for o in outs:
-            for j in range(len(o[0])):
-                po.postproc(o[0][j], o[1][j], o[2][j])
-        t_post = time.perf_counter() - t0
-    total = t_stain + t_net + t_post
-    return sample / total, {"stain_s": t_stain, "forward_s": t_net, "postproc_s": t_post}
+        desc = (f"{sample} seeded tiles per step: reference {method.capitalize()}Normalizer.transform over {procs} processes; reference "
+                f"HoVerNet.infer_batch(device='cpu') with {threads} torch threads (best of 8..{cores}); reference HoVerNet.postproc over "
+                f"{procs} processes (scikit-image's remove_small_objects / watershed are absent from the image: compiled-C restatements)")
+        return step, desc, pipe
+    if workload == "macenko":
+        pipe = rr.CpuPipeline("macenko", he_target(PATCH, PATCH), procs)
+        pipe.start_pool()
+        tiles = _tiles(sample, seed=0)
 
+        def step():
+            t0 = time.perf_counter()
+            pipe.stain(tiles)
+            return {"stain_s": time.perf_counter() - t0}
 
-def _best_torch_threads(cores: int) -> int:
-    """oneDNN convs on these boxes slow down badly when every hyper-thread is used: give the CPU arm its best setting."""
-    import torch
+        return step, f"{sample} seeded tiles per step: reference MacenkoNormalizer.transform over {procs} processes", pipe
+    if workload == "resnet18":
+        net, cls = rr.resnet18(_resnet18_weights())
+        x = torch.from_numpy(_tiles(sample, seed=0, size=224).astype(np.float32) / 255.0)
+        threads = rr.best_torch_threads(lambda: cls.infer_batch(net, x[:16], device="cpu"), cores)
 
-    from oracle.torch_reference import hovernet_forward_reference
+        def step():
+            t0 = time.perf_counter()
+            for i in range(0, sample, 64):
+                cls.infer_batch(net, x[i:i + 64], device="cpu")
+            return {"forward_s": time.perf_counter() - t0}
 
-    sd = _hovernet_weights()
-    x = torch.from_numpy(_tiles(1, seed=5)).permute(0, 3, 1, 2).float()
-    best, best_t = cores, float("inf")
-    for th in sorted({min(cores, t) for t in (8, 16, 32, 64, cores)}):
-        torch.set_num_threads(th)
-        t0 = time.perf_counter()
-        with torch.inference_mode():
-            hovernet_forward_reference(sd, x, "fast", 6)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = th, dt
-    return best
+        return step, f"{sample} seeded 224x224 tiles per step: reference CNNModel.infer_batch(device='cpu'), {threads} torch threads", None
+    if workload == "fcn_tissue_mask":
+        net, cls = rr.unet(_unet_weights())
+        x = torch.from_numpy(_tiles(sample, seed=0, size=1024))
+        threads = rr.best_torch_threads(lambda: cls.infer_batch(net, x[:1], device="cpu"), cores)
+
+        def step():
+            t0 = time.perf_counter()
+            for i in range(sample):
+                cls.infer_batch(net, x[i:i + 1], device="cpu")
+            return {"forward_s": time.perf_counter() - t0}
+
+        return step, f"{sample} seeded 1024x1024 tiles per step: reference UNetModel.infer_batch(device='cpu'), {threads} torch threads", None
+    raise ValueError(workload)
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 8 if args.workload == "macenko_hovernet" else max(64, 8 * cores)
-    threads = _best_torch_threads(cores) if args.workload == "macenko_hovernet" else cores
-    total_s, n = 0.0, 0
-    parts = {}
+    wl = args.workload
+    sample = {"macenko_hovernet": 16, "wsi": 16, "macenko": max(64, 8 * cores), "resnet18": 256, "fcn_tissue_mask": 4}[wl]
+    unit = UNITS.get(wl, "patches/s")
+    try:
+        step, desc, pipe = reference_pipeline(wl, sample, cores)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "reference", "unavailable": repr(e)[:200]}), flush=True)
+        return
+    total_s, n, parts = 0.0, 0, {}
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        _, parts = cpu_pipeline(args.workload, sample, min(cores, sample), threads)
+        parts = step()
         if i >= args.warmup:
             total_s += time.perf_counter() - t0
             n += sample
+    if pipe is not None:
+        pipe.close()
     value = n / total_s
     line = {
-        "impl": "reference", "metric": METRICS[args.workload], "value": value, "unit": "patches/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRICS[wl], "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sample_tiles_per_step": sample, "last_step_split_s": parts, "torch_threads": threads},
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} seeded 256x256x3 tiles per step; numpy Macenko oracle over {min(cores, sample)} processes"
-                                   + ("; fp32 torch HoVer-Net forward on all cores; post-proc oracle (cv2/scipy + restated skimage)"
-                                      if args.workload == "macenko_hovernet" else "")},
-        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic", "config": common_config(wl),
+        "detail": {"sample_units_per_step": sample, "last_step_split_s": parts},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": desc},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers of the GPU arm
+# ---------------------------------------------------------------------------------------------------
+def _event_time(fn, warm: int, iters: int) -> float:
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def conv_roofline(plan, algorithmic_flops: float, pk: dict) -> tuple[dict, float]:
+    """Per-launch CUDA events over the plan's ops -> the roofline object of the conv engine (+ aux kernel ms)."""
+    import torch
+
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rows = []
+    aux_ms = 0.0
+    for rep in range(3):                                      # repetition 0 warms the eager launch path
+        for i, op in enumerate(plan.ops):
+            a.record()
+            op()
+            b.record()
+            torch.cuda.synchronize()
+            dt = a.elapsed_time(b)
+            if rep == 0:
+                rows.append([op, []])
+            rows[i][1].append(dt)
+    conv_ms = flops_grid = mma = 0.0
+    classes = {"tensor": [0, 0.0, 0.0, 0.0], "hbm": [0, 0.0, 0.0, 0.0]}    # launches, ms, flops, bytes
+    for op, ts in rows:
+        dt = statistics.median(ts[1:])
+        if not hasattr(op, "desc"):
+            aux_ms += dt
+            continue
+        conv_ms += dt
+        flops_grid += op.flops
+        mma += op.mma_flops
+        t_tensor = op.flops / (pk["tf_sustained"] * 1e12)
+        t_hbm = getattr(op, "bytes", 0.0) / (pk["hbm"] * 1e9)
+        c = classes["tensor" if t_tensor >= t_hbm else "hbm"]
+        c[0] += 1
+        c[1] += dt
+        c[2] += op.flops
+        c[3] += getattr(op, "bytes", 0.0)
+    ach = algorithmic_flops / (conv_ms / 1e3) / 1e12
+    by_class = {}
+    ct = classes["tensor"]
+    if ct[0]:
+        tf = ct[2] / (ct[1] / 1e3) / 1e12
+        by_class["tensor_bound_layers"] = {"launches": ct[0], "ms": ct[1], "achieved_tflops_on_grid_flops": tf, "frac_of_tensor_peak": tf / pk["tf_sustained"]}
+    ch = classes["hbm"]
+    if ch[0]:
+        gb = ch[3] / (ch[1] / 1e3) / 1e9
+        by_class["hbm_bound_layers"] = {"launches": ch[0], "ms": ch[1], "achieved_gbs_on_min_traffic": gb, "frac_of_hbm_peak": gb / pk["hbm"]}
+    roof = {
+        "bound": "tensor", "kernel": "conv_gemm_kernel (all launches of one step)", "achieved": ach, "peak": pk["tf_sustained"],
+        "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+        "algorithmic_flops_per_step": algorithmic_flops, "grid_flops_per_step": flops_grid, "kernel_ms_per_step": conv_ms,
+        "mma_issue_rate_tflops": mma / (conv_ms / 1e3) / 1e12,
+        "launches_per_step": sum(1 for op, _ in rows if hasattr(op, "desc")), "by_class": by_class,
+        "note": "frac is on ALGORITHMIC flops (SURVEY App. C); fp16x3 issues 3 tensor-core passes per algorithmic FLOP (cap 1/3); "
+                "by_class: a launch is tensor-bound when flops/tensor-peak >= min-traffic/HBM-peak, else HBM-bound",
+    }
+    return roof, aux_ms
+
+
+def stain_roofline(norm, dev, pk: dict, tiles: int = 16384) -> dict:
+    """The fused Macenko kernel on a launch big enough to fill the GPU (16 384 tiles = 3.2 GB in + 3.2 GB out)."""
+    import torch
+
+    uniq = torch.from_numpy(_tiles(64, seed=7)).to(dev)
+    x = uniq.repeat(tiles // len(uniq), 1, 1, 1).contiguous()
+    ms = _event_time(lambda: norm.transform_batch(x, raise_on_error=False), 2, 5)
+    ach = tiles * STAIN_BYTES_PER_PATCH / (ms / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "stain_fused_traffic.json"
+    if tp.exists():
+        t = json.loads(tp.read_text()).get("dram_bytes_per_tile")
+        traffic = None if t is None else t * tiles
+    del x
+    return {"bound": "hbm", "kernel": "stain_fused_kernel", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+            "traffic": traffic, "peak_source": pk["src"], "algorithmic_bytes_per_launch": tiles * STAIN_BYTES_PER_PATCH, "kernel_ms": ms,
+            "tiles_per_launch": tiles, "patches_per_s": tiles / ms * 1e3}
+
+
+def library_baseline(dev, x_u8, ours_forward_ms: float) -> dict:
+    """The reference's own CUDA path: its unmodified HoVerNet nn.Module (eager PyTorch / cuDNN) on the same GPU and the same tiles
+    (hovernet.py:896 `model(x)` inside infer_batch), TF32 on (PyTorch's cuDNN default) and off.  Informational: the kernel to beat."""
+    import torch
+
+    from oracle import reference_runner as rr
+
+    out = {"what": "reference HoVerNet nn.Module forward on cuda (eager PyTorch/cuDNN), same tiles, CUDA events",
+           "ours_forward_ms": ours_forward_ms, "batch": int(x_u8.shape[0])}
+    try:
+        net, cls = rr.hovernet(_hovernet_weights())
+        net = net.to(dev)
+        xin = x_u8.permute(0, 3, 1, 2).float().contiguous()
+        for name, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.inference_mode():
+                ms = _event_time(lambda: net(xin), 2, 4)
+            out[f"forward_ms_{name}"] = ms
+            out[f"patches_per_s_{name}"] = x_u8.shape[0] / ms * 1e3
+        torch.backends.cudnn.allow_tf32 = True
+        with torch.inference_mode():                      # the full public call: infer_batch incl. head activations and D2H
+            t0 = time.perf_counter()
+            for _ in range(2):
+                cls.infer_batch(net, x_u8, device=str(dev))
+            torch.cuda.synchronize()
+            out["infer_batch_ms_tf32_with_d2h"] = (time.perf_counter() - t0) / 2 * 1e3
+        del net
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 - an informational figure must never cost the bench line
+        out["error"] = repr(e)[:200]
+    return out
+
+
+def cpu_baseline_leg(workload: str) -> dict:
+    """Bounded sample of the reference's CPU path on this box's host cores (rank 0, N = 1 only)."""
+    cores = os.cpu_count() or 1
+    sample = {"macenko_hovernet": 8, "wsi": 8, "macenko": 256, "resnet18": 128, "fcn_tissue_mask": 2}[workload]
+    try:
+        step, desc, pipe = reference_pipeline(workload, sample, cores)
+        step()
+        t0 = time.perf_counter()
+        parts = step()
+        dt = time.perf_counter() - t0
+        if pipe is not None:
+            pipe.close()
+        return {"value": sample / dt, "unit": UNITS.get(workload, "patches/s"), "cores": cores, "kind": "reference", "sample": desc, "split_s": parts}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": UNITS.get(workload, "patches/s"), "cores": cores, "kind": "reference", "sample": f"failed: {e!r}"[:300]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -226,10 +483,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="macenko_hovernet", choices=sorted(METRICS))
-    ap.add_argument("--batch", type=int, default=None, help="tiles per GPU per step (device-resident leg)")
-    ap.add_argument("--e2e-batch", type=int, default=None, help="tiles per GPU per step (host-buffer leg)")
+    ap.add_argument("--batch", type=int, default=None, help="units per GPU per step (device-resident leg)")
+    ap.add_argument("--e2e-batch", type=int, default=None, help="units per GPU per step (host-buffer leg)")
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
+    ap.add_argument("--patches", type=int, default=20000, help="wsi workload: output patches of the virtual slide")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--stain-roofline-tiles", type=int, default=16384)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,8 +507,6 @@ def main():
     ge.build()
     from tiatoolbox_b200 import _lib
     from tiatoolbox_b200.models import postproc as pp
-    from tiatoolbox_b200.models.architecture.hovernet import HoVerNet
-    from tiatoolbox_b200.models.engine import NucleusInstanceSegmentor
     from tiatoolbox_b200.synthetic import he_target
     from tiatoolbox_b200.tools.stainnorm import get_normalizer
 
@@ -257,50 +515,100 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    combined = args.workload == "macenko_hovernet"
-    B = args.batch or (16 if combined else 8192)
-    # tiles per e2e call: a slide region feeds thousands of tiles per run(); 64 = four engine batches, enough for the engine's host / device
-    # pipelining to reach steady state while the default bench still finishes in seconds
-    Be = args.e2e_batch or (64 if combined else 1024)
+    wl = args.workload
     lib = _lib.lib()
     h = _lib.handle(local_rank)
+    pk = _peaks()
+    unit = UNITS.get(wl, "patches/s")
+    if wl == "wsi":
+        run_wsi(args, rank, world, local_rank, dev)
+        return
 
-    norm = get_normalizer("macenko")
-    norm.device = local_rank
-    norm.fit(he_target(PATCH, PATCH))
-    uniq = torch.from_numpy(_tiles(min(128, max(B, 16)), seed=rank)).to(dev)
+    B = args.batch or {"macenko_hovernet": 16, "macenko": 8192, "resnet18": 1024, "fcn_tissue_mask": 4}[wl]
+    # units per e2e call: a slide region feeds thousands of tiles per run(); a few engine batches are enough for the engine's host / device
+    # pipelining to reach steady state while the default bench still finishes in seconds
+    Be = args.e2e_batch or {"macenko_hovernet": 64, "macenko": 1024, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
+    size = {"resnet18": 224, "fcn_tissue_mask": 1024}.get(wl, PATCH)
+    uniq = torch.from_numpy(_tiles(min(128, max(B, 16)) if size != 1024 else 8, seed=rank, size=size)).to(dev)
     x = uniq.repeat((B + len(uniq) - 1) // len(uniq), 1, 1, 1)[:B].contiguous()
 
-    plan = None
-    if combined:
-        model = HoVerNet(num_types=6, mode="fast")
-        model.load_state_dict(_hovernet_weights())
+    norm = None
+    if wl in ("macenko_hovernet", "macenko"):
+        norm = get_normalizer("macenko")
+        norm.device = local_rank
+        norm.fit(he_target(PATCH, PATCH))
+
+    plan = model = eng = None
+    launches = {}
+    if wl == "macenko_hovernet":
+        from tiatoolbox_b200.models.engine import NucleusInstanceSegmentor
+
+        model = make_bench_hovernet(max(4 * B, 64), dev)
         model.precision = args.precision
         model.to(dev)
+        model._plan_batch = B
         plan = model.plan_for(B, dev, (PATCH, PATCH))
+        cls = type(model)
 
-    launches = {}
-
-    def step():
-        out, info = norm.transform_batch(x, return_info=True, raise_on_error=False)
-        launches["stain"] = lib.tiab_last_launch_count(h)
-        if not combined:
-            res = info["stain_matrix_source"]
-        else:
-            np_m, hv_m, tp_m = plan.forward(out)
-            inst, _table = pp.proc_np_hv_batch(np_m, hv_m, tp_m)
+        def step():
+            out, info = norm.transform_batch(x, return_info=True, raise_on_error=False)
+            launches["stain"] = lib.tiab_last_launch_count(h)
+            heads = cls.infer_batch_device(model, out, device=dev)
+            inst, table = pp.proc_np_hv_batch(*heads)
             launches["postproc"] = lib.tiab_last_launch_count(h)
-            res = inst
-        if world > 1:  # the only collective: all-gather of the final result map
-            gathered = torch.empty((world * res.shape[0], *res.shape[1:]), dtype=res.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, res.contiguous())
-        return out, info, res
+            pp.trace_contours(inst, table)
+            launches["contours"] = lib.tiab_last_launch_count(h)
+            if world > 1:  # the only collective: all-gather of the final result map
+                gathered = torch.empty((world * inst.shape[0], *inst.shape[1:]), dtype=inst.dtype, device=dev)
+                dist.all_gather_into_tensor(gathered, inst.contiguous())
+            return info, table
+    elif wl == "macenko":
+        def step():
+            _, info = norm.transform_batch(x, return_info=True, raise_on_error=False)
+            launches["stain"] = lib.tiab_last_launch_count(h)
+            return info, None
+    elif wl == "resnet18":
+        from tiatoolbox_b200.models.architecture.vanilla import CNNModel
 
+        model = CNNModel("resnet18", 9)
+        model.load_state_dict(_resnet18_weights())
+        model.precision = args.precision
+        model.to(dev)
+        model._plan_batch = B
+        plan = model.plan_for(B, dev, (224, 224))
+
+        def step():
+            probs = CNNModel.infer_batch_device(model, x, device=dev)
+            if world > 1:
+                g = torch.empty((world * probs.shape[0], probs.shape[1]), dtype=probs.dtype, device=dev)
+                dist.all_gather_into_tensor(g, probs.contiguous())
+            return None, None
+    else:  # fcn_tissue_mask
+        from tiatoolbox_b200.models.architecture.unet import UNetModel
+
+        model = UNetModel(3, 2, "resnet50", decoder_block=[3])
+        model.load_state_dict(_unet_weights())
+        model.precision = args.precision
+        model.to(dev)
+        model._plan_batch = B
+        plan = model.plan_for(B, dev, (1024, 1024))
+
+        def step():
+            probs = UNetModel.infer_batch_device(model, x, device=dev)
+            pred = probs.argmax(-1).to(torch.uint8)
+            if world > 1:
+                g = torch.empty((world * pred.shape[0], *pred.shape[1:]), dtype=pred.dtype, device=dev)
+                dist.all_gather_into_tensor(g, pred.contiguous())
+            return None, None
+
+    info = table = None
     for _ in range(args.warmup):
-        out, info, res = step()
+        info, table = step()
     torch.cuda.synchronize()
-    assert int(info["status"].sum().item()) == 0, "synthetic tiles must all normalise"
-    launches_per_step = launches.get("stain", 0) + launches.get("postproc", 0) + (plan.num_launches if plan else 0)
+    if info is not None:
+        assert int(info["status"].sum().item()) == 0, "synthetic tiles must all normalise"
+    nuclei_per_step = int(table["count"].sum().item()) if table is not None else None
+    launches_per_step = sum(launches.values()) + (plan.num_launches if plan else 0)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -325,74 +633,56 @@ def main():
     value = world * B * args.steps / (total_ms / 1e3)
 
     # ---- per-kernel timings for the rooflines (CUDA events around every launch; rank 0 only) ----
-    roof = {}
+    roofline = roofline_stain = None
+    breakdown = {}
     if rank == 0:
-        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-        a, b = ev(), ev()
-        ts = []
-        for _ in range(5):
-            a.record()
-            norm.transform_batch(x, raise_on_error=False)
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        roof["stain_ms"] = statistics.median(ts)
-        if combined:
-            conv_ms, conv_fl, conv_mma, aux_ms = 0.0, 0.0, 0.0, 0.0
-            for op in plan.ops:
-                a.record()
-                op()
-                b.record()
-                torch.cuda.synchronize()
-                dt = a.elapsed_time(b)
-                if hasattr(op, "desc"):
-                    conv_ms += dt
-                    conv_fl += op.flops
-                    conv_mma += op.mma_flops
-                else:
-                    aux_ms += dt
-            maps = plan.forward(out)
-            torch.cuda.synchronize()
-            a.record()
-            pp.proc_np_hv_batch(*maps)
-            b.record()
-            torch.cuda.synchronize()
-            roof.update(conv_ms=conv_ms, conv_flops=conv_fl, conv_mma_flops=conv_mma, aux_ms=aux_ms, postproc_ms=a.elapsed_time(b),
-                        conv_launches=sum(1 for op in plan.ops if hasattr(op, "desc")))
-            # random-weight heads hold almost no nuclei, so the post-processing is ALSO timed on synthetic head maps
-            # (~40 nuclei per 164-px map); reported beside the step's own figure, not part of `value`
-            try:
-                from tiatoolbox_b200.synthetic import hovernet_head_maps
-
-                syn = [torch.from_numpy(m).to(dev) for m in hovernet_head_maps(B, 164, seed=0)]
-                for _ in range(2):
-                    pp.proc_np_hv_batch(*syn)
-                torch.cuda.synchronize()
-                a.record()
-                for _ in range(3):
-                    pp.proc_np_hv_batch(*syn)
-                b.record()
-                torch.cuda.synchronize()
-                roof["postproc_synthetic_ms"] = a.elapsed_time(b) / 3
-            except Exception as e:  # noqa: BLE001 - an auxiliary figure must never cost the bench line
-                roof["postproc_synthetic_ms"] = None
-                print(f"[bench] synthetic post-processing timing skipped: {e!r}", file=sys.stderr)
+        if norm is not None:
+            breakdown["stain"] = _event_time(lambda: norm.transform_batch(x, raise_on_error=False), 1, 5)
+        if plan is not None:
+            key = {"macenko_hovernet": "hovernet_fast", "resnet18": "resnet18", "fcn_tissue_mask": "fcn_tissue_mask"}[wl]
+            roofline, aux_ms = conv_roofline(plan, GFLOP[key] * 1e9 * B, pk)
+            breakdown["conv_gemm"] = roofline["kernel_ms_per_step"]
+            breakdown["aux_glue"] = aux_ms
+            xin = norm.transform_batch(x, raise_on_error=False) if norm is not None else x
+            breakdown["forward_graph_replay"] = _event_time(lambda: plan.forward(xin), 2, 5)
+        if wl == "macenko_hovernet":
+            heads = [p[:B].contiguous() for p in type(model)._pool]
+            breakdown["postproc"] = _event_time(lambda: pp.proc_np_hv_batch(*heads), 2, 5)
+            inst, tab = pp.proc_np_hv_batch(*heads)
+            breakdown["contours"] = _event_time(lambda: pp.trace_contours(inst, tab), 2, 5)
+            breakdown["note"] = ("per-launch CUDA events, eager launches; postproc / contours on the synthetic config-4 head maps the timed step uses "
+                                 f"({nuclei_per_step} nuclei per step of {B} maps)")
+        if norm is not None:
+            roofline_stain = stain_roofline(norm, dev, pk, args.stain_roofline_tiles if wl == "macenko_hovernet" else max(B, 8192))
 
     # ---- e2e leg: numpy host buffers through the public API ----
-    # combined workload under torchrun: every rank hands the SAME tile list to eng.run, which shards it — so the list holds Be tiles per
-    # rank (weak scaling, like the device-resident leg)
-    Be_total = Be * world if combined else Be
+    # under torchrun every rank hands the SAME list to eng.run, which shards it — so the list holds Be units per rank (weak scaling)
+    sharded = wl != "macenko"
+    Be_total = Be * world if sharded else Be
     host_tiles = np.ascontiguousarray(x[:min(Be_total, B)].cpu().numpy())
     if len(host_tiles) < Be_total:
         host_tiles = np.concatenate([host_tiles] * (-(-Be_total // len(host_tiles))))[:Be_total]
-    if combined:
+    if wl == "macenko_hovernet":
         eng = NucleusInstanceSegmentor(model, batch_size=B, device=str(dev))
         model.preproc_func = norm.transform
         e2e_call = lambda: eng.run(host_tiles)  # noqa: E731
-        d2h = Be * 164 * 164 * 4
-    else:
+        api = "NucleusInstanceSegmentor.run(numpy tiles), preproc_func = MacenkoNormalizer.transform"
+    elif wl == "macenko":
         e2e_call = lambda: norm.transform_batch(host_tiles, raise_on_error=False)  # noqa: E731
-        d2h = world * (Be * PATCH * PATCH * 3 + Be * 68)
+        api = "StainNormalizer.transform_batch(numpy)"
+    elif wl == "resnet18":
+        from tiatoolbox_b200.models.engine import PatchPredictor
+
+        eng = PatchPredictor(model, batch_size=B, device=str(dev))
+        e2e_call = lambda: eng.run(host_tiles, return_probabilities=True)  # noqa: E731
+        api = "PatchPredictor.run(numpy tiles, return_probabilities=True)"
+    else:
+        from tiatoolbox_b200.models.engine import SemanticSegmentor
+
+        eng = SemanticSegmentor(model, batch_size=B, device=str(dev))
+        e2e_call = lambda: eng.run(host_tiles)  # noqa: E731
+        api = "SemanticSegmentor.run(numpy tiles)"
+    r = None
     for _ in range(2):
         r = e2e_call()
     if world > 1:
@@ -403,69 +693,114 @@ def main():
         r = e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if combined:   # bytes the engine actually copied device -> host in one call: instance maps + instance tables + contour vertices
-        d2h = int(getattr(eng, "d2h_bytes", d2h))
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    # total tiles per step over all ranks: eng.run shards the Be_total list itself; the stain-only call runs Be tiles on every rank
-    e2e_units = Be_total if combined else world * Be
+    e2e_units = Be_total if sharded else world * Be
     e2e_value = e2e_units * args.steps / float(te.item())
+    if wl == "macenko_hovernet":
+        d2h = int(getattr(eng, "d2h_bytes", Be * 164 * 164 * 4))
+        e2e_nuclei = int(sum(len(b) for b in r["box"]))
+    elif wl == "macenko":
+        d2h, e2e_nuclei = world * (Be * PATCH * PATCH * 3 + Be * 68), None
+    elif wl == "resnet18":
+        d2h, e2e_nuclei = e2e_units * 9 * 4, None
+    else:
+        d2h, e2e_nuclei = e2e_units * 512 * 512 * 2 * 4, None
 
     if rank == 0:
-        pk = _peaks()
+        cfg = common_config(wl)
         line = {
-            "metric": METRICS[args.workload], "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRICS[wl], "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16x3 (split-fp16 operands, fp32 accumulate)" if args.precision == "fp16x3" else "f16",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "tiles_per_gpu_per_step": B, "tile": [PATCH, PATCH, 3],
-                       "model": "hovernet_fast (num_types=6), seeded+calibrated random weights" if combined else None,
-                       "precision": args.precision if combined else "f32",
-                       "l2_policy": ("activations %.1f GB per step >> 126 MB L2" % (plan.bytes_allocated() / 1e9)) if combined else
+            "vs_baseline": None,
+            "dtype": ("u8 in / f32 math" if wl == "macenko" else
+                      "f16x3 (split-fp16 operands, fp32 accumulate)" if args.precision == "fp16x3" else "f16"),
+            "data": "synthetic", "config": cfg,
+            "detail": {"units_per_gpu_per_step": B, "precision": args.precision if plan is not None else "f32",
+                       "nuclei_per_step": nuclei_per_step,
+                       "l2_policy": ("activations %.1f GB per step >> 126 MB L2" % (plan.bytes_allocated() / 1e9)) if plan is not None else
                                     f"inputs+outputs {2 * B * PATCH * PATCH * 3 / 1e6:.0f} MB per step > 126 MB L2",
-                       "parallelism": f"patch-shard x{world}, all-gather of the result map"},
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": e2e_units * PATCH * PATCH * 3, "d2h_bytes_per_step": d2h,
-                    "tiles_per_step": e2e_units, "api": "NucleusInstanceSegmentor.run(numpy tiles), preproc_func = MacenkoNormalizer.transform"
-                    if combined else "StainNormalizer.transform_batch(numpy)"},
+                       "parallelism": f"unit-shard x{world}, all-gather of the result"},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e_units * size * size * 3, "d2h_bytes_per_step": d2h,
+                    "units_per_step": e2e_units, "api": api, "nuclei_per_step": e2e_nuclei},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
-        stain_ach = B * STAIN_BYTES_PER_PATCH / (roof["stain_ms"] / 1e3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "stain_fused_traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_tile")
-            traffic = None if traffic is None else traffic * B
-        stain_roof = {"bound": "hbm", "kernel": "stain_fused_kernel", "achieved": stain_ach, "peak": pk["hbm"], "unit": "GB/s",
-                      "frac": stain_ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
-                      "algorithmic_bytes_per_launch": B * STAIN_BYTES_PER_PATCH, "kernel_ms": roof["stain_ms"]}
-        if combined:
-            ach = roof["conv_flops"] / (roof["conv_ms"] / 1e3) / 1e12
-            line["roofline"] = {
-                "bound": "tensor", "kernel": "conv_gemm_kernel (all launches of one step)", "achieved": ach, "peak": pk["tf_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
-                "algorithmic_flops_per_step": roof["conv_flops"], "kernel_ms_per_step": roof["conv_ms"],
-                "mma_issue_rate_tflops": roof["conv_mma_flops"] / (roof["conv_ms"] / 1e3) / 1e12,
-                "launches_per_step": roof["conv_launches"],
-                "note": "fp16x3 issues 3 tensor-core passes per algorithmic FLOP; the 1x1 layers of the network are HBM-bound, "
-                        "so the aggregate sits well below the tensor peak (per-launch table: profiles/)",
-            }
-            line["breakdown_ms"] = {"stain": roof["stain_ms"], "conv_gemm": roof["conv_ms"], "aux_glue": roof["aux_ms"],
-                                    "postproc": roof["postproc_ms"],
-                                    "postproc_on_synthetic_nuclei_maps": roof.get("postproc_synthetic_ms"),
-                                    "note": "per-launch CUDA events, eager (not graph) launches; the last entry times the same post-processing on "
-                                            "synthetic head maps with ~40 nuclei per map (the network's random-weight heads hold almost none)"}
-            line["roofline_stain"] = stain_roof
-        else:
-            line["roofline"] = stain_roof
+        if roofline is not None:
+            line["roofline"] = roofline
+            if roofline_stain is not None:
+                line["roofline_stain"] = roofline_stain
+        elif roofline_stain is not None:
+            line["roofline"] = roofline_stain
+        line["breakdown_ms"] = breakdown
+        if wl == "macenko_hovernet" and world == 1 and not args.no_library_baseline:
+            line["library_baseline"] = library_baseline(dev, x, breakdown.get("forward_graph_replay"))
         if not args.no_cpu_baseline and world == 1:
-            sample = 4 if combined else 64
-            v, parts = cpu_pipeline(args.workload, sample, 1, min(32, os.cpu_count() or 1))
-            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": min(32, os.cpu_count() or 1) if combined else 1, "kind": "port",
-                                    "sample": f"{sample} seeded tiles: numpy Macenko oracle (1 process)"
-                                              + (", fp32 torch HoVer-Net forward (all cores), post-proc oracle" if combined else ""),
-                                    "split_s": parts}
+            line["cpu_baseline"] = cpu_baseline_leg(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_wsi(args, rank, world, local_rank, dev):
+    """BASELINE config 5: Vahadane -> HoVer-Net on a virtual 20k-patch slide through the WSI-mode public call; the slide is cut into bands of
+    post-processing tile rows (one per rank, strong scaling), NCCL gather of the tile instance maps.  Wall clock between barriers, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from tiatoolbox_b200.models.engine import NucleusInstanceSegmentor
+    from tiatoolbox_b200.synthetic import he_target
+    from tiatoolbox_b200.tools.stainnorm import get_normalizer
+
+    B = args.batch or 16
+    slide = synthetic_slide(args.patches)
+    norm = get_normalizer("vahadane")
+    norm.device = local_rank
+    norm.fit(he_target(PATCH, PATCH))
+    model = make_bench_hovernet(256, dev)
+    model.precision = args.precision
+    eng = NucleusInstanceSegmentor(model, batch_size=B, device=str(dev))
+    model.preproc_func = norm.transform
+
+    def once(img):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = eng.run(img, patch_mode=False, return_predictions=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return time.perf_counter() - t0, out
+
+    once(synthetic_slide(400))                      # warm-up: plan build, CUDA graph capture, pinned buffers
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    times, out = [], None
+    for _ in range(max(1, min(args.steps, 2))):
+        dt, out = once(slide)
+        times.append(dt)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        n = len(out["coordinates"])
+        v = n / float(t.item())
+        line = {
+            "metric": METRICS["wsi"], "value": v, "unit": "patches/s", "n_gpus": world, "steps": len(times), "warmup": 1,
+            "ms_per_step": float(t.item()) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16x3 (split-fp16 operands, fp32 accumulate)", "data": "synthetic", "config": common_config("wsi"),
+            "detail": {"slide_shape": list(slide.shape), "patches": n, "batch": B, "instances": int(len(out.get("box", []))),
+                       "timed": "host slide -> merged instance table + int32 WSI instance map (wall clock incl. H2D, stitching, tile post-processing, gather, merge)"},
+            "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": int(slide.nbytes), "d2h_bytes_per_step": int(getattr(eng, "d2h_bytes", 0)),
+                    "api": "NucleusInstanceSegmentor.run(slide, patch_mode=False, return_predictions=True), preproc_func = VahadaneNormalizer.transform"},
+            "gpu_launches": None, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg("wsi")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -162,3 +162,21 @@ def make_unet() -> None:
     probs = m.unet.UNetModel.infer_batch(net, torch.from_numpy(tiles), device="cpu")
     np.savez_compressed(GOLDEN / "unet_golden.npz", probs=np.asarray(probs, np.float32))
     print("unet golden:", probs.shape, probs.mean(axis=(0, 1, 2)))
+
+
+def make_unet_1024() -> None:
+    """BASELINE config 3 at its real tile size: the UNMODIFIED reference UNetModel.infer_batch on one seeded 1024 x 1024 tile (CPU fp32),
+    every 4th output pixel (512 x 512 x 2 -> 128 x 128 x 2 keeps the fixture at ~130 KB).   python -c "from oracle.make_golden_cnn import make_unet_1024 as f; f()" """
+    from oracle import ref_shim
+    from tests.cnn_common import unet_test_weights
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    m = ref_shim.load_models()
+    net = m.unet.UNetModel(3, 2, "resnet50", decoder_block=[3]).eval()
+    net.load_state_dict(unet_test_weights())
+    tile = he_tiles(1, 1024, 1024, seed=42)
+    probs = np.asarray(m.unet.UNetModel.infer_batch(net, torch.from_numpy(tile), device="cpu"), np.float32)
+    assert probs.shape == (1, 512, 512, 2)
+    np.savez_compressed(GOLDEN / "unet1024_golden.npz", probs_stride4=probs[:, ::4, ::4], mean=probs.mean(axis=(0, 1, 2)),
+                        frac_class1=np.float64((probs.argmax(-1) == 1).mean()))
+    print("unet 1024 golden:", probs.shape, probs.mean(axis=(0, 1, 2)), (probs.argmax(-1) == 1).mean())

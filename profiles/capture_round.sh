@@ -9,13 +9,13 @@ step() { name=$1; lim=$2; shift 2; echo "== $name"; ( timeout $lim "$@" ) > $out
 
 # 1. parity: the whole GPU suite (established modules first, newest last: tests/conftest.py)
 step tests 600 python -m pytest tests -q -m gpu -x --durations=8
-# 2. the opt-in code paths (floods v2 / v3, fused Reinhard): bit-exactness against the defaults + timings
-step experimental 240 env TIAB_EXPERIMENTAL=1 python -m pytest tests/test_watershed_v2_gpu.py tests/test_reinhard_fused_gpu.py tests/test_hovernetplus_gpu.py::test_two_task_wsi_mode_region -q -m gpu -s
+# 2. flood implementations 1-4 incl. the adversarial tie floods on the device + timings (printed with -s)
+step floods 240 python -m pytest tests/test_watershed_v2_gpu.py -q -m gpu -s
 # 3. benches (clock sampling is inside bench.py)
 ( timeout 400 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err ); tail -c 400 $out/${tag}_bench_n1.json
 ( timeout 200 python bench.py --workload macenko --steps 10 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_macenko.json 2>> $out/${tag}_bench_n1.err )
 ( timeout 120 python profiles/measure_new_kernels.py > $out/${tag}_new_kernels.jsonl 2> $out/${tag}_new_kernels.err ); cat $out/${tag}_new_kernels.jsonl | cut -c1-160
-( timeout 300 python bench_wsi.py --patches 2000 > $out/${tag}_bench_wsi_2000.json 2> $out/${tag}_bench_wsi.err ); tail -c 300 $out/${tag}_bench_wsi_2000.json
+( timeout 300 python bench.py --workload wsi --patches 2000 --no-cpu-baseline > $out/${tag}_bench_wsi_2000.json 2> $out/${tag}_bench_wsi.err ); tail -c 300 $out/${tag}_bench_wsi_2000.json
 # 4. launch list of one short bench run (shares, not absolutes)
 step ncu_launches 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
      python bench.py --steps 2 --warmup 1 --no-cpu-baseline

@@ -57,7 +57,7 @@ def test_logits_match_fp32_reference_and_golden(hv):
         e = rel_l2(got, r)
         m = np.abs(got - r).max() / np.abs(r).max()
         print(f"{b}: rel_l2 {e:.2e}  max/max {m:.2e}")
-        assert e <= 1e-3 and m <= 4e-3, (b, e, m)
+        assert e <= 1e-3 and m <= 1e-3, (b, e, m)     # north_star: 1e-3 relative (rel-L2 and max-error / max-magnitude)
         # the unmodified reference (CPU fp32) on the same weights, every 2nd pixel
         g = gold[f"fast_logits_{b}"]
         assert rel_l2(got[:, ::2, ::2], g) <= 1e-3

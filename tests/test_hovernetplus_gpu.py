@@ -75,8 +75,6 @@ def test_two_task_engine_contract(built_lib):
     assert np.array_equal(res[0]["predictions"], nuc["predictions"][0]) and np.array_equal(res[1]["predictions"], lay["predictions"][0])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TIAB_EXPERIMENTAL") != "1",
-                    reason="written after round 1's last GPU minute: first run with TIAB_EXPERIMENTAL=1 (profiles/capture_round.sh)")
 def test_two_task_wsi_mode_region(built_lib):
     """HoVerNetPlus on an in-memory region (fits one 2048-px tile: the un-tiled branch): nested two-task output == the oracle post-processing
     of the stitched head maps."""

@@ -120,7 +120,8 @@ def test_patch_pipeline_on_cpu_stand_ins(built_lib, monkeypatch, rows_fast, xy_f
     if rows_fast == 8 or xy_fast == 64:
         assert eng.d2h_bytes > 5 * full_rows * 16          # at least the full box columns came across
     else:
-        assert eng.d2h_bytes < 5 * (164 * 164 * 4 + 512 * 64 + 4096 * 8 + 4096)
+        # three batches of two fixed-size records: count / cont_total, f64 columns, instance map, int32 columns, contour vertices
+        assert eng.d2h_bytes == 6 * 4 * (2 + 2 * 512 * 3 + 164 * 164 + 512 * 8 + 2 * 4096)
 
 
 # ---- world_size 2 (gloo): contiguous patch shards, all-gather of the instance maps + object gather of the records ----------------------

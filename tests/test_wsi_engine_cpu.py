@@ -297,3 +297,34 @@ def test_plan_properties_over_random_slides():
             if len(p.my_patches):
                 assert np.array_equal(p.my_patches, np.arange(p.my_patches[0], p.my_patches[-1] + 1))
         assert sorted(owned) == list(range(len(p.tasks))), (w, h, world)
+
+
+def test_vertically_overlapping_patch_rows_are_averaged_like_the_reference():
+    """stride < patch_output in y: consecutive patch rows share output rows, which merge_vertical_chunkwise averages
+    (semantic_segmentor.py:1398-1534).  The band's blocks must go through ONE stitch call (stitching row by row let the later
+    row overwrite the shared pixels).  The stand-in network adds a per-call offset so that overlapping blocks differ."""
+    from oracle import stitch_oracle
+
+    io = IOConfig(patch_input_shape=(64, 64), stride_shape=(30, 30), patch_output_shape=(40, 40), margin=24, tile_shape=(170, 170))
+
+    class Eng(StubEngine):
+        def __init__(self):
+            super().__init__(batch_size=7)
+            self.ioconfig = io
+            self.seen = []
+
+        def _wsi_forward(self, x):
+            heads = [h + np.float32(0.01 * (self.forward_calls % 7)) for h in decode_heads(x.numpy()[:, 12:52, 12:52])]
+            self.forward_calls += 1
+            self.seen.append(heads[0])
+            return [torch.from_numpy(np.ascontiguousarray(h)) for h in heads]
+
+    image = synthetic_slide(200, 230, seed=5)
+    eng = Eng()
+    eng.return_probabilities = True
+    out = eng.run(image, patch_mode=False)
+    plan = WsiTilePlan((230, 200), io)
+    blocks = np.concatenate(eng.seen)
+    assert len(blocks) == len(plan.out_boxes) and plan.stride[1] < plan.patch_out[1]
+    want = stitch_oracle.stitch(blocks, plan.out_boxes.astype(np.int32), canvas_width=230, output_shape=(200, 230))
+    assert np.array_equal(out["probabilities"][0], want)

@@ -46,7 +46,7 @@ extern "C" int tiab_stain_augment(tiab_handle_t h, const float* conc_dev, const 
     h->err = "tiab_stain_augment: invalid argument";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   AugmentArgs a;
   for (int i = 0; i < 6; ++i) a.m[i] = (float)(M[i] * 1.4426950408889634);
   for (int i = 0; i < 2; ++i) a.alpha[i] = (float)alpha[i], a.beta[i] = (float)beta[i];

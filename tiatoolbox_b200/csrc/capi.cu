@@ -19,7 +19,9 @@ int tiab_create(int device, tiab_handle_t* out) {
   tiab_ctx* h = new (std::nothrow) tiab_ctx();
   if (!h) return TIAB_E_NOMEM;
   h->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) {
+  tiab_device_guard guard(device);   // the caller's current device is restored on return
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != device) {
     delete h;
     return TIAB_E_CUDA;
   }
@@ -35,7 +37,7 @@ int tiab_create(int device, tiab_handle_t* out) {
 
 void tiab_destroy(tiab_handle_t h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  TIAB_ON_DEVICE(h);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   void* dev[] = {h->stain_work, h->stain_state, h->stain_lut, h->dev_in, h->dev_out, h->dev_small, h->pp_work};
   for (void* p : dev)

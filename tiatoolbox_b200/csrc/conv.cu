@@ -1242,7 +1242,7 @@ int tiab_conv_gemm(tiab_handle_t h, const tiab_conv_desc_t* d, void* stream) {
     h->err = "tiab_conv_gemm: weight pitch smaller than taps*planes*ceil64(cin)";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   const int BN = (d->N % 256 == 0) ? 256 : (d->N % 128 == 0) ? 128 : (d->N % 64 == 0) ? 64 : 32;
   CUtensorMap ta, ta2, tb;
   int xcols = d->cin;   // extent of the operand map along the channels (taps may address different channel blocks of a row)
@@ -1358,7 +1358,7 @@ int tiab_im2col(tiab_handle_t h, const void* src, int src_is_u8, float u8_scale,
                 int ldsrc, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, void* out_f16, int ldout,
                 int Kpad, int out_lo, void* stream) {
   if (!h || !src || !out_f16 || Kpad < KH * KW * C || ldout < Kpad) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   if (!src_is_u8 && (C % 8) == 0 && (Kpad % 8) == 0 && (ldsrc % 8) == 0 && (ldout % 8) == 0 && (src_lo % 8) == 0 && (out_lo % 8) == 0 &&
       ((uintptr_t)src & 15) == 0 && ((uintptr_t)out_f16 & 15) == 0 && (!out_lo || src_lo)) {
     long long total8 = (long long)N * Ho * Wo * (Kpad >> 3);
@@ -1389,7 +1389,7 @@ int tiab_bn_relu(tiab_handle_t h, const void* src, int src_is_f32, int ldsrc, in
                  void* stream) {
   if (!h || !src || !dst_f16 || (C & 7) || (ldsrc & 7) || (lddst & 7) || (coffsrc & 7) || (coffdst & 7) || (src_lo & 7) || (dst_lo & 7))
     return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   bn_relu_kernel<<<aux_grid(h, rows * (C >> 3), 256), 256, 0, (cudaStream_t)stream>>>(src, src_is_f32, ldsrc, coffsrc, src_lo, scale,
                                                                                        shift, relu, rows, C, (__half*)dst_f16, lddst,
                                                                                        coffdst, dst_lo);
@@ -1402,7 +1402,7 @@ int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Ha
                       const float* shift, int relu, void* dst_f16, int Hd, int Wd, int dy, int dx, int ldd, int dst_lo,
                       void* stream) {
   if (!h || !a_f16 || !dst_f16 || (C & 7) || (lda & 7) || (ldb & 7) || (ldd & 7)) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   long long total = (long long)N * 4 * Ha * Wa * (C >> 3);
   upsample_add_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)a_f16, Ha, Wa, Hag, Wag, ay, ax, lda, a_lo, (const __half*)b_f16, Hb, Wb, by, bx, ldb, b_lo, N, C, scale, shift,
@@ -1414,7 +1414,7 @@ int tiab_upsample_add(tiab_handle_t h, const void* a_f16, int Ha, int Wa, int Ha
 int tiab_maxpool3x3s2(tiab_handle_t h, const void* src_f16, int N, int H, int W, int C, int lds, int src_lo, void* dst_f16,
                       int Hd, int Wd, int dy, int dx, int ldd, int dst_lo, void* stream) {
   if (!h || !src_f16 || !dst_f16 || (C & 7) || (lds & 7) || (ldd & 7)) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C >> 3);
   maxpool3x3s2_kernel<<<aux_grid(h, total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, N, H, W, C, lds, src_lo,
@@ -1427,7 +1427,7 @@ int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int 
                         const float* shift, int relu, const float* Wt, const float* bias, int nout, float* out, int ldout,
                         int coffout, void* stream) {
   if (!h || !x_f16 || !Wt || !out || nout < 1 || nout > 16 || (C & 7) || (ldx & 7) || (x_lo & 7)) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   size_t sm = (size_t)(nout * C + 2 * C) * sizeof(float);
   pointwise_head_kernel<<<aux_grid(h, rows, 128), 128, sm, (cudaStream_t)stream>>>((const __half*)x_f16, rows, C, ldx, x_lo, scale, shift,
                                                                                     relu, Wt, bias, nout, out, ldout, coffout);
@@ -1438,7 +1438,7 @@ int tiab_pointwise_head(tiab_handle_t h, const void* x_f16, long long rows, int 
 int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C, int ldx, int x_lo, const float* Wt,
                         const float* bias, int ncls, float* feat_out, float* probs, void* stream) {
   if (!h || !x_f16 || !Wt || !bias || !probs || ncls < 1 || ncls > 1024) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   size_t sm = (size_t)(C + ncls) * sizeof(float);
   gap_fc_softmax_kernel<<<N, 256, sm, (cudaStream_t)stream>>>((const __half*)x_f16, HW, C, ldx, x_lo, Wt, bias, ncls, feat_out, probs);
   AUX_LAUNCH_CHECK(h, "gap_fc_softmax");
@@ -1448,7 +1448,7 @@ int tiab_gap_fc_softmax(tiab_handle_t h, const void* x_f16, int N, int HW, int C
 int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv_logits, const float* tp_logits, int nt,
                         long long rows, float* np_out, float* hv_out, float* tp_out, void* stream) {
   if (!h || !np_logits || !hv_logits || !np_out || !hv_out || (tp_logits && (!tp_out || nt < 1))) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   hovernet_heads_kernel<<<aux_grid(h, rows, 256), 256, 0, (cudaStream_t)stream>>>(np_logits, hv_logits, tp_logits, nt, rows, np_out,
                                                                                   hv_out, tp_out);
   AUX_LAUNCH_CHECK(h, "hovernet_heads");
@@ -1457,7 +1457,7 @@ int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv
 
 int tiab_softmax_up2_crop(tiab_handle_t h, const float* logits, int N, int H, int W, int C, float* out, void* stream) {
   if (!h || !logits || !out || C < 1 || C > 8) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   softmax_up2_crop_kernel<<<aux_grid(h, (long long)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(logits, N, H, W, C, out);
   AUX_LAUNCH_CHECK(h, "softmax_up2_crop");
   return TIAB_OK;

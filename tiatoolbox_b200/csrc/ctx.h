@@ -39,6 +39,21 @@ struct tiab_ctx {
   cudaStream_t copy_stream = nullptr;
 };
 
+// Every C entry point works on the handle's device and puts the calling thread's CURRENT device back afterwards: a library that silently
+// changes it would make the caller's next allocation (e.g. PyTorch's on another rank's GPU) land on the wrong device.
+struct tiab_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit tiab_device_guard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    else if (prev < 0) cudaSetDevice(device);
+  }
+  ~tiab_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define TIAB_ON_DEVICE(h) tiab_device_guard _tiab_guard((h)->device)
+
 #define TIAB_CUDA_OK(h, expr)                                                                  \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \

@@ -1050,7 +1050,7 @@ int tiab_dbg_watershed_local(const double* dist_host, const int32_t* markers_hos
 int tiab_dbg_watershed_device(tiab_handle_t h, const double* dist_host, const int32_t* markers_host, const uint8_t* mask_host, int H, int W,
                               int impl, int32_t* out_host) {
   if (!h || !dist_host || !markers_host || !mask_host || !out_host || H <= 0 || W <= 0 || (impl != 3 && impl != 4)) return TIAB_E_INVALID;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   const int P = H * W;
   std::vector<int> lab((size_t)P), size((size_t)P, 0), bbox((size_t)P * 4, 0), hoff((size_t)P, 0), mk((size_t)P);
   std::vector<uint8_t> blb((size_t)P);
@@ -1162,7 +1162,7 @@ int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const fl
     h->err = "tiab_hovernet_postproc: incomplete instance table outputs";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (!h->pp_const_set) {
     double d[21], sm[21];
@@ -1321,7 +1321,7 @@ int tiab_hovernet_contours(tiab_handle_t h, const int32_t* inst_map, int N, int 
     h->err = "tiab_hovernet_contours: invalid argument";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
   TIAB_CUDA_OK(h, cudaMemsetAsync(cont_total, 0, (size_t)N * sizeof(int32_t), s));
   const long long threads = (long long)N * max_inst;

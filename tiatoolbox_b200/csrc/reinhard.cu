@@ -338,7 +338,7 @@ int tiab_reinhard_fit(tiab_handle_t h, const uint8_t* target_dev, int H, int W, 
     return TIAB_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   if (int rc = ensure_tables(h, s)) return rc;
   h->last_launches = 0;
   void* work = nullptr;
@@ -366,7 +366,7 @@ int tiab_reinhard_transform_batch(tiab_handle_t h, const uint8_t* in_dev, uint8_
     return TIAB_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   if (int rc = ensure_tables(h, s)) return rc;
   h->last_launches = 0;
   const long long npix = (long long)H * W;
@@ -421,7 +421,7 @@ int tiab_lab_convert(tiab_handle_t h, const uint8_t* in_dev, uint8_t* out_dev, l
     return TIAB_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   if (int rc = ensure_tables(h, s)) return rc;
   const int grid = (int)std::min<long long>((npix + RH_THREADS - 1) / RH_THREADS, (long long)h->sm_count * 8);
   lab_convert_kernel<<<grid, RH_THREADS, 0, s>>>(in_dev, out_dev, npix, inverse);

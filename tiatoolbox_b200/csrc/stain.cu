@@ -1471,7 +1471,7 @@ int tiab_stain_transform_batch(tiab_handle_t h, const tiab_stain_params_t* p, co
   StainConst C;
   int rc = make_const(h, p, H, W, M_target, maxC_target, 1, &C);
   if (rc) return rc;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   return run_stain(h, C, in_dev, out_dev, out_f32_dev, N, M_src_dev, maxC_src_dev, status_dev, (cudaStream_t)stream);
 }
 
@@ -1498,7 +1498,7 @@ int tiab_stain_fit(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t*
   StainConst C;
   int rc = make_const(h, p, H, W, nullptr, nullptr, 0, &C);
   if (rc) return rc;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   if ((rc = ensure_small(h, 1))) return rc;
   double* dM = (double*)h->dev_small;
   double* dC = dM + 6;
@@ -1545,7 +1545,7 @@ int tiab_stain_fit_host(tiab_handle_t h, const tiab_stain_params_t* p, const uin
     h->err = "tiab_stain_fit_host: null/empty argument";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   size_t bytes = (size_t)H * W * 3;
   int rc = ensure_staging(h, bytes);
   if (rc) return rc;
@@ -1563,7 +1563,7 @@ int tiab_stain_transform_host(tiab_handle_t h, const tiab_stain_params_t* p, con
     h->err = "tiab_stain_transform_host: null/empty argument";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   size_t bytes = (size_t)N * H * W * 3;
   int rc = ensure_staging(h, bytes);
   if (rc) return rc;
@@ -1599,7 +1599,7 @@ int tiab_stain_tissue_mask(tiab_handle_t h, const tiab_stain_params_t* p, const 
   StainConst C;
   int rc = make_const(h, p, H, W, nullptr, nullptr, 0, &C);
   if (rc) return rc;
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   if ((rc = stain_setup(h))) return rc;
   h->last_launches = 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1637,7 +1637,7 @@ int tiab_stain_concentrations(tiab_handle_t h, const uint8_t* in_dev, int N, int
     h->err = "tiab_stain_concentrations: singular stain matrix";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   int rc = stain_setup(h);
   if (rc) return rc;
   long long npix = (long long)N * H * W;

@@ -198,7 +198,7 @@ int tiab_merge_batch_to_canvas(tiab_handle_t h, const float* blocks_dev, int N, 
       return TIAB_E_INVALID;
     }
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   StitchTables t;
   build_row(locs_host, 0, N, W, 0, H, t);
   return run_stitch(h, blocks_dev, N, bh, bw, C, locs_host, t, W, H, W, 0, canvas_dev, count_dev, (cudaStream_t)stream);
@@ -212,7 +212,7 @@ int tiab_stitch_patches(tiab_handle_t h, const float* blocks_dev, int N, int bh,
     h->err = "tiab_stitch_patches: invalid argument (1 <= C <= 16, at least one block)";
     return TIAB_E_INVALID;
   }
-  TIAB_CUDA_OK(h, cudaSetDevice(h->device));
+  TIAB_ON_DEVICE(h);
   StitchTables t;
   int i0 = 0;
   for (int i = 1; i <= N; ++i) {

@@ -133,7 +133,15 @@ class EngineABC:
         func = self.model.preproc_func
         owner = getattr(func, "__self__", None)
         if isinstance(owner, StainNormalizer) and getattr(func, "__name__", "") == "transform":
-            return owner.transform_batch(x, raise_on_error=False)
+            # A patch whose stain fit fails (empty tissue mask on background / 255-padded patches, degenerate estimate) passes through
+            # UNNORMALISED — the reference raises ValueError for such a patch (utils/misc.py:286-288).  Deliberate deviation: a slide
+            # must not die on its background patches.  The failures are counted on the device (no sync per batch), reported once per
+            # run() (`stain_failures`, a warning), and `raise_on_stain_failure=True` restores the reference's behaviour.
+            out, info = owner.transform_batch(x, return_info=True, raise_on_error=False)
+            failed = (info["status"] != 0).sum()
+            acc = self.__dict__.get("_stain_failed")
+            self.__dict__["_stain_failed"] = failed if acc is None else acc + failed
+            return out
         if func is self.model.preproc or func is ModelABC.preproc:
             return x
         host = x.cpu().numpy()
@@ -155,13 +163,31 @@ class EngineABC:
         dist, rank, world = self._dist()
         lo, hi = self.shard_bounds(n_total, rank, world)
         self.model._plan_batch = self.batch_size
+        self._n_total = n_total
+        self._stain_failed = None
         raw = self.infer_patches(patches[lo:hi])
+        self._report_stain_failures()
         out = self.post_process_patches(raw, n_total)
         if self.labels is not None:
             out["labels"] = np.asarray(self.labels)
         return out
 
     predict = run  # tiatoolbox 1.x name
+
+    #: raise ValueError (like the reference) instead of passing a patch through unnormalised when its stain fit fails
+    raise_on_stain_failure = False
+
+    def _report_stain_failures(self) -> int:
+        acc = self.__dict__.get("_stain_failed")
+        self.stain_failures = 0 if acc is None else int(acc.item())
+        self.__dict__["_stain_failed"] = None
+        if self.stain_failures:
+            msg = (f"{self.stain_failures} patch(es) could not be stain-normalised (empty tissue mask / degenerate estimate) and were "
+                   "passed to the network unnormalised")
+            if self.raise_on_stain_failure:
+                raise ValueError("Empty tissue mask computed. " + msg)
+            logger.warning(msg)
+        return self.stain_failures
 
     # ---- to be specialised ----
     def infer_patches(self, patches: np.ndarray):

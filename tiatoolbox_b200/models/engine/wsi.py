@@ -123,11 +123,19 @@ class WsiTileModeMixin:
         return host.to(self.device, non_blocking=True)
 
     def _wsi_infer(self, band: torch.Tensor, plan: WsiTilePlan) -> list[torch.Tensor]:
-        """All patch rows of the band -> head canvases [(canvas rows, W, C) float32] in HBM."""
+        """All patch rows of the band -> head canvases [(canvas rows, W, C) float32] in HBM.
+
+        Rows that do not overlap vertically (stride == patch_output: every registry ioconfig) are stitched row by row as they finish.
+        With a vertical overlap (stride[1] < patch_output[1]) consecutive rows share output pixels that the reference's
+        merge_vertical_chunkwise averages (semantic_segmentor.py:1398-1534): the head blocks of the whole band are kept and go through
+        ONE `stitch_patches` call, which folds neighbouring rows exactly like the reference."""
         pw, ph = plan.patch_in
         Wp = band.shape[1]
         canvases: list[torch.Tensor] | None = None
         rowbufs: list[torch.Tensor] | None = None
+        v_overlap = plan.stride[1] < plan.patch_out[1]
+        kept_blocks: list[list[torch.Tensor]] = []
+        kept_locs: list[np.ndarray] = []
         for idx in plan.patch_rows():
             nx = len(idx)
             ins, outs = plan.in_boxes[idx], plan.out_boxes[idx]
@@ -136,21 +144,40 @@ class WsiTileModeMixin:
             sx = plan.stride[0]
             base = band[yoff: yoff + ph]
             view = base.as_strided((nx, ph, pw, 3), (sx * 3, Wp * 3, 3, 1), base.storage_offset() + xoff * 3)
+            if v_overlap:
+                rowbufs = None                 # the row's blocks are kept until the band is stitched: fresh buffers per row
             for k0 in range(0, nx, self.batch_size):
                 k1 = min(nx, k0 + self.batch_size)
                 heads = self._wsi_forward(view[k0:k1].contiguous())
                 if canvases is None:   # head count / channels are known after the first forward (infer_wsi :581-589)
                     ch = plan.canvas_y1 - plan.canvas_y0
+                    need = sum(ch * plan.W * h.shape[3] * 4 for h in heads)
+                    if self.device.type == "cuda":
+                        free = torch.cuda.mem_get_info(self.device)[0]
+                        if need > 0.9 * free:
+                            msg = (f"the head canvases of this band need {need / 1e9:.1f} GB of HBM ({free / 1e9:.1f} GB free): run the slide "
+                                   "on more ranks (bands shrink with the world size) or in regions; the B200 path keeps canvases resident "
+                                   "instead of spilling to zarr like the reference")
+                            raise MemoryError(msg)
                     canvases = [torch.zeros((ch, plan.W, h.shape[3]), dtype=torch.float32, device=self.device) for h in heads]
                 if rowbufs is None or rowbufs[0].shape[0] < nx:
                     rowbufs = [torch.empty((nx, *h.shape[1:]), dtype=torch.float32, device=self.device) for h in heads]
                 for buf, h in zip(rowbufs, heads):
                     buf[k0:k1].copy_(h)
+            locs = outs.astype(np.int32)
+            if v_overlap:
+                kept_blocks.append([buf[:nx] for buf in rowbufs])
+                kept_locs.append(locs)
+                continue
             y0 = int(outs[0, 1]) - plan.canvas_y0
             y1 = min(int(outs[0, 3]) - plan.canvas_y0, canvases[0].shape[0])
-            locs = outs.astype(np.int32)
             for buf, canvas in zip(rowbufs, canvases):
                 self._wsi_stitch_row(buf[:nx], locs, plan.W, canvas[y0:y1])
+        if v_overlap and kept_blocks:
+            locs = np.concatenate(kept_locs)
+            locs[:, [1, 3]] -= plan.canvas_y0          # band-local rows: the stitcher writes canvas rows [0, canvas height)
+            for hidx, canvas in enumerate(canvases):
+                self._wsi_stitch_row(torch.cat([blk[hidx] for blk in kept_blocks]), locs, plan.W, canvas)
         return canvases or []
 
     def _wsi_postproc_tiles(self, canvases: list[torch.Tensor], plan: WsiTilePlan, *, keep_maps: bool):
@@ -188,7 +215,10 @@ class WsiTileModeMixin:
                 pp.trace_contours(inst.contiguous(), table)     # vertices in tile coordinates, before any sliver crop (pad is background)
             inst = inst[:, :th, :tw]
             inst_h = inst.cpu().numpy()
-            if "cont_xy" in table:   # only the vertices that were written travel (the buffer is sized for the worst case)
+            # only the rows / vertices that were written travel (the buffers are sized for the worst case: H*W/10 rows, H*W/2 vertices)
+            rows_used = max(int(table["count"].max().item()), 1) if table["count"].numel() else 1
+            table = {k: (v[:, :rows_used] if v.dim() > 1 and k != "cont_xy" else v) for k, v in table.items()}
+            if "cont_xy" in table:
                 used = min(int(table["cont_total"].max().item()), table["cont_xy"].shape[1]) if table["cont_total"].numel() else 0
                 table = {**table, "cont_xy": table["cont_xy"][:, : max(used, 1)]}
             tab = {k: v.cpu().numpy() for k, v in table.items()}
@@ -307,11 +337,13 @@ class WsiTileModeMixin:
         dist, rank, world = self._dist()
         plan = WsiTilePlan((image.shape[1], image.shape[0]), io, rank, world)
         self.model._plan_batch = self.batch_size  # noqa: SLF001
+        self._stain_failed = None
         canvases = []
         if len(plan.my_patches):
             band = self._wsi_upload(image, plan)
             canvases = self._wsi_infer(band, plan)
             del band
+        self._report_stain_failures()
         results = self._wsi_postproc_tiles(canvases, plan, keep_maps=return_predictions)
         merged = self._wsi_gather(results, plan, keep_maps=return_predictions)
         out = self._wsi_replay(merged, plan, return_predictions=return_predictions)

@@ -117,6 +117,12 @@ class ConvOp:
         self._keep = (x, w, out16, out32, out16b, scale2, shift2, bias, res32, res16, pre_scale, pre_shift)
         self.flops = 2.0 * M * N * len(taps) * cin
         self.mma_flops = self.flops * nseg
+        # minimum HBM traffic of the launch (every operand read once, every output written once) — bench.py's HBM-bound / tensor-bound split
+        in_b = float(M) * cin * (4 if x_is_f32 else (4 if nseg == 3 else 2))   # fp32 stream, or fp16 hi (+ lo) planes
+        out_b = float(M) * N * ((4 if out32 is not None else 0) + (2 * (2 if lo16 else 1) if out16 is not None else 0)
+                                + (2 * (2 if lo16b else 1) if out16b is not None else 0))
+        res_b = float(M) * N * (4 if res32 is not None else ((4 if reslo else 2) if res16 is not None else 0))
+        self.bytes = in_b + out_b + res_b + float(w.numel()) * 2
 
     def __call__(self):
         h = _lib.handle(self.dev.index or 0)

@@ -58,6 +58,8 @@ class _ExtractorBase:
     """Shared plumbing: the C-ABI parameter block of this extractor."""
 
     method = "custom"
+    #: CUDA device index the extraction runs on (a StainNormalizer sets it to its own `device` in fit / transform)
+    device = 0
 
     def _params(self) -> _lib.StainParams:
         p = _lib.StainParams()
@@ -71,7 +73,8 @@ class _ExtractorBase:
                 p.fixed_matrix[i] = float(v)
         return p
 
-    def _device_stain_matrix(self, img: np.ndarray, device: int = 0) -> np.ndarray:
+    def _device_stain_matrix(self, img: np.ndarray, device: int | None = None) -> np.ndarray:
+        device = self.device if device is None else device
         img = np.ascontiguousarray(np.asarray(img).astype("uint8"))  # "ensure input image is uint8"
         if img.ndim != 3 or img.shape[2] != 3:
             msg = "img must be HxWx3"

@@ -27,6 +27,15 @@ from tiatoolbox_b200.utils.misc import load_stain_matrix
 from tiatoolbox_b200.utils.transforms import od2rgb
 
 
+def _current_device() -> int:
+    try:
+        import torch
+
+        return int(torch.cuda.current_device()) if torch.cuda.is_available() else 0
+    except Exception:  # noqa: BLE001
+        return 0
+
+
 def _is_torch_cuda(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
 
@@ -49,13 +58,15 @@ class StainNormalizer:
         self.stain_matrix_target_RGB: np.ndarray
         self._target = None
         self._target_conc = None
-        self.device = 0
+        self.device = _current_device()      # one process per GPU: the thread's current CUDA device (torch.cuda.set_device(local_rank))
 
     # -- reference API ------------------------------------------------------------------------
     @staticmethod
-    def get_concentrations(img: np.ndarray, stain_matrix: np.ndarray, device: int = 0) -> np.ndarray:
-        """Estimate the (H*W, 2) concentration matrix (stainnorm.py:49-66) on the GPU."""
+    def get_concentrations(img: np.ndarray, stain_matrix: np.ndarray, device: int | None = None) -> np.ndarray:
+        """Estimate the (H*W, 2) concentration matrix (stainnorm.py:49-66) on the GPU (`device`: default = the current CUDA device)."""
         import torch
+
+        device = _current_device() if device is None else int(device)
 
         img = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
         m = np.ascontiguousarray(np.asarray(stain_matrix, dtype=np.float64))
@@ -85,10 +96,12 @@ class StainNormalizer:
         if target.ndim != 3 or target.shape[2] != 3:
             msg = "target must be HxWx3"
             raise ValueError(msg)
-        if np.asarray(self.extractor.get_stain_matrix(target)).shape != (2, 3):
+        fixed = getattr(self.extractor, "stain_matrix", None)     # only a user matrix can have three rows (CustomExtractor)
+        if fixed is not None and np.asarray(fixed).shape != (2, 3):
             # the reference fails in np.percentile(...).reshape((1, 2)) for 3-row matrices (:81-85)
             msg = "cannot reshape array of size 3 into shape (1,2)"
             raise ValueError(msg)
+        self.extractor.device = self.device                        # extraction runs on this normaliser's GPU
         h = _lib.handle(self.device)
         m = np.zeros(6, np.float64)
         mc = np.zeros(2, np.float64)
