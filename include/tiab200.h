@@ -15,6 +15,7 @@
 #ifndef TIAB200_H
 #define TIAB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -225,6 +226,22 @@ int tiab_hovernet_heads(tiab_handle_t h, const float* np_logits, const float* hv
                         long long rows, float* np_out, float* hv_out, float* tp_out, void* stream);
 /* UNetModel.infer_batch tail (unet.py:458-465): softmax -> bilinear x2 -> centre crop */
 int tiab_softmax_up2_crop(tiab_handle_t h, const float* logits, int N, int H, int W, int C, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole networks from C.  Replaces ModelABC.infer_batch (tiatoolbox/models/models_abc.py:105-131;
+ * HoVerNet.infer_batch hovernet.py:862-910, UNetModel.infer_batch unet.py:420-468, CNNModel.infer_batch vanilla.py:215-253)
+ * for a binder without Python: `blob` is a serialised device plan (tiatoolbox_b200/models/export.py::export_plan — buffer table,
+ * packed weights / folded BatchNorm constants, launch list with relocatable pointers; host memory, copied during the call).
+ * tiab_net_create uploads it, replays it once and captures it into a CUDA graph; tiab_net_infer copies N <= batch uint8 NHWC
+ * images (device pointer) into the plan's input buffer, launches the graph on `stream` and copies the first N rows of every
+ * output head into out_heads[k] (device pointers, float32; NULL = skip that head).  tiab_net_info: info[0..4] = batch, in_h, in_w,
+ * in_c, n_outputs, then per output {ndim, dims[4]}.
+ */
+typedef struct tiab_net* tiab_net_t;
+int tiab_net_create(tiab_handle_t h, const void* blob, size_t blob_bytes, tiab_net_t* out);
+int tiab_net_info(tiab_net_t net, int* info, int capacity);
+int tiab_net_infer(tiab_net_t net, const uint8_t* in_nhwc_u8, int N, void* const* out_heads, void* stream);
+void tiab_net_destroy(tiab_net_t net);
 
 /* ---------------------------------------------------------------------------------------------
  * WSI stitching on the device.  Replaces the Python block loops of

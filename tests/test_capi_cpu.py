@@ -43,12 +43,12 @@ def test_ctypes_signatures_match_the_header_prototypes():
         res, args = _lib.SIGNATURES[name]
         assert len(args) == len(plist), (name, len(args), plist)
         for a, q in zip(args, plist):
-            is_ptr = "*" in q or "[" in q or q.startswith("tiab_handle_t")
+            is_ptr = "*" in q or "[" in q or q.startswith(("tiab_handle_t", "tiab_net_t"))
             ct_ptr = a in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(a, "_type_") and isinstance(a._type_, type)
             assert is_ptr == bool(ct_ptr), (name, q, a)
             if not is_ptr:
                 want = {"int": ctypes.c_int, "int32_t": ctypes.c_int, "long long": ctypes.c_longlong, "double": ctypes.c_double,
-                        "float": ctypes.c_float, "unsigned": ctypes.c_uint}
+                        "float": ctypes.c_float, "unsigned": ctypes.c_uint, "size_t": ctypes.c_size_t}
                 base = re.sub(r"\bconst\b", "", q).strip().rsplit(" ", 1)[0].strip()
                 assert a is want[base], (name, q, a)
 

@@ -109,6 +109,10 @@ SIGNATURES = {
     "tiab_gap_fc_softmax": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "tiab_hovernet_heads": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_longlong, _vp, _vp, _vp, _vp]),
     "tiab_softmax_up2_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "tiab_net_create": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(_vp)]),
+    "tiab_net_info": (C.c_int, [_vp, _ip, C.c_int]),
+    "tiab_net_infer": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "tiab_net_destroy": (None, [_vp]),
     "tiab_merge_batch_to_canvas": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "tiab_stitch_patches": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "tiab_hovernet_postproc": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -119,11 +119,19 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 __global__ void pp_threshold(const float* __restrict__ npm, long long total, uint8_t* __restrict__ fg) {
   PP_GRID_LOOP(i, total) fg[i] = npm[i] >= 0.5f ? 1 : 0;
 }
-__global__ void pp_ccl_init(const uint8_t* __restrict__ fg, int P, long long total, int* __restrict__ lab, int* __restrict__ size,
+__global__ void pp_ccl_init(const uint8_t* __restrict__ fg, int P, int W, long long total, int* __restrict__ lab, int* __restrict__ size,
                             int* __restrict__ bbox, uint8_t* __restrict__ border) {
   PP_GRID_LOOP(i, total) {
     const int p = (int)(i % P);
-    lab[i] = fg[i] ? p : -1;
+    // initial label = first pixel of the pixel's horizontal run (the run is one set from the start: no horizontal unions needed)
+    int s = -1;
+    if (fg[i]) {
+        const int x = p % W;
+        int k = 0;
+        while (k < x && fg[i - k - 1]) ++k;
+        s = p - k;
+    }
+    lab[i] = s;
     size[i] = 0;
     border[i] = 0;
     if (bbox) {
@@ -139,8 +147,8 @@ __global__ void pp_ccl_merge(const uint8_t* __restrict__ fg, int H, int W, long 
     const long long base = i - p;
     const int x = p % W, y = p / W;
     int* L = lab + base;
-    if (x + 1 < W && fg[i + 1]) uf_union(L, p, p + 1);
-    if (y + 1 < H && fg[i + W]) uf_union(L, p, p + W);
+    // two vertically adjacent runs are joined once, at the first column they share (the start of the upper or of the lower run)
+    if (y + 1 < H && fg[i + W] && (x == 0 || !fg[i - 1] || !fg[i + W - 1])) uf_union(L, p, p + W);
   }
 }
 __global__ void pp_ccl_flatten(int H, int W, long long total, int* __restrict__ lab, int* __restrict__ size, int* __restrict__ bbox,
@@ -732,74 +740,63 @@ __global__ void __launch_bounds__(32) pp_watershed_v3(const int* __restrict__ wl
 // bounding box is staged with a one-pixel frame (label -1 = not in the component) so that the four neighbour tests need no bounds
 // checks and are made by four lanes at once.  Components whose working set exceeds the shared-memory budget use the version-2 flood.
 struct WHeap {
-  uint32_t* khi;
-  uint32_t* klo;
-  uint32_t* t;
-  uint32_t* idx;
+  unsigned long long* key;   // order-preserving 64-bit image of the distance
+  unsigned long long* ti;    // (tie-break word << 32) | local pixel index
   int n;
 };
-__device__ __forceinline__ bool wkey_less(uint32_t ah, uint32_t al, uint32_t at, uint32_t bh, uint32_t bl, uint32_t bt) {
-  return ah != bh ? ah < bh : (al != bl ? al < bl : at < bt);
+__device__ __forceinline__ bool wkey_less(unsigned long long ak, uint32_t at, unsigned long long bk, uint32_t bt) {
+  return ak != bk ? ak < bk : at < bt;
 }
 // order-preserving map double -> uint64 (no NaNs; -0.0 canonicalised to +0.0 so that equal doubles give equal keys)
 __device__ __forceinline__ unsigned long long wkey_of(double d) {
   const long long b = __double_as_longlong(d + 0.0);
   return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
 }
-// place item (ih, il, it, ii) at node p and sift it down; every lane passes the same arguments
-__device__ __forceinline__ void wheap_sift_down(WHeap& h, int p, uint32_t ih, uint32_t il, uint32_t it, uint32_t ii, int lane) {
+// place item (ik, iti) at node p and sift it down; every lane passes the same arguments
+__device__ __forceinline__ void wheap_sift_down(WHeap& h, int p, unsigned long long ik, unsigned long long iti, int lane) {
   const unsigned FULL = 0xffffffffu;
   const int n = h.n;
+  const uint32_t it = (uint32_t)(iti >> 32);
   for (;;) {
     const int c0 = 32 * p + 1;
     if (c0 >= n) break;
     const int c = c0 + lane;
     const bool valid = c < n;
-    const uint32_t ch = valid ? h.khi[c] : 0xffffffffu;
-    const uint32_t cl = valid ? h.klo[c] : 0xffffffffu;
-    const uint32_t ct = valid ? h.t[c] : 0xffffffffu;
-    const uint32_t ci = valid ? h.idx[c] : 0u;
+    const unsigned long long ck = valid ? h.key[c] : ~0ull;
+    const unsigned long long cti = valid ? h.ti[c] : ~0ull;
+    const uint32_t ch = (uint32_t)(ck >> 32), cl = (uint32_t)ck, ct = (uint32_t)(cti >> 32);
     const uint32_t r1 = __reduce_min_sync(FULL, ch);
     unsigned e = __ballot_sync(FULL, valid && ch == r1);
-    uint32_t r2, r3;
-    int w;
-    if (__popc(e) == 1) {
-      w = __ffs(e) - 1;
-      r2 = __shfl_sync(FULL, cl, w);
-      r3 = __shfl_sync(FULL, ct, w);
-    } else {
+    if (__popc(e) != 1) {   // several children share the high word (plateaus, exact ties): refine on the low word, then the tie-break word
       const bool m1 = valid && ch == r1;
-      r2 = __reduce_min_sync(FULL, m1 ? cl : 0xffffffffu);
+      const uint32_t r2 = __reduce_min_sync(FULL, m1 ? cl : 0xffffffffu);
       e = __ballot_sync(FULL, m1 && cl == r2);
-      if (__popc(e) == 1) {
-        w = __ffs(e) - 1;
-        r3 = __shfl_sync(FULL, ct, w);
-      } else {
+      if (__popc(e) != 1) {
         const bool m2 = m1 && cl == r2;
-        r3 = __reduce_min_sync(FULL, m2 ? ct : 0xffffffffu);
+        const uint32_t r3 = __reduce_min_sync(FULL, m2 ? ct : 0xffffffffu);
         e = __ballot_sync(FULL, m2 && ct == r3);
-        w = __ffs(e) - 1;
       }
     }
-    if (!wkey_less(r1, r2, r3, ih, il, it)) break;
-    const uint32_t wi = __shfl_sync(FULL, ci, w);
-    if (lane == 0) h.khi[p] = r1, h.klo[p] = r2, h.t[p] = r3, h.idx[p] = wi;
+    const int w = __ffs(e) - 1;
+    const unsigned long long wk = __shfl_sync(FULL, ck, w), wti = __shfl_sync(FULL, cti, w);
+    if (!wkey_less(wk, (uint32_t)(wti >> 32), ik, it)) break;
+    if (lane == 0) h.key[p] = wk, h.ti[p] = wti;
     p = c0 + w;
   }
-  if (lane == 0) h.khi[p] = ih, h.klo[p] = il, h.t[p] = it, h.idx[p] = ii;
+  if (lane == 0) h.key[p] = ik, h.ti[p] = iti;
   __syncwarp();
 }
-__device__ __forceinline__ void wheap_push(WHeap& h, uint32_t ih, uint32_t il, uint32_t it, uint32_t ii, int lane) {
+__device__ __forceinline__ void wheap_push(WHeap& h, unsigned long long ik, unsigned long long iti, int lane) {
+  const uint32_t it = (uint32_t)(iti >> 32);
   int c = h.n++;
   while (c > 0) {
     const int par = (c - 1) >> 5;
-    const uint32_t ph = h.khi[par], pl = h.klo[par], pt = h.t[par];
-    if (!wkey_less(ih, il, it, ph, pl, pt)) break;
-    const uint32_t pi = h.idx[par];
-    if (lane == 0) h.khi[c] = ph, h.klo[c] = pl, h.t[c] = pt, h.idx[c] = pi;
+    const unsigned long long pk = h.key[par], pti = h.ti[par];
+    if (!wkey_less(ik, it, pk, (uint32_t)(pti >> 32))) break;
+    if (lane == 0) h.key[c] = pk, h.ti[c] = pti;
     c = par;
   }
-  if (lane == 0) h.khi[c] = ih, h.klo[c] = il, h.t[c] = it, h.idx[c] = ii;
+  if (lane == 0) h.key[c] = ik, h.ti[c] = iti;
   __syncwarp();
 }
 
@@ -823,7 +820,8 @@ __global__ void __launch_bounds__(32) pp_watershed_v4(const int* __restrict__ wl
     const int* bb = bbox + 4 * (base + r);
     const int x0 = bb[0], y0 = bb[1], bw = bb[2] - bb[0] + 1, bh = bb[3] - bb[1] + 1;
     const int pw = bw + 2, ph = bh + 2, parea = pw * ph, npx = size[base + r];
-    const size_t need = (size_t)parea * 12 + (size_t)npx * 16 + 64;
+    const int parea2 = (parea + 1) & ~1;
+    const size_t need = (size_t)parea2 * 12 + (size_t)npx * 16 + 64;
     if (need > (size_t)smem_bytes) {   // too large for shared memory: flood in place (global memory), lane 0, 8-ary heap
       if (lane == 0)
         ws_flood<8>(lab + base, r, bb[0], bb[1], bb[2], bb[3], blb + base, marker + base, dist + base, H, W,
@@ -831,20 +829,17 @@ __global__ void __launch_bounds__(32) pp_watershed_v4(const int* __restrict__ wl
       __syncwarp();
       continue;
     }
-    uint32_t* pkhi = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* pklo = pkhi + parea;
-    int* lout = reinterpret_cast<int*>(pklo + parea);
+    unsigned long long* pkey = reinterpret_cast<unsigned long long*>(smem);
     WHeap h;
-    h.khi = reinterpret_cast<uint32_t*>(lout + parea);
-    h.klo = h.khi + npx;
-    h.t = h.klo + npx;
-    h.idx = h.t + npx;
+    h.key = pkey + parea2;
+    h.ti = h.key + npx;
+    int* lout = reinterpret_cast<int*>(h.ti + npx);
     h.n = 0;
     // stage the framed box; marker pixels go straight into the (not yet ordered) heap array, tie-break word = raveled local index
     for (int q0 = 0; q0 < parea; q0 += 32) {
       const int q = q0 + lane;
       bool is_marker = false;
-      uint32_t kh = 0, kl = 0;
+      unsigned long long k = 0ull;
       if (q < parea) {
         const int ly = q / pw, lx = q - ly * pw;
         int lo = -1;
@@ -852,51 +847,61 @@ __global__ void __launch_bounds__(32) pp_watershed_v4(const int* __restrict__ wl
           const long long g = base + (long long)(y0 + ly - 1) * W + (x0 + lx - 1);
           if (lab[g] == r) {
             lo = marker[g];
-            const unsigned long long k = wkey_of(dist[g]);
-            kh = (uint32_t)(k >> 32), kl = (uint32_t)k;
+            k = wkey_of(dist[g]);
             is_marker = lo > 0;
           }
         }
         lout[q] = lo;
-        pkhi[q] = kh, pklo[q] = kl;
+        pkey[q] = k;
       }
       const unsigned mk = __ballot_sync(FULL, is_marker);
       if (is_marker) {
         const int pos = h.n + __popc(mk & ((1u << lane) - 1u));
-        h.khi[pos] = kh, h.klo[pos] = kl, h.t[pos] = (uint32_t)q, h.idx[pos] = (uint32_t)q;
+        h.key[pos] = k;
+        h.ti[pos] = ((unsigned long long)(uint32_t)q << 32) | (uint32_t)q;
       }
       h.n += __popc(mk);
     }
     __syncwarp();
     // heapify (Floyd): sift every internal node down, last parent first
     for (int p = (h.n - 2) >> 5; p >= 0 && h.n > 1; --p) {
-      const uint32_t ih = h.khi[p], il = h.klo[p], it = h.t[p], ii = h.idx[p];
+      const unsigned long long ik = h.key[p], iti = h.ti[p];
       __syncwarp();
-      wheap_sift_down(h, p, ih, il, it, ii, lane);
+      wheap_sift_down(h, p, ik, iti, lane);
     }
-    // the flood
+    // the flood.  The popped pixel's first new neighbour REPLACES the root (one sift-down instead of pop + push); only when there is
+    // none does the last item move to the root.
     uint32_t age = 0;
     const int off = lane == 0 ? -pw : (lane == 1 ? -1 : (lane == 2 ? 1 : pw));
     while (h.n > 0) {
-      const uint32_t pidx = h.idx[0];
-      const int last = --h.n;
-      if (last > 0) {
-        const uint32_t lh = h.khi[last], ll = h.klo[last], lt = h.t[last], li = h.idx[last];
-        __syncwarp();
-        wheap_sift_down(h, 0, lh, ll, lt, li, lane);
-      }
+      const int pidx = (int)(uint32_t)h.ti[0];
       const int label = lout[pidx];
-      const int q = (int)pidx + off;
+      const int q = pidx + off;
       const bool cand = lane < 4 && lout[q] == 0;
       unsigned bits = __ballot_sync(FULL, cand);
       if (cand) lout[q] = label;
-      __syncwarp();
+      if (bits) {
+        const int k = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int qq = pidx + (k == 0 ? -pw : (k == 1 ? -1 : (k == 2 ? 1 : pw)));
+        ++age;
+        const unsigned long long nk = pkey[qq];
+        __syncwarp();
+        wheap_sift_down(h, 0, nk, ((unsigned long long)(0x80000000u | age) << 32) | (uint32_t)qq, lane);
+      } else {
+        const int last = --h.n;
+        if (last > 0) {
+          const unsigned long long lk = h.key[last], lti = h.ti[last];
+          __syncwarp();
+          wheap_sift_down(h, 0, lk, lti, lane);
+        }
+      }
       while (bits) {
         const int k = __ffs(bits) - 1;
         bits &= bits - 1;
-        const int qq = (int)pidx + (k == 0 ? -pw : (k == 1 ? -1 : (k == 2 ? 1 : pw)));
+        const int qq = pidx + (k == 0 ? -pw : (k == 1 ? -1 : (k == 2 ? 1 : pw)));
         ++age;
-        wheap_push(h, pkhi[qq], pklo[qq], 0x80000000u | age, (uint32_t)qq, lane);
+        wheap_push(h, pkey[qq], ((unsigned long long)(0x80000000u | age) << 32) | (uint32_t)qq, lane);
       }
     }
     // labels back to the instance map (members only; unreached members stay 0 like in the reference)
@@ -1221,7 +1226,7 @@ int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const fl
 
   // 1. foreground: threshold -> CCL -> keep components > 9 px  (hovernet.py:541-545)
   PP_LAUNCH(h, pp_threshold, g, PP_THREADS, np_map, T, w.fg);
-  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.fg, P, T, w.lab, w.size, w.bbox, w.border);
+  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.fg, P, W, T, w.lab, w.size, w.bbox, w.border);
   PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.fg, H, W, T, w.lab);
   PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, w.lab, w.size, w.bbox, w.border);
   PP_LAUNCH(h, pp_rank_roots, N, 1024, w.lab, P, w.cid, w.roots, w.ncomp);
@@ -1244,7 +1249,7 @@ int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const fl
   PP_LAUNCH(h, pp_blur_cols, g, PP_THREADS, w.rowh, H, W, T, w.dist);
   // 4. fill holes (hovernet.py:604): CCL of the complement, holes = components that do not touch the border
   PP_LAUNCH(h, pp_invert, g, PP_THREADS, w.mk, T, w.fg);
-  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.fg, P, T, lab2, size2, (int*)nullptr, w.border);
+  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.fg, P, W, T, lab2, size2, (int*)nullptr, w.border);
   PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.fg, H, W, T, lab2);
   PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, lab2, size2, (int*)nullptr, w.border);
   PP_LAUNCH(h, pp_fill_holes, g, PP_THREADS, w.mk, lab2, w.border, P, T, w.tmp);
@@ -1252,7 +1257,7 @@ int tiab_hovernet_postproc_scaled(tiab_handle_t h, const float* np_map, const fl
   PP_LAUNCH(h, pp_morph, g, PP_THREADS, w.tmp, H, W, T, 0, w.fg);
   PP_LAUNCH(h, pp_morph, g, PP_THREADS, w.fg, H, W, T, 1, w.mk);
   // 6. label the seeds, drop <= obj_size - 1 px (9 at scale 1), keep ids (hovernet.py:607-614)
-  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.mk, P, T, lab2, size2, (int*)nullptr, w.border);
+  PP_LAUNCH(h, pp_ccl_init, g, PP_THREADS, w.mk, P, W, T, lab2, size2, (int*)nullptr, w.border);
   PP_LAUNCH(h, pp_ccl_merge, g, PP_THREADS, w.mk, H, W, T, lab2);
   PP_LAUNCH(h, pp_ccl_flatten, g, PP_THREADS, H, W, T, lab2, size2, (int*)nullptr, w.border);
   PP_LAUNCH(h, pp_rank_roots, N, 1024, lab2, P, w.cid, roots2, ncomp2);
