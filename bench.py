@@ -761,6 +761,9 @@ def run_wsi(args, rank, world, local_rank, dev):
     model = make_bench_hovernet(256, dev)
     model.precision = args.precision
     eng = NucleusInstanceSegmentor(model, batch_size=B, device=str(dev))
+    from tiatoolbox_b200.models.architecture import PRETRAINED_INFO
+
+    eng.ioconfig = PRETRAINED_INFO["hovernet_fast-pannuke"]["ioconfig"]     # pretrained_model.yaml:642-672 (patch 256 -> 164, tiles 1024, margin 128)
     model.preproc_func = norm.transform
 
     def once(img):

@@ -752,9 +752,30 @@ __device__ __forceinline__ unsigned long long wkey_of(double d) {
   const long long b = __double_as_longlong(d + 0.0);
   return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
 }
-// place item (ik, iti) at node p and sift it down; every lane passes the same arguments
-__device__ __forceinline__ void wheap_sift_down(WHeap& h, int p, unsigned long long ik, unsigned long long iti, int lane) {
+// minimum of the lanes' items under the total order (key, tie-break word): returns the winning lane, its item in (wk, wti).
+// One redux.sync on the key's high word settles it unless several lanes share that word (plateaus / exact ties).
+__device__ __forceinline__ int warp_argmin(unsigned long long ck, unsigned long long cti, bool valid, unsigned long long& wk,
+                                           unsigned long long& wti) {
   const unsigned FULL = 0xffffffffu;
+  const uint32_t ch = (uint32_t)(ck >> 32), cl = (uint32_t)ck, ct = (uint32_t)(cti >> 32);
+  const uint32_t r1 = __reduce_min_sync(FULL, valid ? ch : 0xffffffffu);
+  unsigned e = __ballot_sync(FULL, valid && ch == r1);
+  if (__popc(e) != 1) {
+    const bool m1 = valid && ch == r1;
+    const uint32_t r2 = __reduce_min_sync(FULL, m1 ? cl : 0xffffffffu);
+    e = __ballot_sync(FULL, m1 && cl == r2);
+    if (__popc(e) != 1) {
+      const bool m2 = m1 && cl == r2;
+      const uint32_t r3 = __reduce_min_sync(FULL, m2 ? ct : 0xffffffffu);
+      e = __ballot_sync(FULL, m2 && ct == r3);
+    }
+  }
+  const int w = __ffs(e) - 1;
+  wk = __shfl_sync(FULL, ck, w), wti = __shfl_sync(FULL, cti, w);
+  return w;
+}
+// place item (ik, iti) at node p of the shared-memory heap and sift it down; every lane passes the same arguments
+__device__ __forceinline__ void wheap_sift_down(WHeap& h, int p, unsigned long long ik, unsigned long long iti, int lane) {
   const int n = h.n;
   const uint32_t it = (uint32_t)(iti >> 32);
   for (;;) {
@@ -764,27 +785,94 @@ __device__ __forceinline__ void wheap_sift_down(WHeap& h, int p, unsigned long l
     const bool valid = c < n;
     const unsigned long long ck = valid ? h.key[c] : ~0ull;
     const unsigned long long cti = valid ? h.ti[c] : ~0ull;
-    const uint32_t ch = (uint32_t)(ck >> 32), cl = (uint32_t)ck, ct = (uint32_t)(cti >> 32);
-    const uint32_t r1 = __reduce_min_sync(FULL, ch);
-    unsigned e = __ballot_sync(FULL, valid && ch == r1);
-    if (__popc(e) != 1) {   // several children share the high word (plateaus, exact ties): refine on the low word, then the tie-break word
-      const bool m1 = valid && ch == r1;
-      const uint32_t r2 = __reduce_min_sync(FULL, m1 ? cl : 0xffffffffu);
-      e = __ballot_sync(FULL, m1 && cl == r2);
-      if (__popc(e) != 1) {
-        const bool m2 = m1 && cl == r2;
-        const uint32_t r3 = __reduce_min_sync(FULL, m2 ? ct : 0xffffffffu);
-        e = __ballot_sync(FULL, m2 && ct == r3);
-      }
-    }
-    const int w = __ffs(e) - 1;
-    const unsigned long long wk = __shfl_sync(FULL, ck, w), wti = __shfl_sync(FULL, cti, w);
+    unsigned long long wk, wti;
+    const int w = warp_argmin(ck, cti, valid, wk, wti);
     if (!wkey_less(wk, (uint32_t)(wti >> 32), ik, it)) break;
     if (lane == 0) h.key[p] = wk, h.ti[p] = wti;
     p = c0 + w;
   }
   if (lane == 0) h.key[p] = ik, h.ti[p] = iti;
   __syncwarp();
+}
+// The two top levels of the heap live in REGISTERS during the flood: the root in every lane (uniform), level-1 node j (heap index 1 + j)
+// in lane j.  A sift-down from the root then starts with a register-only argmin and touches shared memory only when the item sinks
+// below level 1; `n` (h.n) counts all items as before, heap indices >= 33 stay in shared memory.
+struct WTop {
+  unsigned long long rk, rti, lk, lti;
+};
+__device__ __forceinline__ void wtop_sift_root(WHeap& h, WTop& t, unsigned long long ik, unsigned long long iti, int lane) {
+  const uint32_t it = (uint32_t)(iti >> 32);
+  const int n = h.n;
+  if (n <= 1) {
+    t.rk = ik, t.rti = iti;
+    return;
+  }
+  unsigned long long wk, wti;
+  int w = warp_argmin(t.lk, t.lti, 1 + lane < n, wk, wti);
+  if (!wkey_less(wk, (uint32_t)(wti >> 32), ik, it)) {
+    t.rk = ik, t.rti = iti;
+    return;
+  }
+  t.rk = wk, t.rti = wti;
+  int p = 1 + w;          // the item sinks into level-1 node w (a register of lane w) or below it (shared memory)
+  const int reg_lane = w;
+  bool in_regs = true;
+  for (;;) {
+    const int c0 = 32 * p + 1;
+    if (c0 >= n) break;
+    const int c = c0 + lane;
+    const bool valid = c < n;
+    const unsigned long long ck = valid ? h.key[c] : ~0ull;
+    const unsigned long long cti = valid ? h.ti[c] : ~0ull;
+    w = warp_argmin(ck, cti, valid, wk, wti);
+    if (!wkey_less(wk, (uint32_t)(wti >> 32), ik, it)) break;
+    if (in_regs) {
+      if (lane == reg_lane) t.lk = wk, t.lti = wti;
+      in_regs = false;
+    } else if (lane == 0) {
+      h.key[p] = wk, h.ti[p] = wti;
+    }
+    p = c0 + w;
+  }
+  if (in_regs) {
+    if (lane == reg_lane) t.lk = ik, t.lti = iti;
+  } else {
+    if (lane == 0) h.key[p] = ik, h.ti[p] = iti;
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void wtop_push(WHeap& h, WTop& t, unsigned long long ik, unsigned long long iti, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t it = (uint32_t)(iti >> 32);
+  int c = h.n++;
+  if (c == 0) {
+    t.rk = ik, t.rti = iti;
+    return;
+  }
+  bool wrote = false;
+  while (c >= 33) {
+    const int par = (c - 1) >> 5;
+    unsigned long long pk, pti;
+    if (par >= 33) {
+      pk = h.key[par], pti = h.ti[par];
+    } else {
+      pk = __shfl_sync(FULL, t.lk, par - 1), pti = __shfl_sync(FULL, t.lti, par - 1);
+    }
+    if (!wkey_less(ik, it, pk, (uint32_t)(pti >> 32))) break;
+    if (lane == 0) h.key[c] = pk, h.ti[c] = pti;
+    wrote = true;
+    c = par;
+  }
+  if (c >= 33) {
+    if (lane == 0) h.key[c] = ik, h.ti[c] = iti;
+    wrote = true;
+  } else if (wkey_less(ik, it, t.rk, (uint32_t)(t.rti >> 32))) {   // level 1 (lane c - 1), then against the root
+    if (lane == c - 1) t.lk = t.rk, t.lti = t.rti;
+    t.rk = ik, t.rti = iti;
+  } else if (lane == c - 1) {
+    t.lk = ik, t.lti = iti;
+  }
+  if (wrote) __syncwarp();
 }
 __device__ __forceinline__ void wheap_push(WHeap& h, unsigned long long ik, unsigned long long iti, int lane) {
   const uint32_t it = (uint32_t)(iti >> 32);
@@ -870,11 +958,15 @@ __global__ void __launch_bounds__(32) pp_watershed_v4(const int* __restrict__ wl
       wheap_sift_down(h, p, ik, iti, lane);
     }
     // the flood.  The popped pixel's first new neighbour REPLACES the root (one sift-down instead of pop + push); only when there is
-    // none does the last item move to the root.
+    // none does the last item move to the root.  Root and level 1 of the heap are held in registers (WTop).
+    WTop top;
+    top.rk = top.rti = top.lk = top.lti = ~0ull;
+    if (h.n > 0) top.rk = h.key[0], top.rti = h.ti[0];
+    if (1 + lane < h.n) top.lk = h.key[1 + lane], top.lti = h.ti[1 + lane];
     uint32_t age = 0;
     const int off = lane == 0 ? -pw : (lane == 1 ? -1 : (lane == 2 ? 1 : pw));
     while (h.n > 0) {
-      const int pidx = (int)(uint32_t)h.ti[0];
+      const int pidx = (int)(uint32_t)top.rti;
       const int label = lout[pidx];
       const int q = pidx + off;
       const bool cand = lane < 4 && lout[q] == 0;
@@ -885,15 +977,17 @@ __global__ void __launch_bounds__(32) pp_watershed_v4(const int* __restrict__ wl
         bits &= bits - 1;
         const int qq = pidx + (k == 0 ? -pw : (k == 1 ? -1 : (k == 2 ? 1 : pw)));
         ++age;
-        const unsigned long long nk = pkey[qq];
-        __syncwarp();
-        wheap_sift_down(h, 0, nk, ((unsigned long long)(0x80000000u | age) << 32) | (uint32_t)qq, lane);
+        wtop_sift_root(h, top, pkey[qq], ((unsigned long long)(0x80000000u | age) << 32) | (uint32_t)qq, lane);
       } else {
         const int last = --h.n;
         if (last > 0) {
-          const unsigned long long lk = h.key[last], lti = h.ti[last];
-          __syncwarp();
-          wheap_sift_down(h, 0, lk, lti, lane);
+          unsigned long long lk, lti;
+          if (last >= 33) {
+            lk = h.key[last], lti = h.ti[last];
+          } else {
+            lk = __shfl_sync(FULL, top.lk, last - 1), lti = __shfl_sync(FULL, top.lti, last - 1);
+          }
+          wtop_sift_root(h, top, lk, lti, lane);
         }
       }
       while (bits) {
@@ -901,8 +995,9 @@ __global__ void __launch_bounds__(32) pp_watershed_v4(const int* __restrict__ wl
         bits &= bits - 1;
         const int qq = pidx + (k == 0 ? -pw : (k == 1 ? -1 : (k == 2 ? 1 : pw)));
         ++age;
-        wheap_push(h, pkey[qq], ((unsigned long long)(0x80000000u | age) << 32) | (uint32_t)qq, lane);
+        wtop_push(h, top, pkey[qq], ((unsigned long long)(0x80000000u | age) << 32) | (uint32_t)qq, lane);
       }
+      __syncwarp();
     }
     // labels back to the instance map (members only; unreached members stay 0 like in the reference)
     for (int q = lane; q < parea; q += 32) {
