@@ -238,27 +238,25 @@ def reference_pipeline(workload: str, sample: int, cores: int):
         pipe = rr.CpuPipeline(method, he_target(PATCH, PATCH), procs)
         net, cls = rr.hovernet(_hovernet_weights())
         rr.set_postproc_model(net)
-        pipe.start_pool()                                   # fork before torch spins up its threads
+        pipe.start_pool((cls, net), cores, kind="hovernet")
         tiles = _tiles(sample, seed=0)
         heads = _head_pool(sample, seed=0)
-        x1 = torch.from_numpy(tiles[:1])
-        threads = rr.best_torch_threads(lambda: cls.infer_batch(net, x1, device="cpu"), cores)
 
         def step():
             t0 = time.perf_counter()
             normed = pipe.stain(tiles)
             t1 = time.perf_counter()
-            for i in range(0, sample, 4):                   # HoVerNet.infer_batch(model, batch, device="cpu") (hovernet.py:862-910)
-                cls.infer_batch(net, torch.from_numpy(normed[i:i + 4]), device="cpu")
+            pipe.forward([normed[i:i + 4] for i in range(0, sample, 4)])   # HoVerNet.infer_batch(model, batch, device="cpu") (hovernet.py:862-910)
             t2 = time.perf_counter()
             res = pipe.postproc(heads)                      # HoVerNet.postproc per patch (hovernet.py:751-859) on the synthetic head maps
             t3 = time.perf_counter()
             assert sum(r[1] for r in res) > 10 * sample
             return {"stain_s": t1 - t0, "forward_s": t2 - t1, "postproc_s": t3 - t2}
 
-        desc = (f"{sample} seeded tiles per step: reference {method.capitalize()}Normalizer.transform over {procs} processes; reference "
-                f"HoVerNet.infer_batch(device='cpu') with {threads} torch threads (best of 8..{cores}); reference HoVerNet.postproc over "
-                f"{procs} processes (scikit-image's remove_small_objects / watershed are absent from the image: compiled-C restatements)")
+        desc = (f"{sample} seeded tiles per step: reference {method.capitalize()}Normalizer.transform over {procs} single-threaded processes; "
+                f"reference HoVerNet.infer_batch(device='cpu') in batches of 4 over {pipe.fwd_workers} worker process(es) x {pipe.fwd_threads} torch "
+                f"threads; reference HoVerNet.postproc over {procs} processes (scikit-image's remove_small_objects / watershed are absent "
+                "from the image: compiled-C restatements)")
         return step, desc, pipe
     if workload == "macenko":
         pipe = rr.CpuPipeline("macenko", he_target(PATCH, PATCH), procs)
@@ -270,31 +268,34 @@ def reference_pipeline(workload: str, sample: int, cores: int):
             pipe.stain(tiles)
             return {"stain_s": time.perf_counter() - t0}
 
-        return step, f"{sample} seeded tiles per step: reference MacenkoNormalizer.transform over {procs} processes", pipe
+        return step, f"{sample} seeded tiles per step: reference MacenkoNormalizer.transform over {procs} single-threaded processes", pipe
     if workload == "resnet18":
         net, cls = rr.resnet18(_resnet18_weights())
-        x = torch.from_numpy(_tiles(sample, seed=0, size=224).astype(np.float32) / 255.0)
-        threads = rr.best_torch_threads(lambda: cls.infer_batch(net, x[:16], device="cpu"), cores)
+        pipe = rr.CpuPipeline(None, None, 1)
+        pipe.start_pool((cls, net), cores, kind="resnet18")
+        x = _tiles(sample, seed=0, size=224).astype(np.float32) / 255.0
+        bs = max(16, sample // max(1, pipe.fwd_workers))
 
         def step():
             t0 = time.perf_counter()
-            for i in range(0, sample, 64):
-                cls.infer_batch(net, x[i:i + 64], device="cpu")
+            pipe.forward([x[i:i + bs] for i in range(0, sample, bs)])
             return {"forward_s": time.perf_counter() - t0}
 
-        return step, f"{sample} seeded 224x224 tiles per step: reference CNNModel.infer_batch(device='cpu'), {threads} torch threads", None
+        return step, (f"{sample} seeded 224x224 tiles per step: reference CNNModel.infer_batch(device='cpu') in batches of {bs} over "
+                      f"{pipe.fwd_workers} worker process(es) x {pipe.fwd_threads} torch threads"), pipe
     if workload == "fcn_tissue_mask":
         net, cls = rr.unet(_unet_weights())
-        x = torch.from_numpy(_tiles(sample, seed=0, size=1024))
-        threads = rr.best_torch_threads(lambda: cls.infer_batch(net, x[:1], device="cpu"), cores)
+        pipe = rr.CpuPipeline(None, None, 1)
+        pipe.start_pool((cls, net), cores, kind="unet")
+        x = _tiles(sample, seed=0, size=1024)
 
         def step():
             t0 = time.perf_counter()
-            for i in range(sample):
-                cls.infer_batch(net, x[i:i + 1], device="cpu")
+            pipe.forward([x[i:i + 1] for i in range(sample)])
             return {"forward_s": time.perf_counter() - t0}
 
-        return step, f"{sample} seeded 1024x1024 tiles per step: reference UNetModel.infer_batch(device='cpu'), {threads} torch threads", None
+        return step, (f"{sample} seeded 1024x1024 tiles per step: reference UNetModel.infer_batch(device='cpu'), one tile per call over "
+                      f"{pipe.fwd_workers} worker process(es) x {pipe.fwd_threads} torch threads"), pipe
     raise ValueError(workload)
 
 
@@ -303,7 +304,8 @@ def run_reference(args, rank: int):
         return
     cores = os.cpu_count() or 1
     wl = args.workload
-    sample = {"macenko_hovernet": 16, "wsi": 16, "macenko": max(64, 8 * cores), "resnet18": 256, "fcn_tissue_mask": 4}[wl]
+    nfw = max(1, cores // 16)                 # forward workers of the CPU arm (oracle/reference_runner.CpuPipeline.start_pool)
+    sample = {"macenko_hovernet": 4 * nfw, "wsi": 4 * nfw, "macenko": max(64, 8 * cores), "resnet18": 64 * nfw, "fcn_tissue_mask": max(2, nfw)}[wl]
     unit = UNITS.get(wl, "patches/s")
     try:
         step, desc, pipe = reference_pipeline(wl, sample, cores)
@@ -461,7 +463,8 @@ def library_baseline(dev, x_u8, ours_forward_ms: float) -> dict:
 def cpu_baseline_leg(workload: str) -> dict:
     """Bounded sample of the reference's CPU path on this box's host cores (rank 0, N = 1 only)."""
     cores = os.cpu_count() or 1
-    sample = {"macenko_hovernet": 8, "wsi": 8, "macenko": 256, "resnet18": 128, "fcn_tissue_mask": 2}[workload]
+    nfw = max(1, cores // 16)
+    sample = {"macenko_hovernet": 4 * nfw, "wsi": 4 * nfw, "macenko": max(64, 4 * cores), "resnet18": 64 * nfw, "fcn_tissue_mask": max(2, nfw)}[workload]
     try:
         step, desc, pipe = reference_pipeline(workload, sample, cores)
         step()
@@ -527,7 +530,7 @@ def main():
     B = args.batch or {"macenko_hovernet": 16, "macenko": 8192, "resnet18": 1024, "fcn_tissue_mask": 4}[wl]
     # units per e2e call: a slide region feeds thousands of tiles per run(); a few engine batches are enough for the engine's host / device
     # pipelining to reach steady state while the default bench still finishes in seconds
-    Be = args.e2e_batch or {"macenko_hovernet": 64, "macenko": 1024, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
+    Be = args.e2e_batch or {"macenko_hovernet": 256, "macenko": 4096, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
     size = {"resnet18": 224, "fcn_tissue_mask": 1024}.get(wl, PATCH)
     uniq = torch.from_numpy(_tiles(min(128, max(B, 16)) if size != 1024 else 8, seed=rank, size=size)).to(dev)
     x = uniq.repeat((B + len(uniq) - 1) // len(uniq), 1, 1, 1)[:B].contiguous()
@@ -797,6 +800,7 @@ def run_wsi(args, rank, world, local_rank, dev):
             "ms_per_step": float(t.item()) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16x3 (split-fp16 operands, fp32 accumulate)", "data": "synthetic", "config": common_config("wsi"),
             "detail": {"slide_shape": list(slide.shape), "patches": n, "batch": B, "instances": int(len(out.get("box", []))),
+                       "rank0_split_s": getattr(eng, "wsi_timings", None),
                        "timed": "host slide -> merged instance table + int32 WSI instance map (wall clock incl. H2D, stitching, tile post-processing, gather, merge)"},
             "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": int(slide.nbytes), "d2h_bytes_per_step": int(getattr(eng, "d2h_bytes", 0)),
                     "api": "NucleusInstanceSegmentor.run(slide, patch_mode=False, return_predictions=True), preproc_func = VahadaneNormalizer.transform"},

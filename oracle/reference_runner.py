@@ -76,9 +76,58 @@ def unet(sd):
 
 
 # ---- process-pool workers (fork: the fitted normaliser / model object is inherited through _STATE) ----
+def _worker_init() -> None:
+    """One BLAS / OpenCV / torch thread per worker process: the pool already uses every core, and 128 processes x 128 BLAS threads
+    would otherwise make the reference look ~30x slower than it is (measured on the GPU box in r2h: 0.7 s instead of 20 ms per tile)."""
+    try:
+        import threadpoolctl
+
+        _STATE["tp_limit"] = threadpoolctl.threadpool_limits(1)
+    except Exception:  # noqa: BLE001, S110
+        pass
+    try:
+        import cv2
+
+        cv2.setNumThreads(1)
+    except Exception:  # noqa: BLE001, S110
+        pass
+    try:
+        import torch
+
+        torch.set_num_threads(1)
+    except Exception:  # noqa: BLE001, S110
+        pass
+
+
 def _stain_worker(chunk: np.ndarray) -> np.ndarray:
     norm = _STATE["norm"]
     return np.stack([norm.transform(t.copy()) for t in chunk])
+
+
+def _forward_init(kind: str, threads: int) -> None:
+    """Forward worker (SPAWNED, not forked: a forked child of a process that has already run torch / CUDA work can hang in OpenMP):
+    builds its own copy of the reference module with the seeded + calibrated test weights."""
+    import torch
+
+    from tests import cnn_common as cc
+
+    torch.set_num_threads(threads)
+    torch.set_grad_enabled(False)
+    if kind == "hovernet":
+        net, cls = hovernet(cc.hovernet_test_weights("fast", 6))
+    elif kind == "resnet18":
+        net, cls = resnet18(cc.resnet18_test_weights(9))
+    else:
+        net, cls = unet(cc.unet_test_weights())
+    _STATE["forward_model"] = (cls, net)
+
+
+def _forward_worker(batch: np.ndarray):
+    """`<Model>.infer_batch(model, batch, device="cpu")` (the reference's own static method) on one batch."""
+    import torch
+
+    cls, net = _STATE["forward_model"]
+    return cls.infer_batch(net, torch.from_numpy(batch), device="cpu")
 
 
 def _postproc_worker(args):
@@ -103,15 +152,39 @@ class CpuPipeline:
         self.pool = None
         self._ctx = mp.get_context("fork")
 
-    def start_pool(self):
-        """Fork the workers (call after every object they need has been put into _STATE, before torch spins up its thread pool)."""
+    def start_pool(self, forward_model=None, cores: int | None = None, threads_per_forward: int = 16, kind: str = "hovernet"):
+        """Fork the stain / post-processing workers (numpy / OpenCV only) and, with `forward_model` = (model class, module), SPAWN
+        cores // threads_per_forward forward workers with `threads_per_forward` torch threads each, so that the CPU arm's network
+        forward uses every core too (oneDNN convolutions stop scaling at ~16 threads on these hosts: r2d measured 16 as the best
+        single-process setting on the 128-thread GPU box).  With fewer than 2 x threads_per_forward cores the forward runs in this
+        process on all cores."""
         if self.procs > 1 and self.pool is None:
-            self.pool = self._ctx.Pool(self.procs)
+            self.pool = self._ctx.Pool(self.procs, initializer=_worker_init)
+        self.fwd_pool, self.fwd_workers, self.fwd_threads = None, 1, cores or os.cpu_count() or 1
+        if forward_model is not None:
+            import multiprocessing as mp
+
+            _STATE["forward_model"] = forward_model
+            cores = cores or os.cpu_count() or 1
+            workers = max(1, cores // threads_per_forward)
+            if workers > 1:
+                self.fwd_pool = mp.get_context("spawn").Pool(workers, initializer=_forward_init, initargs=(kind, threads_per_forward))
+                self.fwd_workers, self.fwd_threads = workers, threads_per_forward
+
+    def forward(self, batches: list) -> list:
+        """`infer_batch` over a list of numpy batches: on the forward workers when there are several, else in this process."""
+        if self.fwd_pool is not None and len(batches) > 1:
+            return self.fwd_pool.map_async(_forward_worker, batches).get(timeout=900)
+        import torch
+
+        torch.set_num_threads(self.fwd_threads)
+        return [_forward_worker(b) for b in batches]
 
     def close(self):
-        if self.pool is not None:
-            self.pool.terminate()
-            self.pool = None
+        for pool in (self.pool, getattr(self, "fwd_pool", None)):
+            if pool is not None:
+                pool.terminate()
+        self.pool = self.fwd_pool = None
 
     def _map(self, fn, chunks):
         chunks = [c for c in chunks if len(c)]

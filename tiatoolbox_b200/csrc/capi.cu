@@ -46,6 +46,7 @@ void tiab_destroy(tiab_handle_t h) {
   for (void* p : pin)
     if (p) cudaFreeHost(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
 }
 

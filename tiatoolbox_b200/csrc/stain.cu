@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tiab200.h"
@@ -1555,6 +1556,26 @@ int tiab_stain_fit_host(tiab_handle_t h, const tiab_stain_params_t* p, const uin
                         h->own_stream);
 }
 
+// memcpy split over a few host threads: one core moves ~10 GB/s, which is less than the PCIe link of a B200 host (the r1 host path —
+// one memcpy into a pinned buffer, one blocking copy, one memcpy out — ran at 5 GB/s end to end)
+static void parallel_memcpy(void* dst, const void* src, size_t n, int threads) {
+  if (threads <= 1 || n < ((size_t)8 << 20)) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = ((n / threads) + 4095) & ~(size_t)4095;
+  for (int t = 1; t < threads; ++t) {
+    const size_t o = std::min(n, per * t), e = std::min(n, per * (t + 1));
+    if (e > o) pool.emplace_back([=] { memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, e - o); });
+  }
+  memcpy(dst, src, std::min(n, per));
+  for (std::thread& th : pool) th.join();
+}
+
+// Host-buffer entry point (what a per-patch `preproc_func` user or the CLI gets, tools/stainnorm.py:89-113): the batch streams through
+// THREE pinned / device slot pairs in chunks — while chunk c runs on the GPU, chunk c + 1 is staged and copied up and chunk c - 1 is
+// copied down and handed back — so the call is bounded by the slower of the host memcpys and one PCIe direction, not by their sum.
 int tiab_stain_transform_host(tiab_handle_t h, const tiab_stain_params_t* p, const uint8_t* in_host, uint8_t* out_host,
                               int N, int H, int W, const double M_target[6], const double maxC_target[2],
                               double* M_src_host, double* maxC_src_host, int* status_host) {
@@ -1564,24 +1585,75 @@ int tiab_stain_transform_host(tiab_handle_t h, const tiab_stain_params_t* p, con
     return TIAB_E_INVALID;
   }
   TIAB_ON_DEVICE(h);
-  size_t bytes = (size_t)N * H * W * 3;
-  int rc = ensure_staging(h, bytes);
+  constexpr int SLOTS = 3;
+  const size_t tile = (size_t)H * W * 3;
+  // chunk: ~32 MB of tiles, at least one SM-count worth for the fused kernel when the batch allows it
+  int chunk = (int)std::max<size_t>(1, ((size_t)32 << 20) / tile);
+  chunk = std::min(chunk, N);
+  if (N > SLOTS && chunk * 2 > N) chunk = (N + 1) / 2;
+  const size_t chunk_bytes = (size_t)chunk * tile;
+  int rc = ensure_staging(h, chunk_bytes * SLOTS);
   if (rc) return rc;
   if ((rc = ensure_small(h, N))) return rc;
+  if (!h->copy_stream) TIAB_CUDA_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   cudaStream_t s = h->own_stream;
-  memcpy(h->pin_in, in_host, bytes);
-  TIAB_CUDA_OK(h, cudaMemcpyAsync(h->dev_in, h->pin_in, bytes, cudaMemcpyHostToDevice, s));
   double* dM = (double*)h->dev_small;
   double* dC = dM + (size_t)N * 6;
   int* dS = (int*)(dC + (size_t)N * 2);
-  rc = tiab_stain_transform_batch(h, p, (const uint8_t*)h->dev_in, (uint8_t*)h->dev_out, N, H, W, M_target,
-                                  maxC_target, dM, dC, dS, nullptr, s);
-  if (rc) return rc;
-  TIAB_CUDA_OK(h, cudaMemcpyAsync(h->pin_out, h->dev_out, bytes, cudaMemcpyDeviceToHost, s));
+  const int nchunks = (N + chunk - 1) / chunk;
+  const int threads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 4));
+  cudaEvent_t up[SLOTS], done[SLOTS], down[SLOTS];
+  for (int i = 0; i < SLOTS; ++i) {
+    TIAB_CUDA_OK(h, cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
+    TIAB_CUDA_OK(h, cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    TIAB_CUDA_OK(h, cudaEventCreateWithFlags(&down[i], cudaEventDisableTiming));
+  }
+  auto cleanup = [&]() {
+    for (int i = 0; i < SLOTS; ++i) cudaEventDestroy(up[i]), cudaEventDestroy(done[i]), cudaEventDestroy(down[i]);
+  };
+  auto slot_ptr = [&](void* base, int slot) { return (uint8_t*)base + (size_t)slot * chunk_bytes; };
+  auto finish = [&](int c) -> int {   // chunk c's result has arrived in its pinned slot: hand it back
+    const int slot = c % SLOTS, n0 = c * chunk, n = std::min(chunk, N - n0);
+    if (cudaEventSynchronize(down[slot]) != cudaSuccess) return TIAB_E_CUDA;
+    parallel_memcpy(out_host + (size_t)n0 * tile, slot_ptr(h->pin_out, slot), (size_t)n * tile, threads);
+    return TIAB_OK;
+  };
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = c % SLOTS, n0 = c * chunk, n = std::min(chunk, N - n0);
+    if (c >= SLOTS && (rc = finish(c - SLOTS))) {      // frees this slot's pinned output (and, by stream order, its device buffers)
+      cleanup();
+      h->err = "tiab_stain_transform_host: device -> host copy failed";
+      return rc;
+    }
+    parallel_memcpy(slot_ptr(h->pin_in, slot), in_host + (size_t)n0 * tile, (size_t)n * tile, threads);
+    // upload on the copy stream (overlaps the previous chunk's kernel and download), compute + download on the handle's stream
+    if (c >= SLOTS) cudaStreamWaitEvent(h->copy_stream, done[slot], 0);   // the kernel that read this device slot has finished
+    cudaMemcpyAsync(slot_ptr(h->dev_in, slot), slot_ptr(h->pin_in, slot), (size_t)n * tile, cudaMemcpyHostToDevice, h->copy_stream);
+    cudaEventRecord(up[slot], h->copy_stream);
+    cudaStreamWaitEvent(s, up[slot], 0);
+    rc = tiab_stain_transform_batch(h, p, slot_ptr(h->dev_in, slot), slot_ptr(h->dev_out, slot), n, H, W, M_target, maxC_target,
+                                    dM + (size_t)n0 * 6, dC + (size_t)n0 * 2, dS + n0, nullptr, s);
+    if (rc) {
+      cudaStreamSynchronize(s), cudaStreamSynchronize(h->copy_stream);
+      cleanup();
+      return rc;
+    }
+    cudaEventRecord(done[slot], s);
+    cudaMemcpyAsync(slot_ptr(h->pin_out, slot), slot_ptr(h->dev_out, slot), (size_t)n * tile, cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(down[slot], s);
+  }
+  for (int c = std::max(0, nchunks - SLOTS); c < nchunks; ++c)
+    if ((rc = finish(c))) {
+      cleanup();
+      h->err = "tiab_stain_transform_host: device -> host copy failed";
+      return rc;
+    }
   size_t small = (size_t)N * (8 * sizeof(double) + sizeof(int));
-  TIAB_CUDA_OK(h, cudaMemcpyAsync(h->pin_small, h->dev_small, small, cudaMemcpyDeviceToHost, s));
-  TIAB_CUDA_OK(h, cudaStreamSynchronize(s));
-  memcpy(out_host, h->pin_out, bytes);
+  cudaError_t ce = cudaMemcpyAsync(h->pin_small, h->dev_small, small, cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  cleanup();
+  TIAB_CUDA_OK(h, ce);
+  TIAB_CUDA_OK(h, cudaGetLastError());
   const double* hp = (const double*)h->pin_small;
   if (M_src_host) memcpy(M_src_host, hp, (size_t)N * 6 * sizeof(double));
   if (maxC_src_host) memcpy(maxC_src_host, hp + (size_t)N * 6, (size_t)N * 2 * sizeof(double));

@@ -338,15 +338,30 @@ class WsiTileModeMixin:
         plan = WsiTilePlan((image.shape[1], image.shape[0]), io, rank, world)
         self.model._plan_batch = self.batch_size  # noqa: SLF001
         self._stain_failed = None
+        import time
+
+        def _sync():
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            return time.perf_counter()
+
         canvases = []
+        t0 = _sync()
         if len(plan.my_patches):
             band = self._wsi_upload(image, plan)
             canvases = self._wsi_infer(band, plan)
             del band
         self._report_stain_failures()
+        t1 = _sync()
         results = self._wsi_postproc_tiles(canvases, plan, keep_maps=return_predictions)
+        t2 = _sync()
         merged = self._wsi_gather(results, plan, keep_maps=return_predictions)
+        t3 = _sync()
         out = self._wsi_replay(merged, plan, return_predictions=return_predictions)
+        #: wall-clock split of the last WSI run on this rank (seconds): upload + inference + stitching | tile post-processing |
+        #: result exchange | ordered merge replay
+        self.wsi_timings = {"infer_s": t1 - t0, "tile_postproc_s": t2 - t1, "gather_s": t3 - t2, "merge_replay_s": time.perf_counter() - t3,
+                            "patches_inferred": int(len(plan.my_patches)), "tiles_owned": int(len(plan.my_tasks))}
         out["coordinates"] = plan.in_boxes
         if return_probabilities:
             if world > 1:
