@@ -139,3 +139,26 @@ def test_against_the_running_reference_functions():
     pi, po = PatchExtractor.get_coordinates(image_shape=(3333, 1111), patch_input_shape=(270, 270), patch_output_shape=(80, 80),
                                             stride_shape=(80, 80))
     assert np.array_equal(ins, pi) and np.array_equal(outs, po)
+
+
+def test_column_store_equals_record_store_on_random_tile_sequences():
+    """`WsiColumnStore` (vectorised per tile, what WSI mode uses) == `WsiInstanceStore` (per record, pinned to the unmodified reference
+    functions above): same survivors, same order, same values and dtypes, with and without a final offset."""
+    for seed in range(6):
+        for margin in (128, 0, 37):
+            tiles = wc.scenario(seed, margin=margin, density=25)
+            want_store = _product_replay(tiles, margin)
+            cs = wm.WsiColumnStore()
+            for bounds, flag, mode, recs in copy.deepcopy(tiles):
+                cs.merge_tile(wm.columns_from_records(recs), tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=margin)
+            assert len(cs) == len(want_store)
+            for off in ((0, 0), (5, -9)):
+                got, want = cs.to_info_dict(offset=off), want_store.to_info_dict(offset=off)
+                assert set(got) == set(want) or (not got and not want)
+                for key in want:
+                    assert len(got[key]) == len(want[key])
+                    for a, b in zip(got[key], want[key]):
+                        assert np.array_equal(np.asarray(a), np.asarray(b)), (seed, margin, key)
+                        if key in ("box", "centroid", "contours"):
+                            assert np.asarray(a).dtype == np.asarray(b).dtype, (key, np.asarray(a).dtype, np.asarray(b).dtype)
+    assert wm.WsiColumnStore().to_info_dict() == {}

@@ -181,7 +181,7 @@ class WsiTileModeMixin:
         return canvases or []
 
     def _wsi_postproc_tiles(self, canvases: list[torch.Tensor], plan: WsiTilePlan, *, keep_maps: bool):
-        """This rank's tiles -> [(task index, tile instance dict, tile inst map (device int32) | None, extra)] in task order; `extra` is
+        """This rank's tiles -> [(task index, tile instance COLUMNS (wsi_merge.columns_from_records layout), tile inst map (device int32) | None, extra)] in task order; `extra` is
         None for HoVer-Net and (layer region dict, layer map uint8 | None) for the two-task HoVerNetPlus (hovernetplus.py:267-410 per tile)."""
         results = []
         if not canvases:
@@ -224,12 +224,12 @@ class WsiTileModeMixin:
             tab = {k: v.cpu().numpy() for k, v in table.items()}
             layers = stacks[3][:, :th, :tw, 0].cpu().numpy() if two_task else None
             for j, i in enumerate(group):
-                info = pp.instance_info(inst_h[j], {k: v[j] for k, v in tab.items()}, with_contours=True)
+                cols = pp.instance_columns(inst_h[j], {k: v[j] for k, v in tab.items()})     # columnar: no Python work per nucleus
                 extra = None
                 if two_task:   # the layer task of this tile: whole-tile morphology + region contours on the host (OpenCV, like the reference)
                     layer = self.model._proc_ls(layers[j])  # noqa: SLF001
                     extra = (self.model._get_layer_info(layer), layer if keep_maps else None)  # noqa: SLF001
-                results.append((i, {k + 1: rec for k, rec in enumerate(info.values())}, inst[j] if keep_maps else None, extra))
+                results.append((i, cols, inst[j] if keep_maps else None, extra))
             group.clear()
 
         shape = None
@@ -237,7 +237,7 @@ class WsiTileModeMixin:
             x0, y0, x1, y1 = clipped(i)
             s = (y1 - y0, x1 - x0)
             if s[0] <= 0 or s[1] <= 0:
-                results.append((i, {}, None, ({}, None) if two_task else None))
+                results.append((i, wm.columns_from_records([]), None, ({}, None) if two_task else None))
                 continue
             if s != shape or len(group) >= self.tile_batch:
                 flush()
@@ -287,14 +287,14 @@ class WsiTileModeMixin:
         """`_process_tile_mode`'s merge loop (:1230-1279) over all tiles in task order -> the output entries of the task (one task), or
         {task name: entries} for the two-task model: its layer regions go through the same margin logic keyed on their boxes, and its
         semantic tile maps are pasted in order (later tiles overwrite, `_update_tile_based_predictions_array` :3160-3212)."""
-        store = wm.WsiInstanceStore()
+        store = wm.WsiColumnStore()
         two_task = any(v[2] is not None for v in merged.values())
         layer_store = wm.WsiInstanceStore() if two_task else None
         wsi_pred = np.zeros((plan.H, plan.W), dtype=np.int32) if return_predictions else None
         wsi_layer = np.zeros((plan.H, plan.W), dtype=np.uint8) if (return_predictions and two_task) else None
         max_inst = None
         for i, (bounds, flag, mode) in enumerate(plan.tasks):
-            inst_dict, inst_map, extra = merged.get(i, ({}, None, None))
+            inst_dict, inst_map, extra = merged.get(i, (wm.columns_from_records([]), None, None))
             if wsi_pred is not None and inst_map is not None:
                 max_inst = wm.update_tile_based_predictions_array(inst_map, wsi_pred, bounds, (0, 0), max_inst)
             if extra is not None and wsi_layer is not None and extra[1] is not None:
@@ -304,8 +304,7 @@ class WsiTileModeMixin:
                 if extra is not None:
                     layer_store.merge_tile(extra[0], tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin)
             else:   # `_process_full_wsi` :999-1076: one postproc call over the whole map, nothing to merge
-                for rec in inst_dict.values():
-                    store._append(rec)  # noqa: SLF001
+                store.append_all(inst_dict)
                 for rec in (extra[0].values() if extra is not None else ()):
                     layer_store._append(rec)  # noqa: SLF001
         out = dict(store.to_info_dict())

@@ -197,6 +197,118 @@ class WsiInstanceStore:
         return out
 
 
+def columns_from_records(recs) -> dict:
+    """A tile's instances as COLUMNS (what the device table already is): box (n, 4) int64, centroid (n, 2) float64, prob (n,) float64,
+    type (n,) int64 with -1 = None, contours as one (V, 2) int32 vertex array + (n + 1,) offsets.  `recs`: iterable of record dicts."""
+    recs = list(recs)
+    n = len(recs)
+    cont = [np.asarray(r["contours"], dtype=np.int32).reshape(-1, 2) for r in recs]
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        off[1:] = np.cumsum([len(c) for c in cont])
+    return {
+        "box": np.array([r["box"] for r in recs], dtype=np.int64).reshape(n, 4),
+        "centroid": np.array([r["centroid"] for r in recs], dtype=np.float64).reshape(n, 2),
+        "prob": np.array([np.nan if r.get("prob") is None else r["prob"] for r in recs], dtype=np.float64),
+        "type": np.array([-1 if r.get("type") is None else r["type"] for r in recs], dtype=np.int64),
+        "cont_xy": np.concatenate(cont) if n else np.zeros((0, 2), np.int32),
+        "cont_off": off,
+    }
+
+
+class WsiColumnStore:
+    """`WsiInstanceStore` for columnar tiles: the same order-dependent merge (`_compute_info_dict_for_merge` :3269-3296 + the update / pop
+    of `_process_tile_mode` :1230-1279), but a tile arrives as arrays (`columns_from_records` layout, tile space) and every step — the
+    margin test, the shift to WSI space, the cross tile's eviction — is one vectorised operation per tile instead of Python work per
+    nucleus.  At 20 000 patches a slide has ~2.5 M tile-level records (680 k survive): the per-record version spent longer on them than the
+    GPU on the whole slide (r2h).  Equality with `WsiInstanceStore` on random tile sequences: tests/test_oracle_wsi.py."""
+
+    def __init__(self) -> None:
+        self._chunks: list[dict] = []          # kept instances per tile, already in WSI space
+        self._starts: list[int] = []
+        self._boxes = np.empty((4096, 4), dtype=np.int64)
+        self._alive = np.zeros(4096, dtype=bool)
+        self.n = 0
+
+    def __len__(self) -> int:
+        return int(self._alive[: self.n].sum())
+
+    def merge_tile(self, cols: dict, *, tile_bounds, tile_flag, tile_mode: int, margin) -> tuple[int, int]:
+        n = len(cols["box"])
+        if n == 0:    # :2903-2904 — an empty cross tile evicts nothing either
+            return 0, 0
+        tile_bounds = np.asarray(tile_bounds)
+        tile_tl = tile_bounds[:2].astype(np.int64)
+        tile_shape = tile_bounds[2:] - tile_bounds[:2]
+        drop = select_tile_removals(cols["box"], tile_shape, tile_flag, tile_mode, margin)
+        evicted = 0
+        if tile_mode == 3:  # noqa: PLR2004
+            hit = np.zeros(self.n, dtype=bool)
+            for line in margin_lines(margin, tile_shape, tile_tl):
+                hit |= boxes_intersect(self._boxes[: self.n], line)
+            hit &= self._alive[: self.n]
+            evicted = int(hit.sum())
+            self._alive[: self.n][hit] = False
+        keep = np.nonzero(~drop)[0]
+        k = len(keep)
+        if k == 0:
+            return 0, evicted
+        off = cols["cont_off"]
+        lens = (off[1:] - off[:-1])[keep]
+        new_off = np.zeros(k + 1, dtype=np.int64)
+        new_off[1:] = np.cumsum(lens)
+        if k == n:
+            xy = cols["cont_xy"]
+        else:     # vertices of the kept instances, in order
+            idx = np.repeat(off[:-1][keep] - new_off[:-1], lens) + np.arange(int(new_off[-1]), dtype=np.int64)
+            xy = cols["cont_xy"][idx]
+        shift4 = np.concatenate([tile_tl, tile_tl])
+        chunk = {"box": cols["box"][keep] + shift4, "centroid": cols["centroid"][keep] + tile_tl.astype(np.float64),
+                 "prob": cols["prob"][keep], "type": cols["type"][keep],
+                 "cont_xy": (xy + tile_tl.astype(xy.dtype)).astype(xy.dtype), "cont_off": new_off}
+        while self.n + k > len(self._boxes):
+            self._boxes = np.concatenate([self._boxes, np.empty_like(self._boxes)])
+            self._alive = np.concatenate([self._alive, np.zeros_like(self._alive)])
+        self._boxes[self.n: self.n + k] = chunk["box"]
+        self._alive[self.n: self.n + k] = True
+        self._chunks.append(chunk)
+        self._starts.append(self.n)
+        self.n += k
+        return k, evicted
+
+    def append_all(self, cols: dict) -> None:
+        """`_process_full_wsi` (:999-1076): one post-processing call over the whole map, nothing to merge or shift."""
+        self.merge_tile(cols, tile_bounds=np.array([0, 0, 1 << 40, 1 << 40]), tile_flag=[0, 0, 0, 0], tile_mode=0, margin=0)
+
+    def to_info_dict(self, offset=(0, 0)) -> dict:
+        """{key: object array over the surviving instances, insertion order} like `WsiInstanceStore.to_info_dict`."""
+        alive = self._alive[: self.n]
+        total = int(alive.sum())
+        if total == 0:
+            return {}
+        dx, dy = (int(v) for v in offset)
+        out = {key: np.empty(total, dtype=object) for key in INFO_KEYS}
+        at = 0
+        for start, ch in zip(self._starts, self._chunks):
+            k = len(ch["box"])
+            sel = np.nonzero(alive[start: start + k])[0]
+            if not len(sel):
+                continue
+            box = ch["box"] + np.array([dx, dy, dx, dy])
+            cen = ch["centroid"] + np.array([dx, dy], dtype=np.float64)
+            xy = (ch["cont_xy"] + np.array([dx, dy], dtype=ch["cont_xy"].dtype)).astype(ch["cont_xy"].dtype)
+            off = ch["cont_off"]
+            probs, types = ch["prob"].tolist(), ch["type"].tolist()
+            for j in sel.tolist():
+                out["box"][at] = box[j]
+                out["centroid"][at] = cen[j]
+                out["contours"][at] = xy[off[j]: off[j + 1]]
+                out["prob"][at] = None if types[j] < 0 else probs[j]
+                out["type"][at] = None if types[j] < 0 else types[j]
+                at += 1
+        return out
+
+
 def tile_instance_dict(info_dict: dict) -> dict:
     """`_get_inst_info_dicts` (:3061-3083) for one task: {i + 1: {key: values[i]}} from a tile's packed `info_dict` columns."""
     keys = list(info_dict.keys())

@@ -136,3 +136,31 @@ def instance_info(inst_map: np.ndarray, table_row: dict, offset=(0, 0), with_con
             rec["prob"] = probs[k]
         info[inst_id] = rec
     return info
+
+
+def instance_columns(inst_map: np.ndarray, table_row: dict, offset=(0, 0)) -> dict:
+    """`instance_info` as COLUMNS (engine/wsi_merge.columns_from_records layout): the instances of ONE image straight from the device
+    table — no Python work per nucleus.  Needs the device contours (`trace_contours`); an image whose vertex buffer overflowed, or a
+    table without contours, goes through `instance_info` (host cv2) and is converted."""
+    from tiatoolbox_b200.models.engine.wsi_merge import columns_from_records
+
+    count = int(table_row["count"])
+    if "cont_xy" not in table_row or int(table_row["cont_total"]) > len(table_row["cont_xy"]):
+        return columns_from_records(instance_info(inst_map, table_row, offset).values())
+    off2 = np.asarray(offset, dtype=np.int64)
+    lens = table_row["cont_len"][:count].astype(np.int64)
+    keep = np.nonzero(lens >= 3)[0]          # hovernet.py:696-701: a 1- or 2-point contour drops the instance  # noqa: PLR2004
+    k = len(keep)
+    new_off = np.zeros(k + 1, dtype=np.int64)
+    new_off[1:] = np.cumsum(lens[keep])
+    src = table_row["cont_off"][:count].astype(np.int64)[keep]
+    idx = np.repeat(src - new_off[:-1], lens[keep]) + np.arange(int(new_off[-1]), dtype=np.int64)
+    xy = (table_row["cont_xy"][idx] + off2.astype(np.int32)).astype(np.int32) if k else np.zeros((0, 2), np.int32)
+    types = table_row["type"][:count][keep].astype(np.int64)
+    return {
+        "box": table_row["box"][:count][keep].astype(np.int64) + np.concatenate([off2, off2]),
+        "centroid": table_row["centroid"][:count][keep] + off2.astype(np.float64),
+        "prob": table_row["prob"][:count][keep].astype(np.float64),
+        "type": np.where(types >= 0, types, -1),
+        "cont_xy": xy, "cont_off": new_off,
+    }
