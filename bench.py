@@ -246,7 +246,8 @@ def reference_pipeline(workload: str, sample: int, cores: int):
             t0 = time.perf_counter()
             normed = pipe.stain(tiles)
             t1 = time.perf_counter()
-            pipe.forward([normed[i:i + 4] for i in range(0, sample, 4)])   # HoVerNet.infer_batch(model, batch, device="cpu") (hovernet.py:862-910)
+            fb = 2 if pipe.fwd_workers > 1 else 4
+            pipe.forward([normed[i:i + fb] for i in range(0, sample, fb)])   # HoVerNet.infer_batch(model, batch, device="cpu") (hovernet.py:862-910)
             t2 = time.perf_counter()
             res = pipe.postproc(heads)                      # HoVerNet.postproc per patch (hovernet.py:751-859) on the synthetic head maps
             t3 = time.perf_counter()
@@ -254,7 +255,7 @@ def reference_pipeline(workload: str, sample: int, cores: int):
             return {"stain_s": t1 - t0, "forward_s": t2 - t1, "postproc_s": t3 - t2}
 
         desc = (f"{sample} seeded tiles per step: reference {method.capitalize()}Normalizer.transform over {procs} single-threaded processes; "
-                f"reference HoVerNet.infer_batch(device='cpu') in batches of 4 over {pipe.fwd_workers} worker process(es) x {pipe.fwd_threads} torch "
+                f"reference HoVerNet.infer_batch(device='cpu') in batches of {2 if pipe.fwd_workers > 1 else 4} over {pipe.fwd_workers} worker process(es) x {pipe.fwd_threads} torch "
                 f"threads; reference HoVerNet.postproc over {procs} processes (scikit-image's remove_small_objects / watershed are absent "
                 "from the image: compiled-C restatements)")
         return step, desc, pipe
@@ -305,7 +306,8 @@ def run_reference(args, rank: int):
     cores = os.cpu_count() or 1
     wl = args.workload
     nfw = max(1, cores // 16)                 # forward workers of the CPU arm (oracle/reference_runner.CpuPipeline.start_pool)
-    sample = {"macenko_hovernet": 4 * nfw, "wsi": 4 * nfw, "macenko": max(64, 8 * cores), "resnet18": 64 * nfw, "fcn_tissue_mask": max(2, nfw)}[wl]
+    # a step = a bounded sample: two tiles per forward worker keep every core busy and (warmup + steps) x ~12 s within a few minutes
+    sample = {"macenko_hovernet": max(4, 2 * nfw), "wsi": max(4, 2 * nfw), "macenko": max(64, 8 * cores), "resnet18": 64 * nfw, "fcn_tissue_mask": max(2, nfw)}[wl]
     unit = UNITS.get(wl, "patches/s")
     try:
         step, desc, pipe = reference_pipeline(wl, sample, cores)
@@ -464,7 +466,7 @@ def cpu_baseline_leg(workload: str) -> dict:
     """Bounded sample of the reference's CPU path on this box's host cores (rank 0, N = 1 only)."""
     cores = os.cpu_count() or 1
     nfw = max(1, cores // 16)
-    sample = {"macenko_hovernet": 4 * nfw, "wsi": 4 * nfw, "macenko": max(64, 4 * cores), "resnet18": 64 * nfw, "fcn_tissue_mask": max(2, nfw)}[workload]
+    sample = {"macenko_hovernet": max(4, 2 * nfw), "wsi": max(4, 2 * nfw), "macenko": max(64, 4 * cores), "resnet18": 64 * nfw, "fcn_tissue_mask": max(2, nfw)}[workload]
     try:
         step, desc, pipe = reference_pipeline(workload, sample, cores)
         step()
@@ -527,10 +529,10 @@ def main():
         run_wsi(args, rank, world, local_rank, dev)
         return
 
-    B = args.batch or {"macenko_hovernet": 16, "macenko": 8192, "resnet18": 1024, "fcn_tissue_mask": 4}[wl]
+    B = args.batch or {"macenko_hovernet": 64, "macenko": 8192, "resnet18": 1024, "fcn_tissue_mask": 4}[wl]
     # units per e2e call: a slide region feeds thousands of tiles per run(); a few engine batches are enough for the engine's host / device
     # pipelining to reach steady state while the default bench still finishes in seconds
-    Be = args.e2e_batch or {"macenko_hovernet": 256, "macenko": 4096, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
+    Be = args.e2e_batch or {"macenko_hovernet": 512, "macenko": 4096, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
     size = {"resnet18": 224, "fcn_tissue_mask": 1024}.get(wl, PATCH)
     uniq = torch.from_numpy(_tiles(min(128, max(B, 16)) if size != 1024 else 8, seed=rank, size=size)).to(dev)
     x = uniq.repeat((B + len(uniq) - 1) // len(uniq), 1, 1, 1)[:B].contiguous()

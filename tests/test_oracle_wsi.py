@@ -162,3 +162,36 @@ def test_column_store_equals_record_store_on_random_tile_sequences():
                         if key in ("box", "centroid", "contours"):
                             assert np.asarray(a).dtype == np.asarray(b).dtype, (key, np.asarray(a).dtype, np.asarray(b).dtype)
     assert wm.WsiColumnStore().to_info_dict() == {}
+
+
+def test_tensor_paste_equals_the_numpy_recurrence_including_int32_wraparound():
+    """`paste_instance_tile_tensor` (torch, branch-free, what WSI mode runs on the device) == `update_tile_based_predictions_array` (numpy,
+    pinned to the reference function above) over a random tile sequence — also when the running `max_inst_value` passes 2^31 (the
+    reference's recurrence roughly doubles it per tile, so real slides wrap after ~31 tiles)."""
+    import warnings
+
+    import torch
+
+    rng = np.random.default_rng(5)
+    for start in (None, 2**31 - 400):
+        H, W = 300, 340
+        want = np.zeros((H, W), np.int32)
+        got = torch.zeros((H, W), dtype=torch.int32)
+        m_np = None if start is None else np.int32(start)
+        m_t = torch.tensor(0 if start is None else start, dtype=torch.int32)
+        lut = torch.zeros(120 * 120 + 2, dtype=torch.int32)
+        for _ in range(40):
+            th, tw = int(rng.integers(20, 120)), int(rng.integers(20, 120))
+            x0, y0 = int(rng.integers(0, W - 10)), int(rng.integers(0, H - 10))
+            tile = np.zeros((th, tw), np.int32)
+            for lab in rng.permutation(np.arange(1, 9))[: int(rng.integers(0, 8))]:
+                yy, xx = int(rng.integers(0, th - 5)), int(rng.integers(0, tw - 5))
+                tile[yy: yy + int(rng.integers(3, 30)), xx: xx + int(rng.integers(3, 30))] = lab
+            bounds = (x0, y0, x0 + tw, y0 + th)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                m_np = wm.update_tile_based_predictions_array(tile, want, bounds, (0, 0), m_np)
+            m_t = wm.paste_instance_tile_tensor(torch.from_numpy(tile), got, bounds, m_t, lut)
+            assert int(lut.abs().sum()) == 0
+            assert np.array_equal(got.numpy(), want)
+            assert int(m_t) == int(np.int32(m_np))

@@ -254,7 +254,7 @@ class WsiTileModeMixin:
         merged = {}
         if dist is None:
             for i, d, m, extra in results:
-                merged[i] = (d, None if m is None else m.cpu().numpy(), extra)
+                merged[i] = (d, m, extra)
             return merged
         gathered = [None] * world
         dist.all_gather_object(gathered, [(i, d, None if m is None else tuple(m.shape), extra) for i, d, m, extra in results])
@@ -270,7 +270,7 @@ class WsiTileModeMixin:
             padded[: mine.numel()] = mine
             out = torch.empty(world * max(cap, 1), dtype=torch.int32, device=self.device)
             dist.all_gather_into_tensor(out, padded)
-            out = out.view(world, -1).cpu().numpy()
+            out = out.view(world, -1)       # stays on the device: the WSI instance map is pasted there (`_wsi_replay`)
             maps_by_rank = [out[r, : int(sizes[r].item())] for r in range(world)]
         for r, part in enumerate(gathered):
             off = 0
@@ -290,13 +290,18 @@ class WsiTileModeMixin:
         store = wm.WsiColumnStore()
         two_task = any(v[2] is not None for v in merged.values())
         layer_store = wm.WsiInstanceStore() if two_task else None
-        wsi_pred = np.zeros((plan.H, plan.W), dtype=np.int32) if return_predictions else None
+        # the WSI instance map is pasted on the device the tile maps live on (torch ops, no sync per tile) and copied back once
+        wsi_pred = torch.zeros((plan.H, plan.W), dtype=torch.int32, device=self.device) if return_predictions else None
         wsi_layer = np.zeros((plan.H, plan.W), dtype=np.uint8) if (return_predictions and two_task) else None
-        max_inst = None
+        max_inst = torch.zeros((), dtype=torch.int32, device=self.device)
+        lut = None
         for i, (bounds, flag, mode) in enumerate(plan.tasks):
             inst_dict, inst_map, extra = merged.get(i, (wm.columns_from_records([]), None, None))
             if wsi_pred is not None and inst_map is not None:
-                max_inst = wm.update_tile_based_predictions_array(inst_map, wsi_pred, bounds, (0, 0), max_inst)
+                inst_map = torch.as_tensor(inst_map).to(self.device)
+                if lut is None or lut.numel() < inst_map.numel() + 2:      # instance ids are bounded by the tile's pixel count
+                    lut = torch.zeros(inst_map.numel() + 2, dtype=torch.int32, device=self.device)
+                max_inst = wm.paste_instance_tile_tensor(inst_map, wsi_pred, bounds, max_inst, lut)
             if extra is not None and wsi_layer is not None and extra[1] is not None:
                 wm.update_tile_based_predictions_array(extra[1], wsi_layer, bounds, (0, 0), seg_type="semantic")
             if plan.tile_mode:
@@ -309,7 +314,7 @@ class WsiTileModeMixin:
                     layer_store._append(rec)  # noqa: SLF001
         out = dict(store.to_info_dict())
         if wsi_pred is not None:
-            out["predictions"] = wsi_pred
+            out["predictions"] = wsi_pred.cpu().numpy()
         if not two_task:
             return out
         layer_out = dict(layer_store.to_info_dict())

@@ -342,3 +342,31 @@ def update_tile_based_predictions_array(new_pred: np.ndarray, wsi_pred: np.ndarr
         max_inst_value = (np.max(new) + max_inst_value) if np.any(keep) else max_inst_value
     wsi_pred[y_start:y_end, x_start:x_end] = new
     return max_inst_value
+
+
+def paste_instance_tile_tensor(new_pred, wsi_pred, bounds, max_inst_value, lut):
+    """`update_tile_based_predictions_array` (instance maps) on torch tensors — the same order-dependent recurrence, branch-free so that
+    it needs no host synchronisation per tile: on the B200 the gathered tile maps stay on the device, the WSI map is pasted there
+    (2 209 tiles of a 20 000-patch slide: ~1 s instead of ~11 s of numpy `unique` / `isin` / masked copies on the host, r2j) and comes
+    back once.  int32 arithmetic wraps exactly like the reference's numpy int32 scalars do.
+
+    new_pred (h, w) int32, wsi_pred (H, W) int32 [updated in place], max_inst_value: 0-dim int32 tensor, lut: int32 scratch of at least
+    new_pred.max() + 1 entries (zero on entry, zero on return).  Returns the new max_inst_value tensor."""
+    import torch
+
+    x_start, y_start, x_end, y_end = (int(v) for v in bounds)
+    max_h, max_w = wsi_pred.shape
+    x_end, y_end = min(x_end, max_w), min(y_end, max_h)
+    new = new_pred[0: y_end - y_start, 0: x_end - x_start]
+    prev = wsi_pred[y_start:y_end, x_start:x_end]
+    pos = new > 0
+    overlap = pos & (prev > 0)
+    ids = new.to(torch.int64)
+    # ids of new instances that touch something already pasted: lut[id] = 1 (id 0 never qualifies: overlap implies new > 0)
+    lut.index_put_((torch.where(overlap, ids, torch.zeros_like(ids)).reshape(-1),), overlap.reshape(-1).to(lut.dtype), accumulate=True)
+    keep = pos & (lut[ids] == 0)
+    combined = torch.where(keep, new + max_inst_value, prev)
+    new_max = torch.where(keep.any(), combined.max() + max_inst_value, max_inst_value)
+    lut.index_fill_(0, ids.reshape(-1), 0)
+    wsi_pred[y_start:y_end, x_start:x_end] = combined
+    return new_max
