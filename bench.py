@@ -529,10 +529,10 @@ def main():
         run_wsi(args, rank, world, local_rank, dev)
         return
 
-    B = args.batch or {"macenko_hovernet": 64, "macenko": 8192, "resnet18": 1024, "fcn_tissue_mask": 4}[wl]
+    B = args.batch or {"macenko_hovernet": 16, "macenko": 8192, "resnet18": 1024, "fcn_tissue_mask": 4}[wl]
     # units per e2e call: a slide region feeds thousands of tiles per run(); a few engine batches are enough for the engine's host / device
     # pipelining to reach steady state while the default bench still finishes in seconds
-    Be = args.e2e_batch or {"macenko_hovernet": 512, "macenko": 4096, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
+    Be = args.e2e_batch or {"macenko_hovernet": 256, "macenko": 4096, "resnet18": 4096, "fcn_tissue_mask": 16}[wl]
     size = {"resnet18": 224, "fcn_tissue_mask": 1024}.get(wl, PATCH)
     uniq = torch.from_numpy(_tiles(min(128, max(B, 16)) if size != 1024 else 8, seed=rank, size=size)).to(dev)
     x = uniq.repeat((B + len(uniq) - 1) // len(uniq), 1, 1, 1)[:B].contiguous()

@@ -363,10 +363,12 @@ def paste_instance_tile_tensor(new_pred, wsi_pred, bounds, max_inst_value, lut):
     overlap = pos & (prev > 0)
     ids = new.to(torch.int64)
     # ids of new instances that touch something already pasted: lut[id] = 1 (id 0 never qualifies: overlap implies new > 0)
-    lut.index_put_((torch.where(overlap, ids, torch.zeros_like(ids)).reshape(-1),), overlap.reshape(-1).to(lut.dtype), accumulate=True)
+    # plain scatter (all writes to an index carry the same value: 1 for a touched id, 0 to slot 0 from every other pixel) — an
+    # accumulating index_put would sort a million indices per tile (r2k: 40 ms per tile)
+    lut.scatter_(0, torch.where(overlap, ids, torch.zeros_like(ids)).reshape(-1), overlap.reshape(-1).to(lut.dtype))
     keep = pos & (lut[ids] == 0)
     combined = torch.where(keep, new + max_inst_value, prev)
     new_max = torch.where(keep.any(), combined.max() + max_inst_value, max_inst_value)
-    lut.index_fill_(0, ids.reshape(-1), 0)
+    lut.zero_()
     wsi_pred[y_start:y_end, x_start:x_end] = combined
     return new_max
