@@ -214,7 +214,7 @@ class WsiTileModeMixin:
             if getattr(self, "device_contours", False) and inst.is_cuda:
                 pp.trace_contours(inst.contiguous(), table)     # vertices in tile coordinates, before any sliver crop (pad is background)
             inst = inst[:, :th, :tw]
-            inst_h = inst.cpu().numpy()
+            inst_h = None      # the instance maps only travel when an image needs the host contour fallback (vertex buffer overflow / no device contours)
             # only the rows / vertices that were written travel (the buffers are sized for the worst case: H*W/10 rows, H*W/2 vertices)
             rows_used = max(int(table["count"].max().item()), 1) if table["count"].numel() else 1
             table = {k: (v[:, :rows_used] if v.dim() > 1 and k != "cont_xy" else v) for k, v in table.items()}
@@ -224,7 +224,10 @@ class WsiTileModeMixin:
             tab = {k: v.cpu().numpy() for k, v in table.items()}
             layers = stacks[3][:, :th, :tw, 0].cpu().numpy() if two_task else None
             for j, i in enumerate(group):
-                cols = pp.instance_columns(inst_h[j], {k: v[j] for k, v in tab.items()})     # columnar: no Python work per nucleus
+                row = {k: v[j] for k, v in tab.items()}
+                if "cont_xy" not in row or int(row["cont_total"]) > len(row["cont_xy"]):
+                    inst_h = inst.cpu().numpy() if inst_h is None else inst_h
+                cols = pp.instance_columns(None if inst_h is None else inst_h[j], row)     # columnar: no Python work per nucleus
                 extra = None
                 if two_task:   # the layer task of this tile: whole-tile morphology + region contours on the host (OpenCV, like the reference)
                     layer = self.model._proc_ls(layers[j])  # noqa: SLF001
