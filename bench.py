@@ -62,16 +62,21 @@ def common_config(workload: str) -> dict:
     """The part of `config` both arms share (the driver compares it)."""
     cfg = {
         "macenko_hovernet": {"workload": "macenko_hovernet", "tile": [PATCH, PATCH, 3], "stain": "macenko, fit on a synthetic 256x256 target",
-                             "model": "hovernet_fast (num_types=6), seeded + BN-calibrated random weights (residual-branch gain 0.2-0.25)",
+                             "network": "hovernet_fast (num_types=6), seeded + BN-calibrated random weights (residual-branch gain 0.2-0.25)",
+                             "l2_policy": "GPU arm: 11.9 GB of activations per 16-tile step >> 126 MB L2, no flush needed",
                              "heads": "network forward runs in full; post-processing input = SURVEY 8d config-4 synthetic head maps "
                                       "(K~U{20..60} nuclei per 164x164 map), because random-weight heads contain no nuclei"},
-        "macenko": {"workload": "macenko", "tile": [PATCH, PATCH, 3], "stain": "macenko, fit on a synthetic 256x256 target"},
-        "resnet18": {"workload": "resnet18", "tile": [224, 224, 3], "model": "resnet18-kather100k architecture (9 classes), seeded + calibrated weights"},
+        "macenko": {"workload": "macenko", "tile": [PATCH, PATCH, 3], "stain": "macenko, fit on a synthetic 256x256 target",
+                    "l2_policy": "GPU arm: 8192 tiles = 1.6 GB in + 1.6 GB out per step >> 126 MB L2, no flush needed"},
+        "resnet18": {"workload": "resnet18", "tile": [224, 224, 3], "network": "resnet18-kather100k architecture (9 classes), seeded + calibrated weights",
+                     "l2_policy": "GPU arm: 1024 tiles per step, activations >> 126 MB L2, no flush needed"},
         "fcn_tissue_mask": {"workload": "fcn_tissue_mask", "tile": [1024, 1024, 3],
-                            "model": "fcn-tissue_mask architecture (UNet, ResNet-50 encoder), seeded + calibrated weights"},
+                            "network": "fcn-tissue_mask architecture (UNet, ResNet-50 encoder), seeded + calibrated weights",
+                            "l2_policy": "GPU arm: 4 tiles of 1024x1024 per step, activations >> 126 MB L2, no flush needed"},
         "wsi": {"workload": "wsi", "tile": [PATCH, PATCH, 3], "stain": "vahadane, fit on a synthetic 256x256 target",
-                "model": "hovernet_fast (num_types=6), seeded + BN-calibrated random weights",
+                "network": "hovernet_fast (num_types=6), seeded + BN-calibrated random weights",
                 "heads": "synthetic config-4 head maps per patch (as in macenko_hovernet)",
+                "l2_policy": "one pass over a 1.6 GB slide, nothing is re-read",
                 "slide": "virtual slide, 141 x 142 output patches of 164 px (SURVEY 8d config 5)"},
     }
     return dict(cfg[workload])
