@@ -292,20 +292,25 @@ class WsiColumnStore:
         for start, ch in zip(self._starts, self._chunks):
             k = len(ch["box"])
             sel = np.nonzero(alive[start: start + k])[0]
-            if not len(sel):
+            m = len(sel)
+            if not m:
                 continue
             box = ch["box"] + np.array([dx, dy, dx, dy])
             cen = ch["centroid"] + np.array([dx, dy], dtype=np.float64)
             xy = (ch["cont_xy"] + np.array([dx, dy], dtype=ch["cont_xy"].dtype)).astype(ch["cont_xy"].dtype)
-            off = ch["cont_off"]
-            probs, types = ch["prob"].tolist(), ch["type"].tolist()
-            for j in sel.tolist():
-                out["box"][at] = box[j]
-                out["centroid"][at] = cen[j]
-                out["contours"][at] = xy[off[j]: off[j + 1]]
-                out["prob"][at] = None if types[j] < 0 else probs[j]
-                out["type"][at] = None if types[j] < 0 else types[j]
-                at += 1
+            pieces = np.split(xy, ch["cont_off"][1:-1])            # one view per instance of the chunk
+            typed = ch["type"] >= 0
+            # object columns filled at C speed (np.fromiter over row views) instead of one Python assignment per nucleus and key
+            out["box"][at: at + m] = np.fromiter(iter(box[sel]), dtype=object, count=m)
+            out["centroid"][at: at + m] = np.fromiter(iter(cen[sel]), dtype=object, count=m)
+            out["contours"][at: at + m] = np.fromiter((pieces[j] for j in sel.tolist()), dtype=object, count=m)
+            probs = np.array(ch["prob"].tolist(), dtype=object)
+            types = np.array(ch["type"].tolist(), dtype=object)
+            probs[~typed] = None
+            types[~typed] = None
+            out["prob"][at: at + m] = probs[sel]
+            out["type"][at: at + m] = types[sel]
+            at += m
         return out
 
 
