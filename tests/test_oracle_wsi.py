@@ -179,7 +179,7 @@ def test_tensor_paste_equals_the_numpy_recurrence_including_int32_wraparound():
         got = torch.zeros((H, W), dtype=torch.int32)
         m_np = None if start is None else np.int32(start)
         m_t = torch.tensor(0 if start is None else start, dtype=torch.int32)
-        lut = torch.zeros(120 * 120 + 2, dtype=torch.int32)
+        lut = torch.zeros(120 * 120 + 2 + wm.PASTE_SCRATCH, dtype=torch.int32)
         for _ in range(40):
             th, tw = int(rng.integers(20, 120)), int(rng.integers(20, 120))
             x0, y0 = int(rng.integers(0, W - 10)), int(rng.integers(0, H - 10))

@@ -225,9 +225,29 @@ class EngineABC:
             cache[k] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
         return cache[k]
 
-    def _to_host_async(self, key, t: torch.Tensor) -> torch.Tensor:
-        """Start a device -> pinned-host copy on the current stream; the caller synchronises on an event before reading."""
+    def _to_host_async(self, key, t: torch.Tensor, side_stream: bool = False):
+        """Start a device -> pinned-host copy; the caller synchronises on an event before reading.  Default: on the current stream.
+        `side_stream=True`: on the engine's copy stream, ordered after the work already queued on the current stream, so that the copy
+        overlaps the NEXT batch's kernels instead of sitting in front of them; returns (buffer, event recorded after the copy)."""
         buf = self._pinned(key, (max(self.batch_size, t.shape[0]), *t.shape[1:]), t.dtype)[: t.shape[0]]
-        buf.copy_(t, non_blocking=True)
         self.__dict__["d2h_bytes"] = self.__dict__.get("d2h_bytes", 0) + buf.numel() * buf.element_size()   # what actually crosses the bus
-        return buf
+        if not side_stream or t.device.type != "cuda":
+            buf.copy_(t, non_blocking=True)
+            if side_stream:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                return buf, ev
+            return buf
+        cs = self.__dict__.get("_copy_stream")
+        if cs is None:
+            cs = self.__dict__["_copy_stream"] = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        cs.wait_event(ready)
+        with torch.cuda.stream(cs):
+            buf.copy_(t, non_blocking=True)
+            t.record_stream(cs)          # the caching allocator must not hand `t`'s memory out before the copy has read it
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return buf, ev

@@ -198,9 +198,7 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
                 gathered = torch.empty((world * self.batch_size, rec.shape[1]), dtype=torch.int32, device=rec.device)
                 dist.all_gather_into_tensor(gathered, rec)
                 rec = gathered
-            host = self._to_host_async(("rec", b & 1), rec)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
+            host, ev = self._to_host_async(("rec", b & 1), rec, side_stream=True)
             if pending is not None:
                 finish(pending)
             pending = (ev, host, table, b * self.batch_size, hw)

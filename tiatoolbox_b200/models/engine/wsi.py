@@ -302,8 +302,9 @@ class WsiTileModeMixin:
             inst_dict, inst_map, extra = merged.get(i, (wm.columns_from_records([]), None, None))
             if wsi_pred is not None and inst_map is not None:
                 inst_map = torch.as_tensor(inst_map).to(self.device)
-                if lut is None or lut.numel() < inst_map.numel() + 2:      # instance ids are bounded by the tile's pixel count
-                    lut = torch.zeros(inst_map.numel() + 2, dtype=torch.int32, device=self.device)
+                need = inst_map.numel() + 2 + wm.PASTE_SCRATCH      # instance ids are bounded by the tile's pixel count
+                if lut is None or lut.numel() < need:
+                    lut = torch.zeros(need, dtype=torch.int32, device=self.device)
                 max_inst = wm.paste_instance_tile_tensor(inst_map, wsi_pred, bounds, max_inst, lut)
             if extra is not None and wsi_layer is not None and extra[1] is not None:
                 wm.update_tile_based_predictions_array(extra[1], wsi_layer, bounds, (0, 0), seg_type="semantic")

@@ -349,6 +349,9 @@ def update_tile_based_predictions_array(new_pred: np.ndarray, wsi_pred: np.ndarr
     return max_inst_value
 
 
+PASTE_SCRATCH = 4096   # scratch slots at the end of `paste_instance_tile_tensor`'s table
+
+
 def paste_instance_tile_tensor(new_pred, wsi_pred, bounds, max_inst_value, lut):
     """`update_tile_based_predictions_array` (instance maps) on torch tensors — the same order-dependent recurrence, branch-free so that
     it needs no host synchronisation per tile: on the B200 the gathered tile maps stay on the device, the WSI map is pasted there
@@ -356,7 +359,7 @@ def paste_instance_tile_tensor(new_pred, wsi_pred, bounds, max_inst_value, lut):
     back once.  int32 arithmetic wraps exactly like the reference's numpy int32 scalars do.
 
     new_pred (h, w) int32, wsi_pred (H, W) int32 [updated in place], max_inst_value: 0-dim int32 tensor, lut: int32 scratch of at least
-    new_pred.max() + 1 entries (zero on entry, zero on return).  Returns the new max_inst_value tensor."""
+    new_pred.max() + 1 + PASTE_SCRATCH entries (zero on entry, zero on return).  Returns the new max_inst_value tensor."""
     import torch
 
     x_start, y_start, x_end, y_end = (int(v) for v in bounds)
@@ -370,7 +373,12 @@ def paste_instance_tile_tensor(new_pred, wsi_pred, bounds, max_inst_value, lut):
     # ids of new instances that touch something already pasted: lut[id] = 1 (id 0 never qualifies: overlap implies new > 0)
     # plain scatter (all writes to an index carry the same value: 1 for a touched id, 0 to slot 0 from every other pixel) — an
     # accumulating index_put would sort a million indices per tile (r2k: 40 ms per tile)
-    lut.scatter_(0, torch.where(overlap, ids, torch.zeros_like(ids)).reshape(-1), overlap.reshape(-1).to(lut.dtype))
+    # (pixels without overlap write a 0 into one of 4096 scratch slots at the END of the table, spread by pixel position: a million
+    # writes to one address serialise — r2l: 4 ms per tile)
+    n_ids = lut.numel() - PASTE_SCRATCH
+    flat = torch.arange(ids.numel(), device=ids.device, dtype=torch.int64).reshape(ids.shape)
+    target = torch.where(overlap, ids, n_ids + (flat & (PASTE_SCRATCH - 1)))
+    lut.scatter_(0, target.reshape(-1), overlap.reshape(-1).to(lut.dtype))
     keep = pos & (lut[ids] == 0)
     combined = torch.where(keep, new + max_inst_value, prev)
     new_max = torch.where(keep.any(), combined.max() + max_inst_value, max_inst_value)
