@@ -90,7 +90,7 @@ class WsiTileModeMixin:
     """`run(image, patch_mode=False)` for instance-segmentation engines.  The three device primitives are methods so that the host
     logic (banding, stitching order, tile batching, gather, replay) can be exercised without a GPU by the gloo tests."""
 
-    tile_batch = 4   # same-shape tiles post-processed per device call
+    tile_batch = 16  # same-shape tiles post-processed per device call (the flood's serial critical path — the largest component — is shared by the batch)
     min_tile = 11    # smallest tile side tiab_hovernet_postproc accepts
 
     # ---- device primitives -------------------------------------------------------------------------------------------------

@@ -228,6 +228,7 @@ class WsiColumnStore:
         self._starts: list[int] = []
         self._boxes = np.empty((4096, 4), dtype=np.int64)
         self._alive = np.zeros(4096, dtype=bool)
+        self._chunk_boxes = np.empty((256, 4), dtype=np.int64)     # bounding box of every chunk's instances (WSI space)
         self.n = 0
 
     def __len__(self) -> int:
@@ -242,13 +243,24 @@ class WsiColumnStore:
         tile_shape = tile_bounds[2:] - tile_bounds[:2]
         drop = select_tile_removals(cols["box"], tile_shape, tile_flag, tile_mode, margin)
         evicted = 0
-        if tile_mode == 3:  # noqa: PLR2004
-            hit = np.zeros(self.n, dtype=bool)
-            for line in margin_lines(margin, tile_shape, tile_tl):
-                hit |= boxes_intersect(self._boxes[: self.n], line)
-            hit &= self._alive[: self.n]
-            evicted = int(hit.sum())
-            self._alive[: self.n][hit] = False
+        if tile_mode == 3 and self._chunks:  # noqa: PLR2004
+            # a cross tile evicts the accumulated instances its inner margin lines cut.  Only tiles placed near it can hold such
+            # instances: the lines are tested against the bounding box of every earlier tile's kept set first (one vectorised test over
+            # ~2 000 chunk boxes), then against the instances of the few chunks that qualify — not against all 680 k accumulated boxes
+            # per cross tile (r2n: 5.8 of the replay's 8.2 s).
+            lines = margin_lines(margin, tile_shape, tile_tl)
+            cb = self._chunk_boxes[: len(self._chunks)]
+            near = np.zeros(len(cb), dtype=bool)
+            for line in lines:
+                near |= boxes_intersect(cb, line)
+            for c in np.nonzero(near)[0].tolist():
+                start, kk = self._starts[c], len(self._chunks[c]["box"])
+                hit = np.zeros(kk, dtype=bool)
+                for line in lines:
+                    hit |= boxes_intersect(self._boxes[start: start + kk], line)
+                hit &= self._alive[start: start + kk]
+                evicted += int(hit.sum())
+                self._alive[start: start + kk][hit] = False
         keep = np.nonzero(~drop)[0]
         k = len(keep)
         if k == 0:
@@ -271,6 +283,10 @@ class WsiColumnStore:
             self._alive = np.concatenate([self._alive, np.zeros_like(self._alive)])
         self._boxes[self.n: self.n + k] = chunk["box"]
         self._alive[self.n: self.n + k] = True
+        if len(self._chunks) == len(self._chunk_boxes):
+            self._chunk_boxes = np.concatenate([self._chunk_boxes, np.empty_like(self._chunk_boxes)])
+        b = chunk["box"]
+        self._chunk_boxes[len(self._chunks)] = (b[:, 0].min(), b[:, 1].min(), b[:, 2].max(), b[:, 3].max())
         self._chunks.append(chunk)
         self._starts.append(self.n)
         self.n += k
