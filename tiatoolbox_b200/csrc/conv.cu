@@ -792,6 +792,20 @@ __device__ __forceinline__ void store8(__half* p, int lo, const float (&v)[8]) {
 
 // Explicit im2col for strided convs / 3-channel stems: out[m, (kh*KW + kw)*C + c] (row pitch ldout, K zero padded to
 // Kpad, lo plane at +out_lo) from an NHWC source that is fp16 (+lo plane) or uint8 (scaled by u8_scale).
+// flattened-index decomposition of the memory-bound glue kernels: a 64-bit division costs ~100 instructions on the GPU, and these
+// kernels move 16-48 bytes per thread — with 64-bit div/mod chains they were instruction-bound (upsample + skip add at ~55 % of the
+// HBM roofline in r2h).  Indices below 2^32 (every launch of the three networks) take the 32-bit path.
+__device__ __forceinline__ long long fast_divmod(long long i, int d, int& rem) {
+  if ((unsigned long long)i <= 0xffffffffull) {
+    const unsigned ui = (unsigned)i, q = ui / (unsigned)d;
+    rem = (int)(ui - q * (unsigned)d);
+    return (long long)q;
+  }
+  const long long q = i / d;
+  rem = (int)(i - q * d);
+  return q;
+}
+
 __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ src, int src_is_u8, float u8_scale, int src_lo,
                                                      int Nimg, int H, int W, int C, int ldsrc, int KH, int KW, int stride,
                                                      int pad_t, int pad_l, int Ho, int Wo, __half* __restrict__ out,
@@ -845,12 +859,10 @@ __global__ void __launch_bounds__(256) im2col_u8c3_kernel(const uint8_t* __restr
   const int k8n = Kpad >> 3;
   const long long total = (long long)Nimg * Ho * Wo * k8n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % k8n);
-    const long long m = i / k8n;
-    const int xo = (int)(m % Wo);
-    const long long my = m / Wo;
-    const int yo = (int)(my % Ho);
-    const int img = (int)(my / Ho);
+    int g, xo, yo;
+    const long long m = fast_divmod(i, k8n, g);
+    const long long my = fast_divmod(m, Wo, xo);
+    const int img = (int)fast_divmod(my, Ho, yo);
     const int ybase = yo * stride - pad_t, xbase = xo * stride - pad_l;
     const uint8_t* sp = src + ((long long)img * H * W + (long long)ybase * W + xbase) * 3;
     const bool interior = ybase >= 0 && xbase >= 0 && ybase + KH <= H && xbase + KW <= W;
@@ -883,14 +895,14 @@ __global__ void __launch_bounds__(256) im2col_vec8_kernel(const __half* __restri
   const long long total = (long long)Nimg * Ho * Wo * k8n;
   const int K = KH * KW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % k8n) * 8;
-    const long long m = i / k8n;
+    int k;
+    const long long m = fast_divmod(i, k8n, k);
+    k *= 8;
     uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
     if (k < K) {
       const int c = k % C, t = k / C, kw = t % KW, kh = t / KW;
-      const int xo = (int)(m % Wo);
-      const int yo = (int)((m / Wo) % Ho);
-      const int img = (int)(m / ((long long)Wo * Ho));
+      int xo, yo;
+      const int img = (int)fast_divmod(fast_divmod(m, Wo, xo), Ho, yo);
       const int y = yo * stride - pad_t + kh, x = xo * stride - pad_l + kw;
       if (y >= 0 && y < H && x >= 0 && x < W) {
         const __half* sp = src + ((long long)(img * H + y) * W + x) * ldsrc + c;
@@ -912,8 +924,9 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const void* __restrict__ s
   const int c8 = C >> 3;
   const long long total = rows * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8) * 8;
-    const long long r = i / c8;
+    int cg;
+    const long long r = fast_divmod(i, c8, cg);
+    cg *= 8;
     float v[8];
     if (src_is_f32) {
       const float* s = reinterpret_cast<const float*>(src) + r * ldsrc + coffsrc + cg;
@@ -941,12 +954,11 @@ upsample_add_kernel(const __half* __restrict__ a, int Ha, int Wa, int Hag, int W
   const int Ho = 2 * Ha, Wo = 2 * Wa, c8 = C >> 3;
   const long long total = (long long)Nimg * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8) * 8;
-    long long r = i / c8;
-    const int x = (int)(r % Wo);
-    r /= Wo;
-    const int y = (int)(r % Ho);
-    const int img = (int)(r / Ho);
+    int cg, x, y;
+    long long r = fast_divmod(i, c8, cg);
+    cg *= 8;
+    r = fast_divmod(r, Wo, x);
+    const int img = (int)fast_divmod(r, Ho, y);
     float v[8];
     load8(a + ((long long)(img * Hag + (y >> 1) + ay) * Wag + (x >> 1) + ax) * lda + cg, a_lo, v);
     if (b) {
@@ -971,12 +983,11 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restr
   const int c8 = C >> 3;
   const long long total = (long long)Nimg * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8) * 8;
-    long long r = i / c8;
-    const int xo = (int)(r % Wo);
-    r /= Wo;
-    const int yo = (int)(r % Ho);
-    const int img = (int)(r / Ho);
+    int cg, xo, yo;
+    long long r = fast_divmod(i, c8, cg);
+    cg *= 8;
+    r = fast_divmod(r, Wo, xo);
+    const int img = (int)fast_divmod(r, Ho, yo);
     float m[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = -3.0e38f;
