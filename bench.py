@@ -393,6 +393,11 @@ def conv_roofline(plan, algorithmic_flops: float, pk: dict) -> tuple[dict, float
         c[2] += op.flops
         c[3] += getattr(op, "bytes", 0.0)
     ach = algorithmic_flops / (conv_ms / 1e3) / 1e12
+    traffic = None      # dram read + write of all conv launches of one step, from the committed ncu --set full capture (HoVer-Net, 16 tiles)
+    tp = ROOT / "profiles" / "conv_gemm_traffic.json"
+    if tp.exists() and abs(algorithmic_flops / (GFLOP["hovernet_fast"] * 1e9) - round(algorithmic_flops / (GFLOP["hovernet_fast"] * 1e9))) < 1e-6:
+        tj = json.loads(tp.read_text())
+        traffic = tj["dram_bytes_per_step"] * (algorithmic_flops / (GFLOP["hovernet_fast"] * 1e9)) / tj["tiles_per_step"]
     by_class = {}
     ct = classes["tensor"]
     if ct[0]:
@@ -404,7 +409,7 @@ def conv_roofline(plan, algorithmic_flops: float, pk: dict) -> tuple[dict, float
         by_class["hbm_bound_layers"] = {"launches": ch[0], "ms": ch[1], "achieved_gbs_on_min_traffic": gb, "frac_of_hbm_peak": gb / pk["hbm"]}
     roof = {
         "bound": "tensor", "kernel": "conv_gemm_kernel (all launches of one step)", "achieved": ach, "peak": pk["tf_sustained"],
-        "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+        "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
         "algorithmic_flops_per_step": algorithmic_flops, "grid_flops_per_step": flops_grid, "kernel_ms_per_step": conv_ms,
         "mma_issue_rate_tflops": mma / (conv_ms / 1e3) / 1e12,
         "launches_per_step": sum(1 for op, _ in rows if hasattr(op, "desc")), "by_class": by_class,
@@ -733,7 +738,8 @@ def main():
                                     f"inputs+outputs {2 * B * PATCH * PATCH * 3 / 1e6:.0f} MB per step > 126 MB L2",
                        "parallelism": f"unit-shard x{world}, all-gather of the result"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e_units * size * size * 3, "d2h_bytes_per_step": d2h,
-                    "units_per_step": e2e_units, "api": api, "nuclei_per_step": e2e_nuclei},
+                    "units_per_step": e2e_units, "api": api, "nuclei_per_step": e2e_nuclei,
+                    "rank0_host_split_of_last_call_s": getattr(eng, "last_timings", None) if eng is not None else None},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }

@@ -148,9 +148,23 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
         pending = None
         use_contours = self.device_contours and self.with_contours
 
+        import time as _time
+
+        tm = {"wait_s": 0.0, "finish_s": 0.0, "issue_s": 0.0, "rounds": rounds}     # host-side split of this call (diagnostics: `last_timings`)
+        self.last_timings = tm
+
         def finish(p):
             ev, host, table_d, base, hw = p
+            _t0 = _time.perf_counter()
             ev.synchronize()
+            _t1 = _time.perf_counter()
+            tm["wait_s"] += _t1 - _t0
+            try:
+                _finish_body(host, table_d, base, hw)
+            finally:
+                tm["finish_s"] += _time.perf_counter() - _t1
+
+        def _finish_body(host, table_d, base, hw):
             rec = host.numpy()
             inst_v, t = self._unpack(rec, hw, rows, verts)
             if st["inst_all"] is None:
@@ -193,6 +207,7 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
 
         batches = self._batches(patches)
         for b in range(rounds):
+            _ti = _time.perf_counter()
             x = next(batches, None)
             if x is not None:
                 outs = type(self.model).infer_batch_device(self.model, x, device=self.device)
@@ -218,6 +233,7 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
                 dist.all_gather_into_tensor(gathered, rec)
                 rec = gathered
             host, ev = self._to_host_async(("rec", b & 1), rec, side_stream=True)
+            tm["issue_s"] += _time.perf_counter() - _ti
             if pending is not None:
                 finish(pending)
             pending = (ev, host, table, b * self.batch_size, hw)
