@@ -15,10 +15,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
-# GPU test modules added last in round 1 (each has passed on a B200 once: profiles/r1h_gpu_tests_*.log): they are collected AFTER the
-# long-established modules, so that with `-x` a failure in the newest code cannot hide the results of the hot-path tests.
+# The long-established hot-path modules run first, the newest modules last, so that with `-x` a failure in the newest code cannot hide the
+# results of the hot-path tests.  Every module listed here has passed on a B200 (profiles/r2q_gpu_tests.log: 116 passed).
 _NEWEST_GPU_MODULES = ("test_reinhard_gpu", "test_augment_gpu", "test_contours_gpu", "test_wsi_gpu", "test_hovernetplus_gpu",
-                       "test_watershed_v2_gpu")   # the last one has NOT run on a B200 yet (opt-in code path, written after the budget was spent)
+                       "test_reinhard_fused_gpu", "test_watershed_v2_gpu", "test_net_capi_gpu")
 
 
 def pytest_collection_modifyitems(config, items):  # noqa: ARG001
