@@ -180,3 +180,30 @@ def make_unet_1024() -> None:
     np.savez_compressed(GOLDEN / "unet1024_golden.npz", probs_stride4=probs[:, ::4, ::4], mean=probs.mean(axis=(0, 1, 2)),
                         frac_class1=np.float64((probs.argmax(-1) == 1).mean()))
     print("unet 1024 golden:", probs.shape, probs.mean(axis=(0, 1, 2)), (probs.argmax(-1) == 1).mean())
+
+
+def make_hovernet_original() -> None:
+    """hovernet `mode="original"` (270 x 270 in, 80 x 80 out, 5 x 5 decoder convolutions): BN calibration on the CPU + the UNMODIFIED reference
+    module's branch logits and `infer_batch` heads on one seeded tile.   python -c "from oracle.make_golden_cnn import make_hovernet_original as f; f()" """
+    from oracle import ref_shim
+    from oracle.torch_reference import hovernet_forward_reference
+    from tiatoolbox_b200.models.architecture._params import calibrate, seeded_state_dict
+    from tiatoolbox_b200.models.architecture.hovernet import hovernet_spec
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    m = ref_shim.load_models()
+    sd = seeded_state_dict(hovernet_spec(3, 6, "original"), seed=0)
+    xcal = torch.from_numpy(he_tiles(2, 270, 270, seed=100)).permute(0, 3, 1, 2).float()
+    stats = calibrate(sd, lambda s, x: hovernet_forward_reference(s, x, "original", 6), xcal)
+    np.savez_compressed(GOLDEN / "hovernet_original_bn_calib.npz", **{k: v.numpy() for k, v in stats.items()})
+    sd.update(stats)
+    net = m.hovernet.HoVerNet(num_types=6, mode="original").eval()
+    net.load_state_dict(sd)
+    tile = he_tiles(1, 270, 270, seed=2)
+    with torch.inference_mode():
+        raw = net(torch.from_numpy(tile).permute(0, 3, 1, 2).float())
+    heads = m.hovernet.HoVerNet.infer_batch(net, torch.from_numpy(tile), device="cpu")
+    out = {f"logits_{k}": _f16(v.permute(0, 2, 3, 1)) for k, v in raw.items()}
+    out.update({f"head_{k}": np.asarray(v, np.float32) for k, v in zip(("np", "hv", "tp"), heads)})
+    np.savez_compressed(GOLDEN / "hovernet_original_golden.npz", **out)
+    print("hovernet original golden:", {k: v.shape for k, v in out.items()})

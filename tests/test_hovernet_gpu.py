@@ -152,3 +152,35 @@ def test_original_mode_270_matches_fp32_reference(built_lib):
         e = rel_l2(got, r)
         print(f"original {b}: rel_l2 {e:.2e}")
         assert np.isfinite(got).all() and e <= 1e-3, (b, e)
+
+
+def test_original_mode_matches_the_unmodified_reference_golden(built_lib):
+    """mode="original" against the UNMODIFIED reference module (CPU fp32; tests/golden/hovernet_original_golden.npz, generator
+    oracle/make_golden_cnn.py::make_hovernet_original): branch logits rel-L2 <= 1e-3 (north_star), heads through the public infer_batch."""
+    import torch
+
+    from tiatoolbox_b200.models.architecture._params import seeded_state_dict
+    from tiatoolbox_b200.models.architecture.hovernet import HoVerNet, hovernet_spec
+    from tiatoolbox_b200.synthetic import he_tiles
+
+    gold = np.load(GOLDEN / "hovernet_original_golden.npz")
+    calib = np.load(GOLDEN / "hovernet_original_bn_calib.npz")
+    sd = seeded_state_dict(hovernet_spec(3, 6, "original"), seed=0)
+    for k in calib.files:
+        sd[k] = torch.from_numpy(calib[k])
+    model = HoVerNet(num_types=6, mode="original")
+    model.load_state_dict(sd)
+    model.to("cuda:0")
+    tile = he_tiles(1, 270, 270, seed=2)
+    logits = model.forward(torch.from_numpy(tile).permute(0, 3, 1, 2))          # the device plan behind the reference's forward() contract
+    for b in ("tp", "np", "hv"):
+        got = logits[b].permute(0, 2, 3, 1).cpu().numpy()
+        e = rel_l2(got, gold[f"logits_{b}"])
+        m = float(np.abs(got - gold[f"logits_{b}"]).max() / np.abs(gold[f"logits_{b}"]).max())
+        print(f"original vs reference golden {b}: rel_l2 {e:.2e}  max/max {m:.2e}")
+        assert e <= 1e-3 and m <= 2e-3, (b, e, m)      # the reference side is CPU fp32 (oneDNN), itself ~1e-4 off float64 on 5x5 convolutions
+    np_o, hv_o, tp_o = HoVerNet.infer_batch(model, torch.from_numpy(tile), device="cuda:0")
+    assert np_o.shape == (1, 80, 80, 1) and hv_o.shape == (1, 80, 80, 2) and tp_o.shape == (1, 80, 80, 1)
+    assert np.abs(np_o - gold["head_np"]).max() <= 1e-3
+    assert rel_l2(hv_o, gold["head_hv"]) <= 1e-3
+    assert (tp_o == gold["head_tp"]).mean() >= 0.999

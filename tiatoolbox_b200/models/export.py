@@ -227,3 +227,34 @@ class NetRunner:
             self.close()
         except Exception:  # noqa: BLE001, S110
             pass
+
+
+def main(argv=None) -> int:
+    """`python -m tiatoolbox_b200.models.export <registry name> <out.plan> [--weights w.pth] [--batch 16] [--size 256] [--device 0]`
+    writes the plan file a non-Python host loads with tiab_net_create.  Registry names: architecture/__init__.py."""
+    import argparse
+    from pathlib import Path
+
+    from tiatoolbox_b200.models.architecture import get_pretrained_model
+
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("model")
+    ap.add_argument("out")
+    ap.add_argument("--weights", default=None, help="tiatoolbox checkpoint (.pth); default: the seeded random weights")
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, default=None, help="input tile side (default: the registry ioconfig's patch_input_shape)")
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args(argv)
+    model, io = get_pretrained_model(a.model, a.weights)
+    dev = torch.device("cuda", a.device)
+    model.to(dev)
+    size = a.size or int(io.patch_input_shape[0])
+    plan = model.plan_for(a.batch, dev, (size, size))
+    blob = export_plan(plan)
+    Path(a.out).write_bytes(blob)
+    print(f"{a.model}: batch {a.batch}, {size}x{size} tiles, {len(plan.ops)} launches, {len(blob) / 1e6:.1f} MB -> {a.out}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
