@@ -172,3 +172,35 @@ def test_patch_pipeline_world2(built_lib):
             ref_inst, ref_info = po.postproc(heads[0][i], heads[1][i], heads[2][i])
             assert np.array_equal(preds[i], ref_inst) and len(boxes[i]) == len(ref_info)
             assert all(np.array_equal(a, r["box"]) for a, r in zip(boxes[i], ref_info.values()))
+
+
+def test_result_pool_returns_a_block_only_when_every_view_is_gone():
+    """`predictions` sits on recycled host memory (engine_abc.HostResultPool): a block may be reused only after the result array AND
+    all views derived from it (slices, reshapes, torch.from_numpy) have been collected."""
+    import gc
+
+    import torch
+
+    from tiatoolbox_b200.models.engine.engine_abc import HostResultPool
+
+    pool = HostResultPool()
+    a = pool.take((8, 16, 16), np.int32)
+    a[:] = 7
+    nbytes = a.nbytes
+    row, flat, tt = a[3], a.reshape(-1)[5:9], torch.from_numpy(a)
+    del a
+    gc.collect()
+    assert not pool.free.get(nbytes)
+    del row, flat
+    gc.collect()
+    assert not pool.free.get(nbytes)
+    assert int(tt.sum()) == 7 * 8 * 16 * 16
+    del tt
+    gc.collect()
+    assert len(pool.free[nbytes]) == 1
+    b = pool.take((8, 16, 16), np.int32)       # same pages again
+    assert not pool.free[nbytes] and b.flags.writeable and b.shape == (8, 16, 16)
+    c = pool.take((8, 16, 16), np.int32)       # pool empty -> a fresh block, not the live one
+    b[:] = 1
+    c[:] = 2
+    assert int(b.max()) == 1 and int(c.min()) == 2

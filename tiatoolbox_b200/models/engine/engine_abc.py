@@ -39,6 +39,48 @@ def cast_to_min_dtype(array: np.ndarray) -> np.ndarray:
     return array
 
 
+class _PooledBlock:
+    """Owner of one pooled byte block: the `.base` of the result array AND of every view of it (numpy collapses view chains to the first
+    non-array owner), so the block goes back to the pool only when the last view is gone.  Python-level buffer protocol: PEP 688."""
+
+    def __init__(self, pool: "HostResultPool", nbytes: int, raw: np.ndarray) -> None:
+        self.pool, self.nbytes, self.raw = pool, nbytes, raw
+
+    def __buffer__(self, flags: int) -> memoryview:
+        return memoryview(self.raw)
+
+    def __del__(self) -> None:
+        pool, raw = self.pool, self.raw
+        if pool is not None and raw is not None:
+            pool._give_back(self.nbytes, raw)  # noqa: SLF001
+
+
+class HostResultPool:
+    """Recycles the host memory of large result arrays.  A result such as `predictions` (107 KB per image, for ALL images of a multi-rank
+    job on every rank) is a fresh numpy array per `run()`; faulting in and zeroing fresh pages costs ~0.3 ms per MB — 66 ms per call at
+    2048 images, more than 15 % of an 8-GPU run (r2s).  Arrays handed out here sit on a pooled byte block owned by a `_PooledBlock`;
+    when the array and every view of it have been garbage-collected the block returns to the pool, so a steady stream of `run()` calls
+    writes into pages that are already mapped.  At most two free blocks per size are kept."""
+
+    def __init__(self) -> None:
+        self.free: dict[int, list] = {}
+
+    def take(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        blocks = self.free.get(nbytes)
+        raw = blocks.pop() if blocks else np.empty(max(nbytes, 1), dtype=np.uint8)
+        return np.ndarray(tuple(shape), dtype=dtype, buffer=_PooledBlock(self, nbytes, raw))
+
+    def _give_back(self, nbytes: int, raw) -> None:
+        lst = self.free.setdefault(nbytes, [])
+        if len(lst) < 2:  # noqa: PLR2004
+            lst.append(raw)
+
+
+_RESULT_POOL = HostResultPool()
+
+
 class EngineABC:
     """Template: run -> shard -> batches -> model on device -> post-process -> gather -> dict."""
 

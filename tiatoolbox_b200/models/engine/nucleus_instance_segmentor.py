@@ -129,22 +129,6 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
         rows, verts = int(self.table_rows_fast), int(self.contour_vertices_fast)
         heads, layers, insts_dev = [], [], []
         st = {"inst_all": None, "infos": [None] * n_local, "remote": {}, "overflow": []}
-        # The result array holds the maps of ALL images (every rank returns the complete `predictions`): 107 KB x n_total.  Its pages are
-        # faulted in by a helper thread while the GPU works on the first batches (numpy's fill releases the GIL) — done on the main
-        # thread it cost ~30 ms per call at 1024 images, i.e. 8 % of a 4-GPU run (r2o).
-        prefault = {"arr": None, "thread": None}
-        if n_total:
-            import threading
-
-            guess = self._empty_round_shape(dist)
-
-            def _alloc():
-                a = np.empty((n_total, *guess), np.int32)
-                a.fill(0)
-                prefault["arr"] = a
-
-            prefault["thread"] = threading.Thread(target=_alloc, daemon=True)
-            prefault["thread"].start()
         pending = None
         use_contours = self.device_contours and self.with_contours
 
@@ -167,11 +151,10 @@ class MultiTaskSegmentor(WsiTileModeMixin, EngineABC):
         def _finish_body(host, table_d, base, hw):
             rec = host.numpy()
             inst_v, t = self._unpack(rec, hw, rows, verts)
-            if st["inst_all"] is None:
-                if prefault["thread"] is not None:
-                    prefault["thread"].join()
-                a = prefault["arr"]
-                st["inst_all"] = a if a is not None and a.shape[1:] == tuple(hw) else np.zeros((n_total, *hw), np.int32)
+            if st["inst_all"] is None:     # every image of the job is written below, so the recycled block needs no clearing
+                from tiatoolbox_b200.models.engine.engine_abc import _RESULT_POOL
+
+                st["inst_all"] = _RESULT_POOL.take((n_total, *hw), np.int32)
             for r in range(world if dist is not None else 1):
                 blk = slice(r * self.batch_size, (r + 1) * self.batch_size)
                 cnt = t["count"][blk]
