@@ -101,3 +101,24 @@ def test_lasso2_matches_sklearn_lars():
             )
         mine = so.lasso2(gram, c, 0.1, n)
         assert np.allclose(mine, coefs, rtol=1e-8, atol=1e-10)
+
+
+def test_three_stain_concentrations_match_the_reference_lstsq():
+    """`StainNormalizer.get_concentrations` with a 3x3 user matrix (the only shape besides 2x3 that CustomExtractor accepts): the tensor-op
+    spelling used on the device equals the unmodified reference's lstsq on the same pixels (run on the CPU device here)."""
+    import torch
+
+    from oracle import ref_shim
+    from tiatoolbox_b200.tools import stainnorm
+
+    if not ref_shim.available():
+        pytest.skip("reference sources not present")
+    sn = ref_shim.load_stain()
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 41, 3), dtype=np.uint8)
+    img[0, :5] = 0
+    m = np.array([[0.65, 0.70, 0.29], [0.07, 0.99, 0.11], [0.27, 0.57, 0.78]])
+    ref = sn.StainNormalizer.get_concentrations(img.copy(), m)
+    got = stainnorm._concentrations_three_stains(torch.from_numpy(img), m).numpy()
+    assert got.shape == ref.shape == (37 * 41, 3)
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-10)

@@ -40,6 +40,17 @@ def _is_torch_cuda(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
 
 
+def _concentrations_three_stains(img_u8, stain_matrix: np.ndarray):
+    """`lstsq(M.T, od.T).T` of stainnorm.py:64-66 for a 3x3 `M` on the tensor's device, float64: the minimum-norm least-squares solution is
+    `od @ pinv(M)`; `od` as `rgb2od` (transforms.py:229-231: zeros -> 1, floor 1e-6)."""
+    import torch
+
+    pinv = torch.from_numpy(np.linalg.pinv(np.asarray(stain_matrix, np.float64))).to(img_u8.device)
+    x = img_u8.reshape(-1, 3).to(torch.float64).clamp_(min=1.0)
+    od = (-torch.log(x / 255.0)).clamp_(min=1e-6)
+    return od @ pinv
+
+
 class StainNormalizer:
     """Stain normalization base class (stainnorm.py:19-113).
 
@@ -70,11 +81,15 @@ class StainNormalizer:
 
         img = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
         m = np.ascontiguousarray(np.asarray(stain_matrix, dtype=np.float64))
+        dev = torch.device("cuda", device)
+        if m.shape == (3, 3):
+            # three-stain user matrix (CustomExtractor accepts it, stainextract.py:73-77; `fit` cannot use it, but this static method can):
+            # not on any engine's path, so it is the same least-squares solve spelled with device tensor ops instead of a kernel
+            return _concentrations_three_stains(torch.from_numpy(img).to(dev), m).cpu().numpy()
         if m.shape != (2, 3):
-            msg = "get_concentrations on the GPU supports 2x3 stain matrices."
+            msg = "Stain matrix must have shape (2, 3) or (3, 3)."
             raise ValueError(msg)
         h = _lib.handle(device)
-        dev = torch.device("cuda", device)
         t_in = torch.from_numpy(img).to(dev)
         t_out = torch.empty((img.shape[0] * img.shape[1], 2), dtype=torch.float32, device=dev)
         rc = _lib.lib().tiab_stain_concentrations(
