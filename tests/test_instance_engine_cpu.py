@@ -176,31 +176,43 @@ def test_patch_pipeline_world2(built_lib):
 
 def test_result_pool_returns_a_block_only_when_every_view_is_gone():
     """`predictions` sits on recycled host memory (engine_abc.HostResultPool): a block may be reused only after the result array AND
-    all views derived from it (slices, reshapes, torch.from_numpy) have been collected."""
+    all views derived from it (slices, reshapes, torch.from_numpy) have been collected; the free list is bounded."""
     import gc
 
     import torch
 
     from tiatoolbox_b200.models.engine.engine_abc import HostResultPool
 
-    pool = HostResultPool()
+    pool = HostResultPool(max_free_bytes=3 * 8192)
     a = pool.take((8, 16, 16), np.int32)
     a[:] = 7
-    nbytes = a.nbytes
     row, flat, tt = a[3], a.reshape(-1)[5:9], torch.from_numpy(a)
     del a
     gc.collect()
-    assert not pool.free.get(nbytes)
+    assert not pool.free
     del row, flat
     gc.collect()
-    assert not pool.free.get(nbytes)
+    assert not pool.free
     assert int(tt.sum()) == 7 * 8 * 16 * 16
     del tt
     gc.collect()
-    assert len(pool.free[nbytes]) == 1
+    assert [n for n, _ in pool.free] == [8192]
     b = pool.take((8, 16, 16), np.int32)       # same pages again
-    assert not pool.free[nbytes] and b.flags.writeable and b.shape == (8, 16, 16)
+    assert not pool.free and b.flags.writeable and b.shape == (8, 16, 16)
     c = pool.take((8, 16, 16), np.int32)       # pool empty -> a fresh block, not the live one
     b[:] = 1
     c[:] = 2
     assert int(b.max()) == 1 and int(c.min()) == 2
+    del b, c
+    gc.collect()
+    d = pool.take((7, 16, 16), np.int32)       # a slightly smaller request reuses a block (<= 25 % slack) ...
+    assert len(pool.free) == 1 and d.shape == (7, 16, 16) and d.nbytes == 7168
+    e = pool.take((2, 16, 16), np.int32)       # ... a much smaller one does not
+    assert len(pool.free) == 1
+    del d, e
+    gc.collect()
+    assert pool.free_bytes() <= pool.max_free_bytes
+    held = [pool.take((8, 16, 16), np.int32) for _ in range(6)]
+    del held
+    gc.collect()
+    assert pool.free_bytes() <= pool.max_free_bytes and len(pool.free) == 3      # bounded: oldest blocks are dropped

@@ -60,22 +60,32 @@ class HostResultPool:
     job on every rank) is a fresh numpy array per `run()`; faulting in and zeroing fresh pages costs ~0.3 ms per MB — 66 ms per call at
     2048 images, more than 15 % of an 8-GPU run (r2s).  Arrays handed out here sit on a pooled byte block owned by a `_PooledBlock`;
     when the array and every view of it have been garbage-collected the block returns to the pool, so a steady stream of `run()` calls
-    writes into pages that are already mapped.  At most two free blocks per size are kept."""
+    writes into pages that are already mapped.  A request takes the smallest free block of at least its size and at most 25 % more; the
+    free list is bounded (`max_free_bytes`, oldest blocks dropped first), so calls of ever-changing sizes cannot pile up memory."""
 
-    def __init__(self) -> None:
-        self.free: dict[int, list] = {}
+    def __init__(self, max_free_bytes: int = 1 << 30) -> None:
+        self.free: list = []                      # [(nbytes, raw)], oldest first
+        self.max_free_bytes = int(max_free_bytes)
+
+    def free_bytes(self) -> int:
+        return sum(n for n, _ in self.free)
 
     def take(self, shape, dtype) -> np.ndarray:
         dtype = np.dtype(dtype)
-        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        blocks = self.free.get(nbytes)
-        raw = blocks.pop() if blocks else np.empty(max(nbytes, 1), dtype=np.uint8)
-        return np.ndarray(tuple(shape), dtype=dtype, buffer=_PooledBlock(self, nbytes, raw))
+        nbytes = max(int(np.prod(shape, dtype=np.int64)) * dtype.itemsize, 1)
+        fits = [(n, i) for i, (n, _) in enumerate(self.free) if nbytes <= n <= nbytes + nbytes // 4]
+        if fits:
+            size, raw = self.free.pop(min(fits)[1])
+        else:
+            size, raw = nbytes, np.empty(nbytes, dtype=np.uint8)
+        return np.ndarray(tuple(shape), dtype=dtype, buffer=_PooledBlock(self, size, raw))
 
     def _give_back(self, nbytes: int, raw) -> None:
-        lst = self.free.setdefault(nbytes, [])
-        if len(lst) < 2:  # noqa: PLR2004
-            lst.append(raw)
+        if nbytes > self.max_free_bytes:
+            return
+        self.free.append((nbytes, raw))
+        while self.free_bytes() > self.max_free_bytes:
+            self.free.pop(0)
 
 
 _RESULT_POOL = HostResultPool()
