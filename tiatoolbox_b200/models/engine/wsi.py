@@ -309,7 +309,7 @@ class WsiTileModeMixin:
             if extra is not None and wsi_layer is not None and extra[1] is not None:
                 wm.update_tile_based_predictions_array(extra[1], wsi_layer, bounds, (0, 0), seg_type="semantic")
             if plan.tile_mode:
-                store.merge_tile(inst_dict, tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin)
+                store.merge_tile(inst_dict, tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin, consume=True)
                 if extra is not None:
                     layer_store.merge_tile(extra[0], tile_bounds=bounds, tile_flag=flag, tile_mode=mode, margin=plan.margin)
             else:   # `_process_full_wsi` :999-1076: one postproc call over the whole map, nothing to merge
