@@ -50,9 +50,10 @@ class _PooledBlock:
         return memoryview(self.raw)
 
     def __del__(self) -> None:
-        pool, raw = self.pool, self.raw
-        if pool is not None and raw is not None:
-            pool._give_back(self.nbytes, raw)  # noqa: SLF001
+        try:
+            self.pool._give_back(self.nbytes, self.raw)  # noqa: SLF001
+        except Exception:  # noqa: BLE001, S110 — interpreter shutdown: the pool's module may already be torn down
+            pass
 
 
 class HostResultPool:
